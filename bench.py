@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native path tracer (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--spp S] [--size W]
+
+One "step" = one full render of the workload through the hot path:
+  workload (N=1)  BASELINE.json configs[1]: Cornell box 1024x1024, 1024 spp, max depth 50
+  N>1 (torchrun)  weak scaling: every rank renders its own 1024 samples of every pixel (global sample
+                  indices [rank*1024, (rank+1)*1024)), then ONE NCCL all-reduce (sum) of the W*H float4
+                  radiance sums -- the only exchange step of the path.
+value  = path samples/s over all ranks, device-timed (CUDA events on the launching stream, max over ranks),
+         scene/BVH/camera already resident in HBM.
+e2e    = same metric through the C-ABI with HOST buffers inside the timed region: b2pt_set_scene (H2D of the
+         scene arrays) + b2pt_build_bvh + b2pt_set_camera + b2pt_render + b2pt_read_color (D2H of the W*H*16 B
+         radiance sum into pinned host memory).
+--impl reference  times the reference's CPU structure (oracle PASSES mode: one full-canvas loop per worklet,
+         full depth, no early exit; VTK-m itself cannot be built here) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cornell_1024_path_samples_per_s"
+UNIT = "path samples/s"
+ALGO_BYTES_PER_SEGMENT = 88  # 44 B ray record read + 44 B written per live segment
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b2pt", choices=["b2pt", "reference"])
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--spp", type=int, default=1024)
+    ap.add_argument("--depth", type=int, default=50)
+    ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-image-check", action="store_true")
+    ap.add_argument("--ref-spp", type=int, default=1, help="samples per step of the CPU reference arm")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, or None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+def cpu_reference_step(O, osc, ocam, spp, depth, threads):
+    t0 = time.perf_counter()
+    img, st = O.render(osc, ocam, spp, depth, mode=O.MODE_PASSES, threads=threads)
+    dt = time.perf_counter() - t0
+    return st.paths / dt, dt, st
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation structure on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    osc, ocam = O.cornell_scene(), O.Camera(args.size, args.size)
+    for _ in range(args.warmup):
+        cpu_reference_step(O, osc, ocam, args.ref_spp, args.depth, cores)
+    t0 = time.perf_counter()
+    paths = 0
+    for _ in range(args.steps):
+        _, _, st = cpu_reference_step(O, osc, ocam, args.ref_spp, args.depth, cores)
+        paths += st.paths
+    dt = time.perf_counter() - t0
+    val = paths / dt
+    sample = "%dx%d, depth %d, %d spp per step (cost is exactly linear in spp; full workload is %d spp)" % (
+        args.size, args.size, args.depth, args.ref_spp, args.spp)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Cornell box %dx%d, %d spp, max depth %d (BASELINE.json configs[1])" % (
+            args.size, args.size, args.spp, args.depth),
+            "reference_arm": "CPU restatement (VTK-m-structured): oracle PASSES mode, OpenMP, all host cores; "
+                             "the reference itself needs VTK-m, which is not installable here"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def image_check(img_sum, total_spp, size, depth):
+    """RMSE vs the reference image (BASELINE.json metric, second half): the GPU image box-filtered to 256^2
+    against the oracle's reference-stream render of the same view."""
+    import numpy as np
+    from oracle import oracle as O
+    if size % 256 != 0:
+        return None
+    f = size // 256
+    ospp = 64
+    o, _ = O.render(O.cornell_scene(), O.Camera(256, 256), ospp, depth, mode=O.MODE_FORWARD_BURN)
+    g = np.nan_to_num(img_sum[:, :3] / total_spp).reshape(256, f, 256, f, 3).mean((1, 3))
+    o = np.nan_to_num(o[:, :3] / ospp).reshape(256, 256, 3)
+    blk = lambda x: x.reshape(32, 8, 32, 8, 3).mean((1, 3))
+    rel_rmse = float(np.sqrt(((blk(g) - blk(o)) ** 2).mean()) / blk(o).mean())
+    mean_err = (np.abs(g.mean((0, 1)) - o.mean((0, 1))) / o.mean((0, 1))).tolist()
+    nan_pixels = int(np.isnan(img_sum[:, :3]).any(1).sum())
+    return {"rel_rmse_8x8_blocks_vs_oracle_256x256_64spp": rel_rmse, "per_channel_mean_rel_err": mean_err,
+            "nan_poisoned_pixels": nan_pixels}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import raytracingtherestofyourlife_b200 as B
+    from raytracingtherestofyourlife_b200.sharding import shard_samples
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W = H = args.size
+    N = W * H
+    total_spp = args.spp * world  # weak scaling: per-GPU work fixed
+    begin, count = shard_samples(total_spp, rank, world)
+
+    scene, cam = B.Scene.cornell(), B.Camera(W, H)
+    ctx = B.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    color = torch.zeros((N, 4), dtype=torch.float32, device="cuda")
+    ctx.set_scene(scene)
+    ctx.build_bvh()
+    ctx.set_camera(cam)
+    ctx.set_color_tensor(color)
+
+    def step():
+        ctx.clear_color()
+        ctx.render_range(begin, count, args.depth, args.flags)
+        if world > 1:
+            dist.all_reduce(color, op=dist.ReduceOp.SUM)
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    fence()
+    st = ctx.stats()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    fence()
+    sampler.stop_flag.set()
+    sampler.join()
+    ms = ev0.elapsed_time(ev1)
+    st = ctx.stats()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    seg = torch.tensor([float(st.segments)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(seg, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    segments_per_step = float(seg.item())
+    paths_per_step = float(N) * total_spp
+    value = paths_per_step * args.steps / (ms * 1e-3)
+    img_sum = color.cpu().numpy()
+
+    # ---- e2e through the C-ABI with host buffers (scene upload + render + D2H inside the timed region)
+    host = torch.empty((N, 4), dtype=torch.float32).pin_memory()
+    ctx.set_color_tensor(None)
+
+    def e2e_step():
+        ctx.set_scene(scene)   # H2D: scene arrays -> device tables / BVH
+        ctx.build_bvh()
+        ctx.set_camera(cam)
+        if world > 1:          # the exchange runs on torch-owned memory
+            ctx.set_color_tensor(color)
+        ctx.clear_color()
+        ctx.render_range(begin, count, args.depth, args.flags)
+        if world > 1:
+            dist.all_reduce(color, op=dist.ReduceOp.SUM)
+            host.copy_(color)  # D2H into pinned memory
+        else:
+            ctx.read_color(host.data_ptr())  # D2H into pinned memory (synchronises)
+
+    e2e_step()
+    fence()
+    t0 = time.perf_counter()
+    e_steps = max(1, min(args.steps, 3))
+    for _ in range(e_steps):
+        e2e_step()
+    fence()
+    e_dt = time.perf_counter() - t0
+    et = torch.tensor([e_dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    e2e_value = paths_per_step * e_steps / float(et.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = segments_per_step * args.steps * ALGO_BYTES_PER_SEGMENT / (ms * 1e-3) / 1e9 / world
+        traffic = ncu_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Cornell box %dx%d, %d spp per GPU (%d total), max depth %d "
+                                   "(BASELINE.json configs[1])" % (W, H, args.spp, total_spp, args.depth),
+                       "parallelism": "samples sharded across %d GPU(s), one NCCL all-reduce of %d B" % (world, N * 16),
+                       "l2": "per-step working set (ray queues + radiance, %.1f GB) exceeds the 126 MB L2" % (
+                           st.samplesPerBatch * N * 112 / 1e9),
+                       "flags": args.flags, "segments_per_path": segments_per_step / paths_per_step,
+                       "batches_per_step": st.batches, "samples_per_batch": st.samplesPerBatch},
+            "segments_per_s": segments_per_step * args.steps / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                         "kernel": "k_bounce (all bounce launches of a step)",
+                         "algorithmic_bytes_per_segment": ALGO_BYTES_PER_SEGMENT,
+                         "note": "per GPU; FP32-issue bound in practice, see DESIGN.md and profiles/"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(scene.nbytes()),
+                    "d2h_bytes_per_step": int(N * 16)},
+            "gpu_launches": int(st.launches) * args.steps,
+            "clocks": sampler.summary(),
+        }
+        if not args.no_image_check:
+            try:
+                line["image_check"] = image_check(img_sum, total_spp, W, args.depth)
+            except Exception as e:  # the check must never hide the measurement
+                line["image_check"] = {"error": repr(e)}
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import oracle as O
+            cores = os.cpu_count() or 1
+            val, dt, _ = cpu_reference_step(O, O.cornell_scene(), O.Camera(W, H), 2, args.depth, cores)
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%dx%d, depth %d, 2 of %d spp in %.1f s, oracle PASSES mode "
+                                              "(VTK-m-structured CPU restatement, OpenMP)" % (W, H, args.depth,
+                                                                                             args.spp, dt)}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

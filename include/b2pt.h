@@ -1,0 +1,160 @@
+/*
+ * b2pt.h -- C-ABI of libb2pt.so, the B200-native (sm_100a) replacement for the Monte-Carlo
+ * render path of m-kim/raytracingtherestofyourlife.
+ *
+ * The reference has no FFI: its boundary is the C++ class surface MapperPathTracer / PathTracer /
+ * Camera / ChannelBuffer / Ray.  The C++ facade under
+ * raytracingtherestofyourlife_b200/host/ keeps those signatures and calls ONLY the functions
+ * declared here; each entry point cites the reference code it replaces (paths relative to the
+ * reference root).
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every function returns 0 on success
+ * or a negative b2pt_status; b2pt_last_error() returns the message of the calling thread's last
+ * failure (the facade converts it to vtkm::cont::ErrorBadValue, as MapperPathTracer.cxx:162 and
+ * pathtracing/Camera.cxx:645,667,700,720-724 throw).  The caller owns all host pointers; the
+ * library owns all device memory unless an external buffer is attached.  One context per GPU;
+ * calls on one context must be serialised by the caller; different contexts are independent
+ * (each has its own CUDA stream), so G contexts can be driven from one host thread.
+ * There is NO CPU fallback: every entry point that computes fails with B2PT_ERR_CUDA when no
+ * sm_100-class device is usable.
+ */
+#ifndef B2PT_H
+#define B2PT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2pt_ctx b2pt_ctx;
+
+typedef enum b2pt_status
+{
+  B2PT_OK = 0,
+  B2PT_ERR_BAD_VALUE = -1, /* vtkm::cont::ErrorBadValue in the reference */
+  B2PT_ERR_CUDA = -2,      /* CUDA runtime failure or no usable device */
+  B2PT_ERR_STATE = -3,     /* call order violated (e.g. render before set_scene) */
+  B2PT_ERR_ALLOC = -4,
+  B2PT_ERR_UNSUPPORTED = -5
+} b2pt_status;
+
+/* b2pt_render flags */
+#define B2PT_FLAG_REFERENCE_STREAM 0x1u /* per-pixel persistent RNG stream; dead paths burn the draws the reference \
+                                           still consumes so every trajectory equals the reference's. \
+                                           One sample per pass; for parity runs, not for speed. */
+#define B2PT_FLAG_KILL_ZERO_THROUGHPUT 0x2u /* stop paths whose throughput is exactly (0,0,0); not valid together   \
+                                               with B2PT_FLAG_REFERENCE_STREAM */
+#define B2PT_FLAG_NO_DEDUP 0x4u             /* keep bit-identical duplicate quads in the trace list */
+#define B2PT_FLAG_FORCE_BVH 0x8u            /* use the BVH traversal kernels even for small scenes */
+
+typedef struct b2pt_stats
+{
+  int64_t paths;      /* path samples rendered by the last b2pt_render* call */
+  int64_t segments;   /* live ray segments traced */
+  int64_t nanSamples; /* path samples with a NaN radiance channel */
+  int64_t launches;   /* kernels launched by the call */
+  int64_t queueBytes; /* bytes read+written on the SoA ray queues */
+  double renderMs;    /* CUDA-event time of the call on the context's stream */
+  int32_t batches;    /* sample batches */
+  int32_t samplesPerBatch;
+  int32_t tracePath;  /* 0 = small-scene (kernel-parameter resident) trace, 1 = BVH traversal */
+  int32_t bvhNodes;
+  int32_t tracedQuads; /* quads in the trace list after dedup */
+  int32_t tracedSpheres;
+} b2pt_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* Replaces MapperPathTracer::InternalsType (MapperPathTracer.cxx:79-92) + VTK-m device selection
+ * (DeviceAdapterTagAny, MapperPathTracer.cxx:220). */
+b2pt_ctx* b2pt_create(int device, int* err);
+void b2pt_destroy(b2pt_ctx* ctx);
+const char* b2pt_last_error(void);
+/* Run the context's work on an existing CUDA stream (cudaStream_t as void*); NULL restores its own. */
+int b2pt_set_stream(b2pt_ctx* ctx, void* cudaStream);
+
+/* ---- scene --------------------------------------------------------------------------------- */
+/* Replaces MapperPathTracer::extract (MapperPathTracer.cxx:178-197), the per-primitive material
+ * lookups (Surface.h:191-192, 391-392; EmitWorklet.h:60-64) and the hard-coded light lists
+ * (MapperPathTracer.cxx:141-148).  quadIds = Vec<Id,5>(cell,p0..p3); spherePt = point id per sphere.
+ * lightQuadIds / lightSpherePt / lightSphereR as used by QuadGenerateDir.h / SphereGenerateDir.h. */
+int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t* quadIds, int64_t nQuads,
+                   const int64_t* spherePt, const float* sphereR, int64_t nSpheres, const int64_t* matIdxQuad,
+                   const int64_t* texIdxQuad, const int64_t* matIdxSph, const int64_t* texIdxSph, const int* matType,
+                   int nMatType, const int* texType, int nTexType, const float* tex, int nTex,
+                   const int64_t* lightQuadIds, int nLightQuads, const int64_t* lightSpherePt,
+                   const float* lightSphereR, int nLightSpheres, int lightables, float refIdx);
+/* Replaces MapperPathTracer::buildBVH (MapperPathTracer.cxx:437-449): QuadIntersector::SetData
+ * (pathtracing/QuadIntersector.cxx:109-135), SphereIntersector::SetData
+ * (pathtracing/SphereIntersector.cxx:46-76), FindQuadAABBs / FindSphereAABBs (pathtracing/AABBSurface.h) and
+ * VTK-m's LinearBVH::Construct.  One tree over quads and spheres; small scenes skip the tree. */
+int b2pt_build_bvh(b2pt_ctx* ctx);
+
+/* ---- camera -------------------------------------------------------------------------------- */
+/* Replaces pathtracing::Camera::SetParameters / CreateRaysImpl set-up (pathtracing/Camera.cxx:625-637,
+ * 880-960) and the RayGen constructor (:438-476).  fovDeg in (0,180]; W,H > 0 else B2PT_ERR_BAD_VALUE. */
+int b2pt_set_camera(b2pt_ctx* ctx, const float pos[3], const float lookAt[3], const float up[3], float fovDeg, int W,
+                    int H);
+/* seeds[i] = i + seedOffset (0 = the reference, MapperPathTracer.cxx:265-267). */
+int b2pt_seed(b2pt_ctx* ctx, uint32_t seedOffset);
+
+/* ---- render -------------------------------------------------------------------------------- */
+/* Replaces MapperPathTracer::RenderCellsImpl's sample x depth loop (MapperPathTracer.cxx:278-350):
+ * clears the radiance sum (:222-223) and accumulates spp samples of depth maxDepth into it. */
+int b2pt_render(b2pt_ctx* ctx, int spp, int maxDepth, uint32_t flags);
+/* Same without clearing, rendering global sample indices [sampleBegin, sampleBegin+sampleCount):
+ * the multi-GPU sharding primitive (each rank renders a disjoint sample range of every pixel). */
+int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDepth, uint32_t flags);
+int b2pt_clear_color(b2pt_ctx* ctx);
+/* Attach a caller-owned device buffer of W*H float4 as the radiance sum (NULL detaches). */
+int b2pt_set_color_buffer(b2pt_ctx* ctx, void* deviceFloat4);
+void* b2pt_color_device_ptr(b2pt_ctx* ctx);
+/* Device->host copy of the un-normalised radiance sum, canvas.GetColorBuffer() layout
+ * (Vec<Float32,4>[W*H], index j*W+i, j=0 bottom row; alpha lane 0). Synchronises the stream. */
+int b2pt_read_color(b2pt_ctx* ctx, float* rgba);
+int b2pt_write_color(b2pt_ctx* ctx, const float* rgba);
+/* Replaces NormalizeFunctor (main.cc:253-287): in-place sqrt(de_nan(sum)/spp) on the device buffer. */
+int b2pt_normalize(b2pt_ctx* ctx, int spp);
+int b2pt_synchronize(b2pt_ctx* ctx);
+int b2pt_get_stats(b2pt_ctx* ctx, b2pt_stats* out);
+
+/* ---- parity hooks and stage-level entry points --------------------------------------------- */
+/* Sample-0 primary rays with seeds[i] = i + seedOffset through the production raygen + trace device
+ * code: hit primitive id per pixel (quad q -> q, sphere s -> nQuads+s, miss -> -1) and hit t.
+ * Either output may be NULL. */
+int b2pt_primary_hits(b2pt_ctx* ctx, int32_t* primId, float* t);
+/* Replaces pathtracing::Camera::CreateRays (pathtracing/Camera.cxx:880-960): one jittered primary ray
+ * per pixel from the current per-pixel seeds; host outputs, any may be NULL. seedsInOut (W*H) is
+ * read as the RNG state and updated (2 draws per pixel). */
+int b2pt_create_rays(b2pt_ctx* ctx, uint32_t* seedsInOut, float* dirX, float* dirY, float* dirZ, float* originX,
+                     float* originY, float* originZ, int64_t* pixelIdx);
+/* Replaces MapperPathTracer::intersect (MapperPathTracer.cxx:410-435) for host ray arrays:
+ * closest hit in (tmin, tmax) per ray; hrec is 9 planar arrays [U,V,T,Nx,Ny,Nz,Px,Py,Pz] (n each),
+ * primId/matId/texId n each. */
+int b2pt_intersect(b2pt_ctx* ctx, int64_t n, const float* ox, const float* oy, const float* oz, const float* dx,
+                   const float* dy, const float* dz, float tmin, float tmax, int32_t* primId, float* hrec9,
+                   int32_t* matId, int32_t* texId);
+
+/* ---- multi-GPU (single process, G contexts) ------------------------------------------------ */
+/* Sum the radiance buffers of G contexts (one per GPU) into every context's buffer: the exchange
+ * step of the sample-sharded render.  Uses peer access over NVLink. */
+int b2pt_allreduce(b2pt_ctx* const* ctxs, int G);
+
+/* ---- host-side scene builders (restated inputs, not kernels) -------------------------------- */
+/* CornellBox::buildDataSet (CornellBox.cpp:141-418): 89 points, 22 quads, 1 sphere. */
+int b2pt_scene_cornell(float* pts /*3*89*/, int64_t* quadIds /*5*22*/, int64_t* spherePt /*1*/, float* sphereR /*1*/,
+                       int64_t* matIdxQuad /*22*/, int64_t* texIdxQuad /*22*/, int64_t* matIdxSph /*1*/,
+                       int64_t* texIdxSph /*1*/, int* matType /*5*/, int* texType /*5*/, float* tex /*3*4*/);
+/* BASELINE.json configs[3]: nSpheres random lambertian spheres + emissive quad + floor.
+ * pts: 3*(nSpheres+8); quadIds: 5*2; spherePt/sphereR/matIdxSph/texIdxSph: nSpheres; mat/tex idx quad: 2;
+ * matType/texType: 5; tex: 3*4. */
+int b2pt_scene_spheres(int64_t nSpheres, float* pts, int64_t* quadIds, int64_t* spherePt, float* sphereR,
+                       int64_t* matIdxQuad, int64_t* texIdxQuad, int64_t* matIdxSph, int64_t* texIdxSph, int* matType,
+                       int* texType, float* tex);
+
+int b2pt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,997 @@
+// b2pt_api.cu -- the C-ABI of libb2pt.so (include/b2pt.h): contexts, scene/camera set-up, BVH build,
+// the wavefront render loop and the stage-level entry points.  Host code only; kernels live in
+// b2pt_kernels.cu.  There is no CPU fallback anywhere in this file: without a usable CUDA device every
+// computing entry point returns B2PT_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/b2pt.h"
+#include "b2pt_bvh.h"
+#include "b2pt_kernels.h"
+#include "b2pt_types.h"
+
+namespace
+{
+
+thread_local std::string g_lastError;
+
+int fail(int code, const char* fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_lastError = buf;
+  return code;
+}
+
+#define CU(call)                                                                                                       \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t e__ = (call);                                                                                          \
+    if (e__ != cudaSuccess)                                                                                            \
+      return fail(B2PT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);         \
+  } while (0)
+
+template <class T>
+struct DevBuf
+{
+  T* p = nullptr;
+  size_t cap = 0; // elements
+  cudaError_t reserve(size_t n)
+  {
+    if (n <= cap)
+      return cudaSuccess;
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e == cudaSuccess)
+      cap = n;
+    return e;
+  }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// host float helpers: same operation order as the reference's vtkm::Vec math (no FMA contraction)
+struct H3
+{
+  float x, y, z;
+};
+inline H3 hsub(H3 a, H3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+inline float hdot(H3 a, H3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline H3 hcross(H3 a, H3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+inline H3 hscale(H3 a, float s) { return { a.x * s, a.y * s, a.z * s }; }
+inline H3 hnormalize(H3 a) { return hscale(a, 1.0f / std::sqrt(hdot(a, a))); }
+inline void hst(float* d, H3 a)
+{
+  d[0] = a.x;
+  d[1] = a.y;
+  d[2] = a.z;
+}
+
+} // namespace
+
+struct b2pt_ctx
+{
+  int device = 0;
+  cudaStream_t ownStream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t evStart = nullptr, evStop = nullptr;
+  b2pt::LaunchCfg cfg{};
+
+  // scene (host)
+  bool haveScene = false, haveBvh = false, haveCamera = false;
+  int64_t nQuads = 0, nSph = 0;
+  std::vector<B2Quad> quads; // by original index
+  std::vector<B2Sphere> sph;
+  std::vector<B2GateBox> gates; // leaf boxes of non-planar quads (B2Quad::gate indexes this, 1-based)
+  B2Lights lights{};
+  // trace structures
+  bool useBvh = false;
+  B2SmallScene small{};
+  B2BvhScene bvh{};
+  DevBuf<B2BvhNode> dNodes;
+  DevBuf<int32_t> dSlots;
+  DevBuf<B2Quad> dQuads;
+  DevBuf<B2Sphere> dSph;
+  DevBuf<B2GateBox> dGates;
+  int32_t tracedQuads = 0, tracedSph = 0, bvhNodes = 0;
+  uint32_t builtFlags = 0;
+
+  // camera
+  B2Camera cam{};
+  uint32_t seedOffset = 0;
+
+  // buffers
+  DevBuf<float4> colorOwn;
+  float4* colorExt = nullptr;
+  int64_t colorPixels = 0;
+  DevBuf<uint4> queue[2][3];
+  DevBuf<float4> rad;
+  DevBuf<uint32_t> counters;
+  DevBuf<uint32_t> seeds;
+  DevBuf<unsigned long long> nanCounter;
+  std::vector<uint32_t> hCounters;
+
+  b2pt_stats stats{};
+  bool statsPending = false;
+  int64_t pendingCounters = 0;
+  int pendingMaxDepth = 0;
+  int64_t pendingPathsPerBatch = 0;
+
+  float4* color() { return colorExt ? colorExt : colorOwn.p; }
+};
+
+namespace
+{
+
+int bind(b2pt_ctx* ctx)
+{
+  if (!ctx)
+    return fail(B2PT_ERR_BAD_VALUE, "null context");
+  CU(cudaSetDevice(ctx->device));
+  return B2PT_OK;
+}
+
+int ensure_color(b2pt_ctx* ctx)
+{
+  const int64_t n = (int64_t)ctx->cam.W * ctx->cam.H;
+  if (ctx->colorExt)
+    return B2PT_OK;
+  if (ctx->colorPixels != n || !ctx->colorOwn.p)
+  {
+    CU(ctx->colorOwn.reserve((size_t)n));
+    ctx->colorPixels = n;
+    CU(cudaMemsetAsync(ctx->colorOwn.p, 0, sizeof(float4) * (size_t)n, ctx->stream));
+  }
+  return B2PT_OK;
+}
+
+// Ray-independent parts of Surface.h:30-104 and :180-181 for one quad (q,r,s,t = v00,v10,v11,v01).
+void precompute_quad(B2Quad& Q, H3 q, H3 r, H3 s, H3 t)
+{
+  hst(Q.v00, q);
+  hst(Q.e01, hsub(r, q));
+  hst(Q.e03, hsub(t, q));
+  hst(Q.v11, s);
+  hst(Q.e21, hsub(r, s));
+  hst(Q.e23, hsub(t, s));
+  hst(Q.nrm, hnormalize(hcross(hsub(r, q), hsub(s, q)))); // vtkm::TriangleNormal(q,r,s), Normalize
+}
+
+// pathtracing/AABBSurface.h:24-78 (FindQuadAABBs): min/max over the four vertices, padded per axis.
+void quad_leaf_box(B2GateBox& G, H3 q, H3 r, H3 s, H3 t)
+{
+  const float v[4][3] = { { q.x, q.y, q.z }, { r.x, r.y, r.z }, { s.x, s.y, s.z }, { t.x, t.y, t.z } };
+  for (int c = 0; c < 3; ++c)
+  {
+    float lo = v[0][c], hi = v[0][c];
+    for (int k = 1; k < 4; ++k)
+    {
+      lo = std::fmin(lo, v[k][c]);
+      hi = std::fmax(hi, v[k][c]);
+    }
+    const float eps = std::fmax(1e-6f, 1.0e-4f * (hi - lo));
+    G.bmin[c] = lo - eps;
+    G.bmax[c] = hi + eps;
+  }
+  G.pad[0] = G.pad[1] = 0.f;
+}
+
+// A quad needs the leaf-box gate unless it is planar: for planar quads every hit the Lagae-Dutre test accepts
+// lies on the quad, hence inside its padded box, and the gate is a no-op.
+bool quad_is_planar(H3 q, H3 r, H3 s, H3 t, const float* unitNormal)
+{
+  const H3 n = { unitNormal[0], unitNormal[1], unitNormal[2] };
+  const H3 e[3] = { hsub(r, q), hsub(s, q), hsub(t, q) };
+  float scale = 0.f;
+  for (const H3& v : e)
+    scale = std::fmax(scale, std::sqrt(hdot(v, v)));
+  const float dev = std::fmax(std::fabs(hdot(n, e[1])), std::fabs(hdot(n, e[2])));
+  return dev <= 1e-5f * scale;
+}
+
+bool same_vertices(const B2Quad& a, const B2Quad& b)
+{
+  return std::memcmp(a.v00, b.v00, 12) == 0 && std::memcmp(a.e01, b.e01, 12) == 0 &&
+    std::memcmp(a.e03, b.e03, 12) == 0 && std::memcmp(a.v11, b.v11, 12) == 0 && std::memcmp(a.e21, b.e21, 12) == 0 &&
+    std::memcmp(a.e23, b.e23, 12) == 0;
+}
+
+} // namespace
+
+extern "C"
+{
+
+int b2pt_version(void) { return 100; }
+
+const char* b2pt_last_error(void) { return g_lastError.c_str(); }
+
+b2pt_ctx* b2pt_create(int device, int* err)
+{
+  auto bail = [&](int code) -> b2pt_ctx* {
+    if (err)
+      *err = code;
+    return nullptr;
+  };
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+  {
+    fail(B2PT_ERR_CUDA, "no CUDA device available (%s); libb2pt has no CPU fallback",
+         e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return bail(B2PT_ERR_CUDA);
+  }
+  if (device < 0 || device >= count)
+  {
+    fail(B2PT_ERR_BAD_VALUE, "device %d out of range [0,%d)", device, count);
+    return bail(B2PT_ERR_BAD_VALUE);
+  }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+  {
+    fail(B2PT_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return bail(B2PT_ERR_CUDA);
+  }
+  if (prop.major != 10)
+  {
+    fail(B2PT_ERR_CUDA, "device %d is sm_%d%d; libb2pt ships sm_100a code only", device, prop.major, prop.minor);
+    return bail(B2PT_ERR_CUDA);
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess)
+  {
+    fail(B2PT_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    return bail(B2PT_ERR_CUDA);
+  }
+  b2pt_ctx* ctx = new b2pt_ctx();
+  ctx->device = device;
+  if ((e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->evStart)) != cudaSuccess || (e = cudaEventCreate(&ctx->evStop)) != cudaSuccess ||
+      (e = b2pt::query_launch_cfg(&ctx->cfg)) != cudaSuccess)
+  {
+    fail(B2PT_ERR_CUDA, "context set-up failed: %s", cudaGetErrorString(e));
+    delete ctx;
+    return bail(B2PT_ERR_CUDA);
+  }
+  ctx->stream = ctx->ownStream;
+  if (err)
+    *err = B2PT_OK;
+  return ctx;
+}
+
+void b2pt_destroy(b2pt_ctx* ctx)
+{
+  if (!ctx)
+    return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->dNodes.release(), ctx->dSlots.release(), ctx->dQuads.release(), ctx->dSph.release(), ctx->dGates.release();
+  ctx->colorOwn.release();
+  for (auto& q : ctx->queue)
+    for (auto& p : q)
+      p.release();
+  ctx->rad.release(), ctx->counters.release(), ctx->seeds.release(), ctx->nanCounter.release();
+  if (ctx->evStart)
+    cudaEventDestroy(ctx->evStart);
+  if (ctx->evStop)
+    cudaEventDestroy(ctx->evStop);
+  if (ctx->ownStream)
+    cudaStreamDestroy(ctx->ownStream);
+  delete ctx;
+}
+
+int b2pt_set_stream(b2pt_ctx* ctx, void* cudaStream)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cudaStream ? static_cast<cudaStream_t>(cudaStream) : ctx->ownStream;
+  return B2PT_OK;
+}
+
+int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t* quadIds, int64_t nQuads,
+                   const int64_t* spherePt, const float* sphereR, int64_t nSpheres, const int64_t* matIdxQuad,
+                   const int64_t* texIdxQuad, const int64_t* matIdxSph, const int64_t* texIdxSph, const int* matType,
+                   int nMatType, const int* texType, int nTexType, const float* tex, int nTex,
+                   const int64_t* lightQuadIds, int nLightQuads, const int64_t* lightSpherePt,
+                   const float* lightSphereR, int nLightSpheres, int lightables, float refIdx)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (!pts || nPts <= 0 || nQuads < 0 || nSpheres < 0 || (nQuads + nSpheres) == 0)
+    return fail(B2PT_ERR_BAD_VALUE, "scene needs points and at least one primitive");
+  if ((nQuads && (!quadIds || !matIdxQuad || !texIdxQuad)) ||
+      (nSpheres && (!spherePt || !sphereR || !matIdxSph || !texIdxSph)))
+    return fail(B2PT_ERR_BAD_VALUE, "null primitive array");
+  if (!matType || !texType || !tex || nMatType <= 0 || nTexType <= 0 || nTex <= 0)
+    return fail(B2PT_ERR_BAD_VALUE, "null or empty material tables");
+  if (nLightQuads < 0 || nLightQuads > B2PT_MAX_LIGHT_QUADS || nLightSpheres < 0 ||
+      nLightSpheres > B2PT_MAX_LIGHT_SPH)
+    return fail(B2PT_ERR_BAD_VALUE, "at most %d light quads and %d light spheres are supported",
+                B2PT_MAX_LIGHT_QUADS, B2PT_MAX_LIGHT_SPH);
+  if ((nLightQuads && !lightQuadIds) || (nLightSpheres && (!lightSpherePt || !lightSphereR)))
+    return fail(B2PT_ERR_BAD_VALUE, "null light array");
+  if (lightables <= 0)
+    return fail(B2PT_ERR_BAD_VALUE, "lightables must be positive");
+  if (nQuads + nSpheres > 0x7fffff00LL)
+    return fail(B2PT_ERR_BAD_VALUE, "too many primitives");
+
+  auto P = [&](int64_t i) -> H3 { return { pts[3 * i], pts[3 * i + 1], pts[3 * i + 2] }; };
+  auto material = [&](int64_t m, int64_t t, int32_t& kind, float* alb) -> bool {
+    if (m < 0 || m >= nMatType || t < 0 || t >= nTexType)
+      return false;
+    const int tt = texType[t];
+    if (tt < 0 || tt >= nTex)
+      return false;
+    kind = matType[m];
+    alb[0] = tex[3 * tt], alb[1] = tex[3 * tt + 1], alb[2] = tex[3 * tt + 2];
+    return true;
+  };
+
+  std::vector<B2Quad> quads((size_t)nQuads);
+  std::vector<B2GateBox> gates;
+  for (int64_t q = 0; q < nQuads; ++q)
+  {
+    const int64_t* id = quadIds + 5 * q;
+    for (int k = 1; k <= 4; ++k)
+      if (id[k] < 0 || id[k] >= nPts)
+        return fail(B2PT_ERR_BAD_VALUE, "quad %lld references point %lld outside [0,%lld)", (long long)q,
+                    (long long)id[k], (long long)nPts);
+    B2Quad& Q = quads[(size_t)q];
+    precompute_quad(Q, P(id[1]), P(id[2]), P(id[3]), P(id[4]));
+    Q.gate = 0;
+    Q.pad[0] = Q.pad[1] = Q.pad[2] = 0;
+    if (!quad_is_planar(P(id[1]), P(id[2]), P(id[3]), P(id[4]), Q.nrm))
+    {
+      B2GateBox G;
+      quad_leaf_box(G, P(id[1]), P(id[2]), P(id[3]), P(id[4]));
+      gates.push_back(G);
+      Q.gate = (int32_t)gates.size();
+    }
+    if (!material(matIdxQuad[q], texIdxQuad[q], Q.kind, Q.alb))
+      return fail(B2PT_ERR_BAD_VALUE, "quad %lld has material/texture index out of range", (long long)q);
+    Q.prim = (int32_t)q;
+    Q.mat = (int32_t)matIdxQuad[q];
+    Q.texi = (int32_t)texIdxQuad[q];
+  }
+  std::vector<B2Sphere> sph((size_t)nSpheres);
+  for (int64_t s = 0; s < nSpheres; ++s)
+  {
+    if (spherePt[s] < 0 || spherePt[s] >= nPts)
+      return fail(B2PT_ERR_BAD_VALUE, "sphere %lld references a point out of range", (long long)s);
+    B2Sphere& S = sph[(size_t)s];
+    hst(S.c, P(spherePt[s]));
+    S.r = sphereR[s];
+    if (!material(matIdxSph[s], texIdxSph[s], S.kind, S.alb))
+      return fail(B2PT_ERR_BAD_VALUE, "sphere %lld has material/texture index out of range", (long long)s);
+    S.prim = (int32_t)(nQuads + s);
+    S.mat = (int32_t)matIdxSph[s];
+    S.texi = (int32_t)texIdxSph[s];
+    S.pad = 0;
+  }
+  B2Lights L{};
+  L.nLightQuads = nLightQuads;
+  L.nLightSph = nLightSpheres;
+  L.weight = (float)(1.0 / (double)(float)lightables); // PdfWorklet.h:294: float weight = 1.0/list_size
+  L.refIdx = refIdx;
+  for (int l = 0; l < nLightQuads; ++l)
+  {
+    const int64_t* id = lightQuadIds + 5 * l;
+    for (int k = 1; k <= 4; ++k)
+      if (id[k] < 0 || id[k] >= nPts)
+        return fail(B2PT_ERR_BAD_VALUE, "light quad %d references a point out of range", l);
+    B2LightQuad& LQ = L.lq[l];
+    std::memset(&LQ, 0, sizeof(LQ));
+    H3 q = P(id[1]), r = P(id[2]), s = P(id[3]), t = P(id[4]);
+    precompute_quad(LQ.geo, q, r, s, t);
+    LQ.geo.prim = -1;
+    LQ.geo.gate = 0; // QuadPDFWorklet calls the leaf intersector directly, no BVH (PdfWorklet.h:238)
+    H3 rq = hsub(r, q), tq = hsub(t, q);
+    LQ.area = std::sqrt(hdot(rq, rq)) * std::sqrt(hdot(tq, tq)); // PdfWorklet.h:236-239
+    hst(LQ.pt1, q);                                              // PdfWorklet.h:124-125
+    hst(LQ.pt2, s);
+  }
+  for (int l = 0; l < nLightSpheres; ++l)
+  {
+    if (lightSpherePt[l] < 0 || lightSpherePt[l] >= nPts)
+      return fail(B2PT_ERR_BAD_VALUE, "light sphere %d references a point out of range", l);
+    hst(L.ls[l].c, P(lightSpherePt[l]));
+    L.ls[l].r = lightSphereR[l];
+  }
+  ctx->quads.swap(quads);
+  ctx->sph.swap(sph);
+  ctx->gates.swap(gates);
+  ctx->lights = L;
+  ctx->nQuads = nQuads;
+  ctx->nSph = nSpheres;
+  ctx->haveScene = true;
+  ctx->haveBvh = false;
+  return B2PT_OK;
+}
+
+static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
+{
+  ctx->builtFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP);
+  // Drop bit-identical duplicate quads: a later copy computes the same t and loses the strict t<tmax
+  // comparison (Surface.h:178-179), so removing it cannot change any result.
+  std::vector<int32_t> keptQuads;
+  for (int64_t q = 0; q < ctx->nQuads; ++q)
+  {
+    bool dup = false;
+    if (!(flags & B2PT_FLAG_NO_DEDUP) && ctx->nQuads <= 4096)
+      for (int32_t k : keptQuads)
+        if (same_vertices(ctx->quads[(size_t)k], ctx->quads[(size_t)q]))
+        {
+          dup = true;
+          break;
+        }
+    if (!dup)
+      keptQuads.push_back((int32_t)q);
+  }
+  ctx->tracedQuads = (int32_t)keptQuads.size();
+  ctx->tracedSph = (int32_t)ctx->nSph;
+  const bool fitsSmall = keptQuads.size() <= B2PT_SMALL_MAX_QUADS && ctx->nSph <= B2PT_SMALL_MAX_SPH &&
+    ctx->gates.size() <= B2PT_SMALL_MAX_GATES;
+  ctx->useBvh = !fitsSmall || (flags & B2PT_FLAG_FORCE_BVH);
+  ctx->bvhNodes = 0;
+  if (!ctx->useBvh)
+  {
+    std::memset(&ctx->small, 0, sizeof(ctx->small));
+    ctx->small.nQuads = (int32_t)keptQuads.size();
+    ctx->small.nSph = (int32_t)ctx->nSph;
+    ctx->small.nGate = (int32_t)ctx->gates.size();
+    for (size_t g = 0; g < ctx->gates.size(); ++g)
+      ctx->small.gate[g] = ctx->gates[g];
+    for (size_t k = 0; k < keptQuads.size(); ++k)
+      ctx->small.quads[k] = ctx->quads[(size_t)keptQuads[k]];
+    for (int64_t s = 0; s < ctx->nSph; ++s)
+      ctx->small.sph[s] = ctx->sph[(size_t)s];
+    return B2PT_OK;
+  }
+  std::vector<B2BvhNode> nodes;
+  std::vector<int32_t> slots;
+  if (!b2pt::build_bvh(ctx->quads, keptQuads, ctx->sph, nodes, slots))
+    return fail(B2PT_ERR_UNSUPPORTED, "scene too large for the 24-bit BVH index packing");
+  CU(ctx->dNodes.reserve(nodes.size()));
+  CU(ctx->dSlots.reserve(slots.size()));
+  CU(ctx->dQuads.reserve(std::max<size_t>(ctx->quads.size(), 1)));
+  CU(ctx->dSph.reserve(std::max<size_t>(ctx->sph.size(), 1)));
+  CU(ctx->dGates.reserve(std::max<size_t>(ctx->gates.size(), 1)));
+  if (!ctx->gates.empty())
+    CU(cudaMemcpyAsync(ctx->dGates.p, ctx->gates.data(), ctx->gates.size() * sizeof(B2GateBox),
+                       cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->dNodes.p, nodes.data(), nodes.size() * sizeof(B2BvhNode), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CU(cudaMemcpyAsync(ctx->dSlots.p, slots.data(), slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  if (!ctx->quads.empty())
+    CU(cudaMemcpyAsync(ctx->dQuads.p, ctx->quads.data(), ctx->quads.size() * sizeof(B2Quad), cudaMemcpyHostToDevice,
+                       ctx->stream));
+  if (!ctx->sph.empty())
+    CU(cudaMemcpyAsync(ctx->dSph.p, ctx->sph.data(), ctx->sph.size() * sizeof(B2Sphere), cudaMemcpyHostToDevice,
+                       ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream)); // host vectors go out of scope
+  ctx->bvh.nodes = ctx->dNodes.p;
+  ctx->bvh.primSlots = ctx->dSlots.p;
+  ctx->bvh.quads = ctx->dQuads.p;
+  ctx->bvh.sph = ctx->dSph.p;
+  ctx->bvh.gate = ctx->dGates.p;
+  ctx->bvh.nGate = (int32_t)ctx->gates.size();
+  ctx->bvh.nNodes = (int32_t)nodes.size();
+  ctx->bvh.nQuads = (int32_t)ctx->quads.size();
+  ctx->bvh.nSph = (int32_t)ctx->sph.size();
+  ctx->bvhNodes = (int32_t)nodes.size();
+  return B2PT_OK;
+}
+
+int b2pt_build_bvh(b2pt_ctx* ctx)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (!ctx->haveScene)
+    return fail(B2PT_ERR_STATE, "b2pt_build_bvh before b2pt_set_scene");
+  if (int rc = build_trace_structures(ctx, 0))
+    return rc;
+  ctx->haveBvh = true;
+  return B2PT_OK;
+}
+
+int b2pt_set_camera(b2pt_ctx* ctx, const float pos[3], const float lookAt[3], const float up[3], float fovDeg, int W,
+                    int H)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (!pos || !lookAt || !up)
+    return fail(B2PT_ERR_BAD_VALUE, "null camera vector");
+  if (H <= 0)
+    return fail(B2PT_ERR_BAD_VALUE, "Camera height must be greater than zero."); // Camera.cxx:645
+  if (W <= 0)
+    return fail(B2PT_ERR_BAD_VALUE, "Camera width must be greater than zero."); // Camera.cxx:667
+  if (!(fovDeg > 0))
+    return fail(B2PT_ERR_BAD_VALUE, "Camera feild of view must be greater than zero."); // Camera.cxx:720
+  if (fovDeg > 180)
+    return fail(B2PT_ERR_BAD_VALUE, "Camera feild of view must be less than 180."); // Camera.cxx:724
+  if ((int64_t)W * H > (int64_t)1 << 26)
+    return fail(B2PT_ERR_BAD_VALUE, "canvas larger than 2^26 pixels");
+  // Camera.cxx:913-914 Look; :803-811 SetUp; RayGen ctor :438-476 with fovX = fovY (:936-938), zoom off
+  H3 look = hnormalize(hsub({ lookAt[0], lookAt[1], lookAt[2] }, { pos[0], pos[1], pos[2] }));
+  H3 upv = { up[0], up[1], up[2] };
+  if (!(upv.x == 0.f && upv.y == 1.f && upv.z == 0.f))
+    upv = hnormalize(upv);
+  const float pi180 = 0.01745329251994329547f;
+  const float thx = std::tan((fovDeg * pi180) * .5f);
+  const float thy = std::tan((fovDeg * pi180) * .5f);
+  H3 u = hnormalize(hcross(look, upv));
+  H3 v = hnormalize(hcross(u, look));
+  B2Camera c{};
+  hst(c.dx, hscale(u, 2 * thx / (float)W));
+  hst(c.dy, hscale(v, 2 * thy / (float)H));
+  hst(c.nlook, hnormalize(look));
+  c.pos[0] = pos[0], c.pos[1] = pos[1], c.pos[2] = pos[2];
+  c.W = W;
+  c.H = H;
+  const bool resized = (W != ctx->cam.W || H != ctx->cam.H);
+  ctx->cam = c;
+  ctx->haveCamera = true;
+  if (resized && !ctx->colorExt)
+    ctx->colorPixels = 0; // force re-allocation + clear
+  return B2PT_OK;
+}
+
+int b2pt_seed(b2pt_ctx* ctx, uint32_t seedOffset)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  ctx->seedOffset = seedOffset;
+  return B2PT_OK;
+}
+
+int b2pt_set_color_buffer(b2pt_ctx* ctx, void* deviceFloat4)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->colorExt = static_cast<float4*>(deviceFloat4);
+  return B2PT_OK;
+}
+
+void* b2pt_color_device_ptr(b2pt_ctx* ctx)
+{
+  if (bind(ctx) != B2PT_OK || !ctx->haveCamera)
+    return nullptr;
+  if (ensure_color(ctx) != B2PT_OK)
+    return nullptr;
+  return ctx->color();
+}
+
+int b2pt_clear_color(b2pt_ctx* ctx)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (!ctx->haveCamera)
+    return fail(B2PT_ERR_STATE, "b2pt_clear_color before b2pt_set_camera");
+  if (int rc = ensure_color(ctx))
+    return rc;
+  CU(cudaMemsetAsync(ctx->color(), 0, sizeof(float4) * (size_t)ctx->cam.W * ctx->cam.H, ctx->stream));
+  return B2PT_OK;
+}
+
+static int64_t batch_target_paths()
+{
+  const char* e = getenv("B2PT_BATCH_PATHS");
+  if (e)
+  {
+    long long v = atoll(e);
+    if (v > 0)
+      return v;
+  }
+  return (int64_t)1 << 25; // 32 Mi paths in flight: 2 queues x 48 B + 16 B radiance = 3.6 GB of the 180 GB HBM
+}
+
+int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDepth, uint32_t flags)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (!ctx->haveScene)
+    return fail(B2PT_ERR_STATE, "render before b2pt_set_scene");
+  if (!ctx->haveCamera)
+    return fail(B2PT_ERR_STATE, "render before b2pt_set_camera");
+  if (sampleCount < 0 || sampleBegin < 0)
+    return fail(B2PT_ERR_BAD_VALUE, "negative sample range");
+  if (maxDepth < 1 || maxDepth > 4096)
+    return fail(B2PT_ERR_BAD_VALUE, "maxDepth must be in [1,4096]");
+  const bool refStream = (flags & B2PT_FLAG_REFERENCE_STREAM) != 0;
+  if (refStream && (flags & B2PT_FLAG_KILL_ZERO_THROUGHPUT))
+    return fail(B2PT_ERR_BAD_VALUE, "KILL_ZERO_THROUGHPUT cannot be combined with REFERENCE_STREAM");
+  if (refStream && sampleBegin != 0)
+    return fail(B2PT_ERR_BAD_VALUE, "REFERENCE_STREAM renders samples from 0 (one persistent stream per pixel)");
+  // MapperPathTracer::RenderCellsImpl builds its acceleration structures on every call (:275-276); here
+  // they are rebuilt only when the scene or the build-affecting flags changed.
+  const uint32_t buildFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP);
+  if (!ctx->haveBvh || ctx->builtFlags != buildFlags)
+  {
+    if (int rc = build_trace_structures(ctx, buildFlags))
+      return rc;
+    ctx->haveBvh = true;
+  }
+  if (int rc = ensure_color(ctx))
+    return rc;
+
+  const int64_t N = (int64_t)ctx->cam.W * ctx->cam.H;
+  int64_t B = refStream ? 1 : std::max<int64_t>(1, batch_target_paths() / N);
+  B = std::min<int64_t>(B, std::max(sampleCount, 1));
+  if (N * B > 0xfffffff0LL)
+    B = 0xfffffff0LL / N;
+  const int64_t nBatches = sampleCount == 0 ? 0 : (sampleCount + B - 1) / B;
+  const int64_t pathsPerBatch = N * B;
+
+  for (int k = 0; k < 2; ++k)
+    for (int p = 0; p < 3; ++p)
+      CU(ctx->queue[k][p].reserve((size_t)pathsPerBatch));
+  CU(ctx->rad.reserve((size_t)pathsPerBatch));
+  const int64_t nCounters = std::max<int64_t>(1, nBatches * maxDepth);
+  CU(ctx->counters.reserve((size_t)nCounters));
+  CU(ctx->nanCounter.reserve(1));
+  CU(cudaEventRecord(ctx->evStart, ctx->stream));
+  CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(uint32_t) * (size_t)nCounters, ctx->stream));
+  CU(cudaMemsetAsync(ctx->nanCounter.p, 0, sizeof(unsigned long long), ctx->stream));
+  if (refStream)
+  {
+    CU(ctx->seeds.reserve((size_t)N));
+    CU(b2pt::launch_fill_seeds(ctx->seeds.p, (int)N, ctx->seedOffset, ctx->stream));
+  }
+
+  int64_t launches = refStream ? 1 : 0;
+  for (int64_t batch = 0; batch < nBatches; ++batch)
+  {
+    const int64_t s0 = batch * B;
+    const int64_t nb = std::min<int64_t>(B, sampleCount - s0);
+    B2RenderArgs A{};
+    A.counters = ctx->counters.p + batch * maxDepth;
+    A.rad = ctx->rad.p;
+    A.seeds = ctx->seeds.p;
+    A.nPaths = N * nb;
+    A.nPixels = (int32_t)N;
+    A.sampleBase = (int32_t)(sampleBegin + s0);
+    A.maxDepth = maxDepth;
+    A.seedOffset = ctx->seedOffset;
+    A.flags = flags;
+    for (int depth = 0; depth < maxDepth; ++depth)
+    {
+      A.depth = depth;
+      const int in = (depth + 1) & 1, out = depth & 1;
+      A.qin = { ctx->queue[in][0].p, ctx->queue[in][1].p, ctx->queue[in][2].p };
+      A.qout = { ctx->queue[out][0].p, ctx->queue[out][1].p, ctx->queue[out][2].p };
+      CU(b2pt::launch_bounce(ctx->cfg, depth == 0, ctx->cam, ctx->useBvh ? nullptr : &ctx->small,
+                             ctx->useBvh ? &ctx->bvh : nullptr, ctx->lights, A, A.nPaths, ctx->stream));
+      ++launches;
+    }
+    CU(b2pt::launch_accumulate(ctx->color(), ctx->rad.p, (int)N, (int)nb, ctx->nanCounter.p, ctx->stream));
+    ++launches;
+  }
+  CU(cudaEventRecord(ctx->evStop, ctx->stream));
+
+  ctx->stats = b2pt_stats{};
+  ctx->stats.paths = N * (int64_t)sampleCount;
+  ctx->stats.launches = launches;
+  ctx->stats.batches = (int32_t)nBatches;
+  ctx->stats.samplesPerBatch = (int32_t)B;
+  ctx->stats.tracePath = ctx->useBvh ? 1 : 0;
+  ctx->stats.bvhNodes = ctx->bvhNodes;
+  ctx->stats.tracedQuads = ctx->tracedQuads;
+  ctx->stats.tracedSpheres = ctx->tracedSph;
+  ctx->statsPending = true;
+  ctx->pendingCounters = nBatches * maxDepth;
+  ctx->pendingMaxDepth = maxDepth;
+  ctx->pendingPathsPerBatch = pathsPerBatch;
+  return B2PT_OK;
+}
+
+int b2pt_render(b2pt_ctx* ctx, int spp, int maxDepth, uint32_t flags)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (!ctx->haveCamera)
+    return fail(B2PT_ERR_STATE, "render before b2pt_set_camera");
+  if (int rc = b2pt_clear_color(ctx)) // MapperPathTracer.cxx:222-223
+    return rc;
+  return b2pt_render_range(ctx, 0, spp, maxDepth, flags);
+}
+
+int b2pt_synchronize(b2pt_ctx* ctx)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2PT_OK;
+}
+
+int b2pt_get_stats(b2pt_ctx* ctx, b2pt_stats* out)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (!out)
+    return fail(B2PT_ERR_BAD_VALUE, "null stats pointer");
+  if (ctx->statsPending)
+  {
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->evStart, ctx->evStop));
+    ctx->stats.renderMs = ms;
+    ctx->hCounters.resize((size_t)std::max<int64_t>(ctx->pendingCounters, 1));
+    if (ctx->pendingCounters > 0)
+      CU(cudaMemcpy(ctx->hCounters.data(), ctx->counters.p, sizeof(uint32_t) * (size_t)ctx->pendingCounters,
+                    cudaMemcpyDeviceToHost));
+    int64_t seg = ctx->stats.paths; // every path traces its primary segment
+    for (int64_t k = 0; k < ctx->pendingCounters; ++k)
+      seg += ctx->hCounters[(size_t)k]; // counters[d] = rays entering bounce d+1 (0 for the last depth)
+    ctx->stats.segments = seg;
+    // queue traffic: each survivor is written once (48 B) and read once (48 B); radiance 16 B written + read per path
+    ctx->stats.queueBytes = (seg - ctx->stats.paths) * 96 + ctx->stats.paths * 32;
+    unsigned long long nan = 0;
+    CU(cudaMemcpy(&nan, ctx->nanCounter.p, sizeof(nan), cudaMemcpyDeviceToHost));
+    ctx->stats.nanSamples = (int64_t)nan;
+    ctx->statsPending = false;
+  }
+  *out = ctx->stats;
+  return B2PT_OK;
+}
+
+int b2pt_read_color(b2pt_ctx* ctx, float* rgba)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (!rgba)
+    return fail(B2PT_ERR_BAD_VALUE, "null output");
+  if (!ctx->haveCamera)
+    return fail(B2PT_ERR_STATE, "b2pt_read_color before b2pt_set_camera");
+  if (int rc = ensure_color(ctx))
+    return rc;
+  CU(cudaMemcpyAsync(rgba, ctx->color(), sizeof(float4) * (size_t)ctx->cam.W * ctx->cam.H, cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2PT_OK;
+}
+
+int b2pt_write_color(b2pt_ctx* ctx, const float* rgba)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (!rgba)
+    return fail(B2PT_ERR_BAD_VALUE, "null input");
+  if (!ctx->haveCamera)
+    return fail(B2PT_ERR_STATE, "b2pt_write_color before b2pt_set_camera");
+  if (int rc = ensure_color(ctx))
+    return rc;
+  CU(cudaMemcpyAsync(ctx->color(), rgba, sizeof(float4) * (size_t)ctx->cam.W * ctx->cam.H, cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2PT_OK;
+}
+
+int b2pt_normalize(b2pt_ctx* ctx, int spp)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (spp <= 0)
+    return fail(B2PT_ERR_BAD_VALUE, "spp must be positive");
+  if (!ctx->haveCamera)
+    return fail(B2PT_ERR_STATE, "b2pt_normalize before b2pt_set_camera");
+  if (int rc = ensure_color(ctx))
+    return rc;
+  CU(b2pt::launch_normalize(ctx->color(), (int64_t)ctx->cam.W * ctx->cam.H, spp, ctx->stream));
+  return B2PT_OK;
+}
+
+static int ensure_trace(b2pt_ctx* ctx)
+{
+  if (!ctx->haveScene)
+    return fail(B2PT_ERR_STATE, "scene not set");
+  if (!ctx->haveBvh)
+  {
+    if (int rc = build_trace_structures(ctx, 0))
+      return rc;
+    ctx->haveBvh = true;
+  }
+  return B2PT_OK;
+}
+
+int b2pt_primary_hits(b2pt_ctx* ctx, int32_t* primId, float* t)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (!ctx->haveCamera)
+    return fail(B2PT_ERR_STATE, "b2pt_primary_hits before b2pt_set_camera");
+  if (int rc = ensure_trace(ctx))
+    return rc;
+  const size_t N = (size_t)ctx->cam.W * ctx->cam.H;
+  DevBuf<int32_t> dPrim;
+  DevBuf<float> dT;
+  CU(dPrim.reserve(N));
+  CU(dT.reserve(N));
+  cudaError_t e = b2pt::launch_primary_hits(ctx->cam, ctx->useBvh ? nullptr : &ctx->small,
+                                            ctx->useBvh ? &ctx->bvh : nullptr, ctx->seedOffset, dPrim.p, dT.p,
+                                            ctx->stream);
+  if (e == cudaSuccess && primId)
+    e = cudaMemcpyAsync(primId, dPrim.p, N * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && t)
+    e = cudaMemcpyAsync(t, dT.p, N * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(ctx->stream);
+  dPrim.release();
+  dT.release();
+  if (e != cudaSuccess)
+    return fail(B2PT_ERR_CUDA, "b2pt_primary_hits: %s", cudaGetErrorString(e));
+  return B2PT_OK;
+}
+
+int b2pt_create_rays(b2pt_ctx* ctx, uint32_t* seedsInOut, float* dirX, float* dirY, float* dirZ, float* originX,
+                     float* originY, float* originZ, int64_t* pixelIdx)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (!ctx->haveCamera)
+    return fail(B2PT_ERR_STATE, "b2pt_create_rays before b2pt_set_camera");
+  if (!seedsInOut)
+    return fail(B2PT_ERR_BAD_VALUE, "null seeds");
+  if ((dirX || dirY || dirZ) && !(dirX && dirY && dirZ))
+    return fail(B2PT_ERR_BAD_VALUE, "direction outputs must be all set or all null");
+  if ((originX || originY || originZ) && !(originX && originY && originZ))
+    return fail(B2PT_ERR_BAD_VALUE, "origin outputs must be all set or all null");
+  const size_t N = (size_t)ctx->cam.W * ctx->cam.H;
+  DevBuf<uint32_t> dSeeds;
+  DevBuf<float> dF; // 6 planes
+  DevBuf<long long> dPix;
+  CU(dSeeds.reserve(N));
+  CU(dF.reserve(6 * N));
+  CU(dPix.reserve(N));
+  cudaError_t e = cudaMemcpyAsync(dSeeds.p, seedsInOut, N * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess)
+    e = b2pt::launch_create_rays(ctx->cam, dSeeds.p, dF.p, dF.p + N, dF.p + 2 * N, dF.p + 3 * N, dF.p + 4 * N,
+                                 dF.p + 5 * N, dPix.p, ctx->stream);
+  auto back = [&](void* dst, const void* src, size_t bytes) {
+    if (e == cudaSuccess && dst)
+      e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  };
+  back(seedsInOut, dSeeds.p, N * sizeof(uint32_t));
+  back(dirX, dF.p, N * 4), back(dirY, dF.p + N, N * 4), back(dirZ, dF.p + 2 * N, N * 4);
+  back(originX, dF.p + 3 * N, N * 4), back(originY, dF.p + 4 * N, N * 4), back(originZ, dF.p + 5 * N, N * 4);
+  back(pixelIdx, dPix.p, N * sizeof(long long));
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(ctx->stream);
+  dSeeds.release(), dF.release(), dPix.release();
+  if (e != cudaSuccess)
+    return fail(B2PT_ERR_CUDA, "b2pt_create_rays: %s", cudaGetErrorString(e));
+  return B2PT_OK;
+}
+
+int b2pt_intersect(b2pt_ctx* ctx, int64_t n, const float* ox, const float* oy, const float* oz, const float* dx,
+                   const float* dy, const float* dz, float tmin, float tmax, int32_t* primId, float* hrec9,
+                   int32_t* matId, int32_t* texId)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (n < 0)
+    return fail(B2PT_ERR_BAD_VALUE, "negative ray count");
+  if (n == 0)
+    return B2PT_OK;
+  if (!ox || !oy || !oz || !dx || !dy || !dz || !primId)
+    return fail(B2PT_ERR_BAD_VALUE, "null ray array");
+  if (int rc = ensure_trace(ctx))
+    return rc;
+  const size_t N = (size_t)n;
+  DevBuf<float> dIn, dRec;
+  DevBuf<int32_t> dIds;
+  CU(dIn.reserve(6 * N));
+  CU(dRec.reserve(9 * N));
+  CU(dIds.reserve(3 * N));
+  const float* src[6] = { ox, oy, oz, dx, dy, dz };
+  cudaError_t e = cudaSuccess;
+  for (int k = 0; k < 6 && e == cudaSuccess; ++k)
+    e = cudaMemcpyAsync(dIn.p + k * N, src[k], N * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess)
+    e = b2pt::launch_intersect(ctx->useBvh ? nullptr : &ctx->small, ctx->useBvh ? &ctx->bvh : nullptr, n, dIn.p,
+                               dIn.p + N, dIn.p + 2 * N, dIn.p + 3 * N, dIn.p + 4 * N, dIn.p + 5 * N, tmin, tmax,
+                               dIds.p, dRec.p, dIds.p + N, dIds.p + 2 * N, ctx->stream);
+  auto back = [&](void* dst, const void* s, size_t bytes) {
+    if (e == cudaSuccess && dst)
+      e = cudaMemcpyAsync(dst, s, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  };
+  back(primId, dIds.p, N * 4), back(matId, dIds.p + N, N * 4), back(texId, dIds.p + 2 * N, N * 4);
+  back(hrec9, dRec.p, 9 * N * 4);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(ctx->stream);
+  dIn.release(), dRec.release(), dIds.release();
+  if (e != cudaSuccess)
+    return fail(B2PT_ERR_CUDA, "b2pt_intersect: %s", cudaGetErrorString(e));
+  return B2PT_OK;
+}
+
+int b2pt_allreduce(b2pt_ctx* const* ctxs, int G)
+{
+  if (!ctxs || G < 1 || G > 8)
+    return fail(B2PT_ERR_BAD_VALUE, "b2pt_allreduce needs 1..8 contexts");
+  if (G == 1)
+    return B2PT_OK;
+  const int W = ctxs[0]->cam.W, H = ctxs[0]->cam.H;
+  for (int g = 0; g < G; ++g)
+  {
+    if (!ctxs[g] || !ctxs[g]->haveCamera || ctxs[g]->cam.W != W || ctxs[g]->cam.H != H)
+      return fail(B2PT_ERR_BAD_VALUE, "contexts must share one canvas size");
+    if (int rc = bind(ctxs[g]))
+      return rc;
+    if (int rc = ensure_color(ctxs[g]))
+      return rc;
+    CU(cudaStreamSynchronize(ctxs[g]->stream));
+  }
+  // peer access over NVLink (idempotent)
+  for (int a = 0; a < G; ++a)
+    for (int b = 0; b < G; ++b)
+      if (a != b && ctxs[a]->device != ctxs[b]->device)
+      {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, ctxs[a]->device, ctxs[b]->device));
+        if (!can)
+          return fail(B2PT_ERR_UNSUPPORTED, "no peer access between devices %d and %d", ctxs[a]->device,
+                      ctxs[b]->device);
+        CU(cudaSetDevice(ctxs[a]->device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[b]->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled)
+          cudaGetLastError();
+        else if (e != cudaSuccess)
+          return fail(B2PT_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+      }
+  const int64_t n = (int64_t)W * H;
+  std::vector<DevBuf<float4>> tmp((size_t)G);
+  const float4* srcs[8];
+  for (int g = 0; g < G; ++g)
+    srcs[g] = ctxs[g]->color();
+  // reduce-scatter: GPU g sums slice g of every peer into a private slice buffer (reads cross NVLink) ...
+  for (int g = 0; g < G; ++g)
+  {
+    const int64_t b = n * g / G, e = n * (g + 1) / G;
+    CU(cudaSetDevice(ctxs[g]->device));
+    CU(tmp[(size_t)g].reserve((size_t)std::max<int64_t>(e - b, 1)));
+    CU(b2pt::launch_sum_peers(tmp[(size_t)g].p, srcs, G, b, e, ctxs[g]->stream));
+  }
+  for (int g = 0; g < G; ++g)
+  {
+    CU(cudaSetDevice(ctxs[g]->device));
+    CU(cudaStreamSynchronize(ctxs[g]->stream));
+  }
+  // ... all-gather: every GPU's reduced slice is copied to every context's buffer
+  for (int g = 0; g < G; ++g)
+  {
+    const int64_t b = n * g / G, e = n * (g + 1) / G;
+    CU(cudaSetDevice(ctxs[g]->device));
+    for (int d = 0; d < G; ++d)
+      CU(cudaMemcpyPeerAsync(ctxs[d]->color() + b, ctxs[d]->device, tmp[(size_t)g].p, ctxs[g]->device,
+                             sizeof(float4) * (size_t)(e - b), ctxs[g]->stream));
+  }
+  for (int g = 0; g < G; ++g)
+  {
+    CU(cudaSetDevice(ctxs[g]->device));
+    CU(cudaStreamSynchronize(ctxs[g]->stream));
+    tmp[(size_t)g].release();
+  }
+  return B2PT_OK;
+}
+
+} // extern "C"

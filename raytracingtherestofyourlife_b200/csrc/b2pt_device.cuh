@@ -1,0 +1,644 @@
+// b2pt_device.cuh -- device functions of the path-tracing hot path (sm_100a).
+//
+// This translation unit is compiled with -fmad=false (and the default -prec-div=true -prec-sqrt=true
+// -ftz=false): every geometric predicate below evaluates the same IEEE-754 single-precision operation
+// sequence as the reference built for x86-64 without FMA contraction, so ray generation, hit/miss
+// decisions, hit points, normals and sampled directions are bit-identical to the CPU oracle (modulo
+// libm sinf/cosf).  Radiance-only arithmetic (pdf mixture, attenuation) runs in FP32 where the reference
+// promotes to Float64 through vtkm::Pi(); that changes radiance by <= a few ulp and never a trajectory.
+//
+// Each function cites the reference code it restates (paths relative to the reference root).
+#ifndef B2PT_DEVICE_CUH
+#define B2PT_DEVICE_CUH
+
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "b2pt_types.h"
+
+namespace b2pt
+{
+
+struct f3
+{
+  float x, y, z;
+};
+
+__device__ __forceinline__ f3 mk3(float x, float y, float z)
+{
+  f3 r;
+  r.x = x;
+  r.y = y;
+  r.z = z;
+  return r;
+}
+__device__ __forceinline__ f3 ld3(const float* p) { return mk3(p[0], p[1], p[2]); }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ f3 mul3(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+// vtkm::Dot for Vec3: (a0*b0 + a1*b1) + a2*b2
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+// vtkm::Cross (plain form)
+__device__ __forceinline__ f3 cross3(f3 a, f3 b)
+{
+  return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+// vtkm::RMagnitude = RSqrt(MagnitudeSquared), host form 1/sqrt (not rsqrtf: keeps CPU bit-parity)
+__device__ __forceinline__ float rmag3(f3 a) { return 1.0f / sqrtf(dot3(a, a)); }
+__device__ __forceinline__ f3 unit3(f3 a) { return a * rmag3(a); } // vec3.h:38-42, vtkm::Normalize
+__device__ __forceinline__ f3 denan3(f3 c) // PdfWorklet.h:39-45
+{
+  if (!(c.x == c.x))
+    c.x = 0.f;
+  if (!(c.y == c.y))
+    c.y = 0.f;
+  if (!(c.z == c.z))
+    c.z = 0.f;
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------- RNG
+// wangXor.h:30-38
+__device__ __forceinline__ uint32_t wang32(uint32_t& seed)
+{
+  uint32_t s = seed;
+  s = (s ^ 61u) ^ (s >> 16);
+  s *= 9u;
+  s = s ^ (s >> 4);
+  s *= 0x27d4eb2du;
+  s = s ^ (s >> 15);
+  seed = s;
+  return s;
+}
+// wangXor.h:55-59: Float32(t) / 4294967295.f.  The divisor rounds to 2^32 in binary32, so the division is
+// an exact scaling and equals the multiplication by 2^-32 below bit for bit.
+__device__ __forceinline__ float randf(uint32_t& seed)
+{
+  uint32_t t = wang32(seed);
+  return __uint2float_rn(t) * 2.3283064365386963e-10f;
+}
+// PdfWorklet.h:19-21 with genDir(3), WhichGenerateDir.cxx:10
+__device__ __forceinline__ int draw_which(uint32_t& seed)
+{
+  int w = (int)(randf(seed) * 3.f + 1.f);
+  return w > 3 ? 3 : w;
+}
+// Draws a dead pixel still consumes in the reference: per remaining depth 1 (which) + 2/3/2 (generator),
+// SURVEY A.3.  Only used by B2PT_FLAG_REFERENCE_STREAM.
+__device__ __forceinline__ void burn_depths(uint32_t& seed, int count)
+{
+  for (int k = 0; k < count; ++k)
+  {
+    int w = draw_which(seed);
+    wang32(seed);
+    wang32(seed);
+    if (w == 2)
+      wang32(seed);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- camera
+// pathtracing/Camera.cxx:483-524 (RayGen::operator()).  Consumes two draws.
+__device__ __forceinline__ f3 raygen(const B2Camera& cam, int pixel, uint32_t& seed)
+{
+  int i = pixel % cam.W;
+  int j = pixel / cam.W;
+  float ru = randf(seed);
+  float rv = randf(seed);
+  float sx = (2.f * ((float)i + (1.f - ru)) - (float)cam.W) / 2.0f;
+  float sy = (2.f * ((float)j + rv) - (float)cam.H) / 2.0f;
+  f3 d = (ld3(cam.nlook) + ld3(cam.dx) * sx) + ld3(cam.dy) * sy;
+  if (d.x == 0.f)
+    d.x += 0.0000001f;
+  if (d.y == 0.f)
+    d.y += 0.0000001f;
+  if (d.z == 0.f)
+    d.z += 0.0000001f;
+  float m = sqrtf(dot3(d, d));
+  return mk3(d.x / m, d.y / m, d.z / m);
+}
+
+// --------------------------------------------------------------------------------------- primitives
+// Surface.h:30-104 (Lagae-Dutre ray/quad test up to t; the bilinear u,v of :106-158 are never consumed
+// downstream and are not computed).  Returns true iff the reference's hit() returns true; t is valid then.
+__device__ __forceinline__ bool quad_hit(const B2Quad& Q, f3 o, f3 d, float& t)
+{
+  f3 E03 = ld3(Q.e03);
+  f3 P = cross3(d, E03);
+  f3 E01 = ld3(Q.e01);
+  float det = dot3(E01, P);
+  if (fabsf(det) < 1e-5f) // vtkm::Epsilon<Float32>()
+    return false;
+  float inv_det = 1.0f / det;
+  f3 T = o - ld3(Q.v00);
+  float alpha = dot3(T, P) * inv_det;
+  if (alpha < 0.0f)
+    return false;
+  f3 Qv = cross3(T, E01);
+  float beta = dot3(d, Qv) * inv_det;
+  if (beta < 0.0f)
+    return false;
+  if ((alpha + beta) > 1.0f)
+  {
+    f3 E23 = ld3(Q.e23);
+    f3 E21 = ld3(Q.e21);
+    f3 Pp = cross3(d, E21);
+    float detp = dot3(E23, Pp);
+    if (fabsf(detp) < 1e-5f)
+      return false;
+    float inv_detp = 1.0f / detp;
+    f3 Tp = o - ld3(Q.v11);
+    float alphap = dot3(Tp, Pp) * inv_detp;
+    if (alphap < 0.0f)
+      return false;
+    f3 Qp = cross3(Tp, E23);
+    float betap = dot3(d, Qp) * inv_detp;
+    if (betap < 0.0f)
+      return false;
+  }
+  t = dot3(E03, Qv) * inv_det;
+  if (t < 0.0f)
+    return false;
+  return true;
+}
+// Surface.h:163-199 acceptance rule.
+__device__ __forceinline__ bool quad_accept(const B2Quad& Q, f3 o, f3 d, float tmin, float tmax, float& t)
+{
+  float tt;
+  bool h = quad_hit(Q, o, d, tt);
+  h = h && (tt < tmax) && (tt > tmin);
+  if (h)
+    t = tt;
+  return h;
+}
+// Surface.h:180-186: geometric normal flipped to oppose the ray.
+__device__ __forceinline__ f3 quad_normal(const B2Quad& Q, f3 d)
+{
+  f3 n = ld3(Q.nrm);
+  if (dot3(n, d) > 0.f)
+    n = -n;
+  return n;
+}
+// Surface.h:319-367: first root in (tmin,tmax) wins.
+__device__ __forceinline__ bool sphere_accept(f3 c, float radius, f3 o, f3 d, float tmin, float tmax, float& t)
+{
+  f3 oc = o - c;
+  float a = dot3(d, d);
+  float b = dot3(oc, d);
+  float cc = dot3(oc, oc) - radius * radius;
+  float disc = b * b - a * cc;
+  if (disc > 0.f)
+  {
+    float sq = sqrtf(b * b - a * cc);
+    float temp = (-b - sq) / a;
+    if (temp < tmax && temp > tmin)
+    {
+      t = temp;
+      return true;
+    }
+    temp = (-b + sq) / a;
+    if (temp < tmax && temp > tmin)
+    {
+      t = temp;
+      return true;
+    }
+  }
+  return false;
+}
+
+// BVHTraverser.h:35-79 slab test against one box with rcp_safe'd inverse direction (:90-93, :145-157).
+__device__ __forceinline__ bool slab_hit(const float* bmin, const float* bmax, f3 inv, f3 od, float tmin,
+                                         float closest, float& tnear)
+{
+  float xmin = bmin[0] * inv.x - od.x, ymin = bmin[1] * inv.y - od.y, zmin = bmin[2] * inv.z - od.z;
+  float xmax = bmax[0] * inv.x - od.x, ymax = bmax[1] * inv.y - od.y, zmax = bmax[2] * inv.z - od.z;
+  float mn = fmaxf(fmaxf(fmaxf(fminf(ymin, ymax), fminf(xmin, xmax)), fminf(zmin, zmax)), tmin);
+  float mx = fminf(fminf(fminf(fmaxf(ymin, ymax), fmaxf(xmin, xmax)), fmaxf(zmin, zmax)), closest);
+  tnear = mn;
+  return mx >= mn;
+}
+__device__ __forceinline__ float rcp_safe(float f) { return 1.0f / ((fabsf(f) < 1e-8f) ? 1e-8f : f); }
+
+struct Hit
+{
+  f3 p, n, alb;
+  float t;
+  int kind; // matType of the hit primitive
+  int prim; // original primitive id (quad q, sphere nQuads+s), -1 miss
+  int mat, texi;
+};
+
+// Closest hit over a kernel-parameter-resident scene.  MapperPathTracer.cxx:410-435: quads first
+// (QuadIntersector.cxx:59-71), then spheres continuing from the quads' closest distance
+// (SphereIntersector.cxx:88-100); strict t<tmax keeps the first-tested primitive on exact ties.
+__device__ __forceinline__ bool trace_small(const B2SmallScene& S, f3 o, f3 d, float tmin, float tmax, Hit& h)
+{
+  float closest = tmax;
+  int slot = -1;
+  f3 inv = mk3(0.f, 0.f, 0.f), od = mk3(0.f, 0.f, 0.f);
+  if (S.nGate > 0)
+  { // BVHTraverser.h:143-157
+    inv = mk3(rcp_safe(d.x), rcp_safe(d.y), rcp_safe(d.z));
+    od = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+  }
+  for (int q = 0; q < S.nQuads; ++q)
+  {
+    float t;
+    const int gate = S.quads[q].gate;
+    if (gate > 0)
+    { // leaf-box gate of the reference's BVH for non-planar quads (warp-uniform branch)
+      float tn;
+      if (!slab_hit(S.gate[gate - 1].bmin, S.gate[gate - 1].bmax, inv, od, tmin, closest, tn))
+        continue;
+    }
+    if (quad_accept(S.quads[q], o, d, tmin, closest, t))
+    {
+      closest = t;
+      slot = q;
+    }
+  }
+  for (int s = 0; s < S.nSph; ++s)
+  {
+    float t;
+    if (sphere_accept(ld3(S.sph[s].c), S.sph[s].r, o, d, tmin, closest, t))
+    {
+      closest = t;
+      slot = S.nQuads + s;
+    }
+  }
+  if (slot < 0)
+  {
+    h.prim = -1;
+    h.t = closest;
+    return false;
+  }
+  h.t = closest;
+  h.p = o + d * closest; // Surface.h:187, :334
+  if (slot < S.nQuads)
+  {
+    const B2Quad& Q = S.quads[slot];
+    h.n = quad_normal(Q, d);
+    h.alb = ld3(Q.alb);
+    h.kind = Q.kind;
+    h.prim = Q.prim;
+    h.mat = Q.mat;
+    h.texi = Q.texi;
+  }
+  else
+  {
+    const B2Sphere& SP = S.sph[slot - S.nQuads];
+    f3 c = ld3(SP.c);
+    h.n = mk3((h.p.x - c.x) / SP.r, (h.p.y - c.y) / SP.r, (h.p.z - c.z) / SP.r); // Surface.h:340
+    h.alb = ld3(SP.alb);
+    h.kind = SP.kind;
+    h.prim = SP.prim;
+    h.mat = SP.mat;
+    h.texi = SP.texi;
+  }
+  return true;
+}
+
+// Closest hit by stack traversal of the 32-byte-node BVH (one tree for quads and spheres).  A stack entry
+// packs (leaf count << 24 | first child / first slot), so a node's own 32 bytes are never re-read: an inner
+// visit is one 64-byte fetch of the adjacent child pair (4 x LDG.128).  Leaves test primitives in ascending
+// original index, so exact-t ties resolve like brute force within a leaf; across leaves the nearer child is
+// visited first (BVHTraverser.h:189-201).
+__device__ __forceinline__ uint32_t bvh_pack(float leftBits, float countBits)
+{
+  return ((uint32_t)__float_as_int(countBits) << 24) | (uint32_t)__float_as_int(leftBits);
+}
+__device__ __forceinline__ bool trace_bvh(const B2BvhScene& S, f3 o, f3 d, float tmin, float tmax, Hit& h)
+{
+  f3 inv = mk3(rcp_safe(d.x), rcp_safe(d.y), rcp_safe(d.z));
+  f3 od = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+  float closest = tmax;
+  int best = 0;
+  bool found = false;
+  uint32_t stack[64];
+  int sp = 0;
+  const float4* root = reinterpret_cast<const float4*>(S.nodes);
+  uint32_t cur = bvh_pack(__ldg(root).w, __ldg(root + 1).w);
+  while (true)
+  {
+    const uint32_t count = cur >> 24;
+    const uint32_t left = cur & 0xffffffu;
+    if (count)
+    {
+      for (uint32_t k = 0; k < count; ++k)
+      {
+        const int enc = __ldg(S.primSlots + left + k);
+        float t;
+        if (enc >= 0)
+        {
+          const int gate = S.quads[enc].gate;
+          if (gate > 0)
+          {
+            float tn;
+            if (!slab_hit(S.gate[gate - 1].bmin, S.gate[gate - 1].bmax, inv, od, tmin, closest, tn))
+              continue;
+          }
+          if (quad_accept(S.quads[enc], o, d, tmin, closest, t))
+          {
+            closest = t;
+            best = enc;
+            found = true;
+          }
+        }
+        else
+        {
+          const float4 cr = __ldg(reinterpret_cast<const float4*>(S.sph + (~enc)));
+          if (sphere_accept(mk3(cr.x, cr.y, cr.z), cr.w, o, d, tmin, closest, t))
+          {
+            closest = t;
+            best = enc;
+            found = true;
+          }
+        }
+      }
+      if (sp == 0)
+        break;
+      cur = stack[--sp];
+    }
+    else
+    {
+      const float4* lp = reinterpret_cast<const float4*>(S.nodes + left);
+      const float4 l0 = __ldg(lp), l1 = __ldg(lp + 1), r0 = __ldg(lp + 2), r1 = __ldg(lp + 3);
+      float tl, tr;
+      const float lmin[3] = { l0.x, l0.y, l0.z }, lmax[3] = { l1.x, l1.y, l1.z };
+      const float rmin[3] = { r0.x, r0.y, r0.z }, rmax[3] = { r1.x, r1.y, r1.z };
+      const bool hl = slab_hit(lmin, lmax, inv, od, tmin, closest, tl);
+      const bool hr = slab_hit(rmin, rmax, inv, od, tmin, closest, tr);
+      const uint32_t cl = bvh_pack(l0.w, l1.w), crr = bvh_pack(r0.w, r1.w);
+      if (hl && hr)
+      {
+        const bool rightCloser = tl > tr;
+        cur = rightCloser ? crr : cl;
+        if (sp < 64)
+          stack[sp++] = rightCloser ? cl : crr;
+      }
+      else if (hl)
+        cur = cl;
+      else if (hr)
+        cur = crr;
+      else
+      {
+        if (sp == 0)
+          break;
+        cur = stack[--sp];
+      }
+    }
+  }
+  h.t = closest;
+  if (!found)
+  {
+    h.prim = -1;
+    return false;
+  }
+  h.p = o + d * closest;
+  if (best >= 0)
+  {
+    const B2Quad& Q = S.quads[best];
+    h.n = quad_normal(Q, d);
+    h.alb = ld3(Q.alb);
+    h.kind = Q.kind;
+    h.prim = Q.prim;
+    h.mat = Q.mat;
+    h.texi = Q.texi;
+  }
+  else
+  {
+    const B2Sphere& SP = S.sph[~best];
+    f3 c = ld3(SP.c);
+    h.n = mk3((h.p.x - c.x) / SP.r, (h.p.y - c.y) / SP.r, (h.p.z - c.z) / SP.r);
+    h.alb = ld3(SP.alb);
+    h.kind = SP.kind;
+    h.prim = SP.prim;
+    h.mat = SP.mat;
+    h.texi = SP.texi;
+  }
+  return true;
+}
+
+__device__ __forceinline__ bool trace(const B2SmallScene& S, f3 o, f3 d, float tmin, float tmax, Hit& h)
+{
+  return trace_small(S, o, d, tmin, tmax, h);
+}
+__device__ __forceinline__ bool trace(const B2BvhScene& S, f3 o, f3 d, float tmin, float tmax, Hit& h)
+{
+  return trace_bvh(S, o, d, tmin, tmax, h);
+}
+
+// ------------------------------------------------------------------------------------------ shading
+struct Onb
+{
+  f3 u, v, w;
+};
+// onb.h:34-45
+__device__ __forceinline__ Onb onb_from_w(f3 n)
+{
+  Onb o;
+  o.w = unit3(n);
+  f3 a = (fabsf(o.w.x) > 0.9f) ? mk3(0.f, 1.f, 0.f) : mk3(1.f, 0.f, 0.f);
+  o.v = unit3(cross3(o.w, a));
+  o.u = cross3(o.w, o.v);
+  return o;
+}
+// onb.h:30-31
+__device__ __forceinline__ f3 onb_local(const Onb& o, f3 a) { return (o.u * a.x + o.v * a.y) + o.w * a.z; }
+
+#define B2PT_TWO_PI_D 6.283185307179586476925286766559
+#define B2PT_INV_PI_F 0.31830988618379067154f
+
+// PdfWorklet.h:47-53: z=sqrt(1-r2), phi=2*Pi()*r1 (Float64 product narrowed), x,y carry the reference's 2*sqrt(r2)
+__device__ __forceinline__ f3 random_cosine_direction(float r1, float r2)
+{
+  float z = sqrtf(1.f - r2);
+  float phi = (float)(B2PT_TWO_PI_D * (double)r1);
+  float sp, cp;
+  sincosf(phi, &sp, &cp);
+  float s2 = sqrtf(r2);
+  return mk3(cp * 2.f * s2, sp * 2.f * s2, z);
+}
+// PdfWorklet.h:157-165
+__device__ __forceinline__ f3 random_to_sphere(float radius, float dist2, float r1, float r2)
+{
+  float z = 1.f + r2 * (sqrtf(1.f - radius * radius / dist2) - 1.f);
+  float phi = (float)(B2PT_TWO_PI_D * (double)r1);
+  float sp, cp;
+  sincosf(phi, &sp, &cp);
+  float s = sqrtf(1.f - z * z);
+  return mk3(cp * s, sp * s, z);
+}
+
+// PdfWorklet.h:230-248 (QuadPDFWorklet::pdf_value) against one light quad.
+__device__ __forceinline__ float quad_pdf_value(const B2LightQuad& L, f3 o, f3 v)
+{
+  float t;
+  if (!quad_accept(L.geo, o, v, 0.001f, FLT_MAX, t))
+    return 0.f;
+  f3 n = quad_normal(L.geo, v);
+  float dist2 = t * t * dot3(v, v);
+  float cosine = fabsf(dot3(v, n) * rmag3(v));
+  return dist2 / (cosine * L.area);
+}
+// PdfWorklet.h:333-347 (SpherePDFWorklet::pdf_value)
+__device__ __forceinline__ float sphere_pdf_value(const B2LightSphere& L, f3 o, f3 v)
+{
+  float t;
+  f3 c = ld3(L.c);
+  if (!sphere_accept(c, L.r, o, v, 0.001f, FLT_MAX, t))
+    return 0.f;
+  f3 co = c - o;
+  float cos_theta_max = sqrtf(1.f - L.r * L.r / dot3(co, co));
+  float solid_angle = (float)(B2PT_TWO_PI_D * (double)(1.f - cos_theta_max));
+  return 1.f / solid_angle;
+}
+
+// EmitWorklet.h:152-226 (DielectricWorklet): returns the specular direction (reflect or refract).
+__device__ __noinline__ f3 dielectric_scatter(f3 dir, f3 n, float refIdx, float rnd)
+{
+  float dn = dot3(dir, n);
+  f3 reflected = dir - n * (2.f * dn);
+  f3 outward;
+  float ni_over_nt, cosine;
+  if (dn > 0.f)
+  {
+    outward = -n;
+    ni_over_nt = refIdx;
+    cosine = refIdx * dn * rmag3(dir);
+  }
+  else
+  {
+    outward = n;
+    ni_over_nt = (float)(1.0 / (double)refIdx);
+    cosine = -dn * rmag3(dir);
+  }
+  f3 uv = unit3(dir);
+  float dt = dot3(uv, outward);
+  float disc = (float)(1.0 - (double)(ni_over_nt * ni_over_nt * (1.f - dt * dt)));
+  float reflect_prob = 1.0f;
+  f3 refracted = mk3(0.f, 0.f, 0.f);
+  if (disc > 0.f)
+  {
+    refracted = (uv - outward * dt) * ni_over_nt - outward * sqrtf(disc);
+    float r0 = (1.f - refIdx) / (1.f + refIdx);
+    r0 = r0 * r0;
+    double x = (double)(1.f - cosine);
+    double x2 = x * x;
+    reflect_prob = (float)((double)r0 + (double)(1.f - r0) * (x2 * x2 * x)); // schlick, pow(x,5)
+  }
+  return (rnd < reflect_prob) ? reflected : refracted;
+}
+
+enum BounceResult
+{
+  BOUNCE_CONTINUE = 0,
+  BOUNCE_DONE = 1
+};
+
+// One bounce of one live path in forward (throughput) form: the reference's per-depth worklet chain
+//   intersect + CollectIntersect (MapperPathTracer.cxx:410-435, SurfaceWorklets.h:98-111)
+//   Lambertian / DiffuseLight / Dielectric (EmitWorklet.h:46-73, 112-135, 244-272)
+//   Which / Cosine / Quad / Sphere generators (PdfWorklet.h:19-21, 63-79, 112-137, 193-213)
+//   QuadPDF / SpherePDF / PDFCosine (PdfWorklet.h:274-316, 374-399; ScatterWorklet.h:67-117)
+// fused, with the depth-layer compositing of MapperPathTracer.cxx:328-348 carried as throughput T.
+// Draw order while alive is the reference's.  On BOUNCE_DONE, L holds the path's radiance.
+template <class SceneT>
+__device__ __forceinline__ BounceResult bounce(const SceneT& scene, const B2Lights& lights, f3& o, f3& d, f3& T,
+                                               uint32_t& rng, uint32_t flags, f3& L, Hit& hit)
+{
+  if (!trace(scene, o, d, 0.001f, FLT_MAX, hit))
+  {
+    L = T * 0.f; // a[d]=1, e[d]=0: radiance 0, NaN/Inf throughput still poisons the pixel like the reference
+    return BOUNCE_DONE;
+  }
+  if (hit.kind == 1)
+  { // DiffuseLightWorklet::emit: front face only, but the normal was already flipped -> two-sided
+    f3 em = (dot3(hit.n, d) < 0.0f) ? hit.alb : mk3(0.f, 0.f, 0.f);
+    L = mul3(T, em);
+    return BOUNCE_DONE;
+  }
+  bool specular = false;
+  f3 sdir = mk3(0.f, 0.f, 0.f);
+  if (hit.kind == 2)
+  {
+    float r = randf(rng);
+    sdir = dielectric_scatter(d, hit.n, lights.refIdx, r);
+    specular = true;
+  }
+  // direction generators (always consume their draws, even for specular hits)
+  int which = draw_which(rng);
+  f3 g;
+  if (which <= 1)
+  {
+    float r1 = randf(rng);
+    float r2 = randf(rng);
+    Onb uvw = onb_from_w(hit.n);
+    g = denan3(onb_local(uvw, random_cosine_direction(r1, r2)));
+  }
+  else if (which == 2)
+  {
+    g = mk3(0.f, 0.f, 0.f);
+    for (int l = 0; l < lights.nLightQuads; ++l)
+    {
+      const B2LightQuad& LQ = lights.lq[l];
+      float r1 = randf(rng);
+      float r2 = randf(rng);
+      float r3 = randf(rng);
+      float y0 = LQ.pt1[1];
+      f3 rp = mk3(LQ.pt1[0] + r1 * (LQ.pt2[0] - LQ.pt1[0]), y0 + r2 * (y0 - y0), LQ.pt1[2] + r3 * (LQ.pt2[2] - LQ.pt1[2]));
+      g = rp - hit.p;
+    }
+  }
+  else
+  {
+    g = mk3(0.f, 0.f, 0.f);
+    for (int l = 0; l < lights.nLightSph; ++l)
+    {
+      // PdfWorklet.h:210: argument evaluation order of GCC x86-64 (right to left): r2 is drawn first
+      float r2 = randf(rng);
+      float r1 = randf(rng);
+      f3 c = ld3(lights.ls[l].c);
+      f3 dirc = c - hit.p;
+      float d2 = dot3(dirc, dirc);
+      Onb uvw = onb_from_w(dirc);
+      g = denan3(onb_local(uvw, random_to_sphere(lights.ls[l].r, d2, r1, r2)));
+    }
+  }
+  wang32(rng); // SpherePDFWorklet's unused index draw (PdfWorklet.h:393)
+  if (specular)
+  { // ScatterWorklet.h:82-92: attenuation = srec.A = 1
+    o = hit.p;
+    d = sdir;
+    return BOUNCE_CONTINUE;
+  }
+  // light pdfs: sum = weight*quad + weight*sphere (no occlusion test in either)
+  float sum = 0.f;
+  for (int l = 0; l < lights.nLightQuads; ++l)
+    sum += lights.weight * quad_pdf_value(lights.lq[l], hit.p, g);
+  for (int l = 0; l < lights.nLightSph; ++l)
+    sum += lights.weight * sphere_pdf_value(lights.ls[l], hit.p, g);
+  // ScatterWorklet.h:20-28, 52-58, 95-110
+  f3 ug = unit3(g);
+  float cosw = dot3(ug, unit3(hit.n));
+  float value = (cosw > 0.f) ? cosw * B2PT_INV_PI_F : 0.f;
+  float pdf_val = 0.5f * sum + 0.5f * value;
+  float c2 = dot3(hit.n, ug);
+  float spdf = (c2 < 0.f) ? 0.f : c2 * B2PT_INV_PI_F;
+  float sctr = spdf / pdf_val;
+  T = mk3(T.x * (hit.alb.x * sctr), T.y * (hit.alb.y * sctr), T.z * (hit.alb.z * sctr));
+  o = hit.p;
+  d = g;
+  if ((flags & B2PT_FLAG_KILL_ZERO_THROUGHPUT_DEV) && T.x == 0.f && T.y == 0.f && T.z == 0.f)
+  {
+    L = mk3(0.f, 0.f, 0.f);
+    return BOUNCE_DONE;
+  }
+  return BOUNCE_CONTINUE;
+}
+
+} // namespace b2pt
+#endif

@@ -1,0 +1,44 @@
+// b2pt_kernels.h -- host-callable launchers of the sm_100a kernels (implemented in b2pt_kernels.cu).
+#ifndef B2PT_KERNELS_H
+#define B2PT_KERNELS_H
+
+#include <cuda_runtime.h>
+
+#include "b2pt_types.h"
+
+namespace b2pt
+{
+
+struct LaunchCfg
+{
+  int numSMs;
+  int bounceBlocksPerSM[2][2]; // [primary][bvh]
+};
+
+// Queries occupancy of the bounce kernels on the current device.
+cudaError_t query_launch_cfg(LaunchCfg* cfg);
+
+// K1+K2+K3+K5 fused: one bounce of every ray of the input queue (or, primary=true, of freshly generated
+// camera rays), survivors compacted into the output queue.  scene is B2SmallScene or B2BvhScene.
+cudaError_t launch_bounce(const LaunchCfg& cfg, bool primary, const B2Camera& cam, const B2SmallScene* small,
+                          const B2BvhScene* bvh, const B2Lights& lights, const B2RenderArgs& args,
+                          int64_t maxRaysIn, cudaStream_t stream);
+// K4: color[p] += sum_b rad[b*N + p] in sample order; counts NaN samples into *nanCounter.
+cudaError_t launch_accumulate(float4* color, const float4* rad, int nPixels, int samplesInBatch,
+                              unsigned long long* nanCounter, cudaStream_t stream);
+cudaError_t launch_primary_hits(const B2Camera& cam, const B2SmallScene* small, const B2BvhScene* bvh,
+                                uint32_t seedOffset, int32_t* primOut, float* tOut, cudaStream_t stream);
+cudaError_t launch_create_rays(const B2Camera& cam, uint32_t* seeds, float* dx, float* dy, float* dz, float* ox,
+                               float* oy, float* oz, long long* pixelIdx, cudaStream_t stream);
+cudaError_t launch_intersect(const B2SmallScene* small, const B2BvhScene* bvh, int64_t n, const float* ox,
+                             const float* oy, const float* oz, const float* dx, const float* dy, const float* dz,
+                             float tmin, float tmax, int32_t* primId, float* hrec9, int32_t* matId, int32_t* texId,
+                             cudaStream_t stream);
+cudaError_t launch_normalize(float4* color, int64_t n, int spp, cudaStream_t stream);
+cudaError_t launch_fill_seeds(uint32_t* seeds, int n, uint32_t seedOffset, cudaStream_t stream);
+// dst[i-begin] = sum_g srcs[g][i] over [begin,end) float4 elements; srcs may be peer-device pointers.
+cudaError_t launch_sum_peers(float4* dst, const float4* const* srcs, int G, int64_t begin, int64_t end,
+                             cudaStream_t stream);
+
+} // namespace b2pt
+#endif

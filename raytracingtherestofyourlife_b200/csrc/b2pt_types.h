@@ -1,0 +1,152 @@
+// b2pt_types.h -- plain data shared by host set-up code and the sm_100a kernels.
+//
+// Layout notes (DESIGN.md "Data layout in HBM"):
+//  * Small scenes (<= B2PT_SMALL_MAX_QUADS quads, <= B2PT_SMALL_MAX_SPH spheres) travel to the kernels as a
+//    __grid_constant__ kernel parameter: every lane reads the same primitive at the same time, so the
+//    constant bank (uniform loads) serves them with no vector-register or LSU traffic.
+//  * Ray-independent pieces of the reference's Lagae-Dutre quad test (edge vectors, the geometric
+//    normal) are precomputed on the host with the same float operations the reference performs per ray
+//    (Surface.h:56-58, 79-80, 180-181), so per-ray results stay bit-identical.
+//  * Ray queues are SoA-of-16-byte-chunks: three uint4 planes per queue (48 B per ray, 44 B used).
+#ifndef B2PT_TYPES_H
+#define B2PT_TYPES_H
+
+#include <stdint.h>
+
+#define B2PT_SMALL_MAX_QUADS 48
+#define B2PT_SMALL_MAX_SPH 8
+#define B2PT_MAX_LIGHT_QUADS 2
+#define B2PT_MAX_LIGHT_SPH 2
+#define B2PT_GOLDEN 0x9E3779B9u
+// device-side copies of the public render flags (include/b2pt.h)
+#define B2PT_FLAG_REFERENCE_STREAM_DEV 0x1u
+#define B2PT_FLAG_KILL_ZERO_THROUGHPUT_DEV 0x2u
+
+struct B2Quad // 32 words = 128 B, 16-byte aligned
+{
+  float v00[3]; // q
+  float e01[3]; // r - q   (Surface.h:58  E01 = v10 - v00)
+  float e03[3]; // t - q   (Surface.h:56  E03 = v01 - v00)
+  float v11[3]; // s
+  float e21[3]; // r - s   (Surface.h:80  E21 = v10 - v11)
+  float e23[3]; // t - s   (Surface.h:79  E23 = v01 - v11)
+  float nrm[3]; // normalize((r-q)x(s-q)) (Surface.h:180-181), not yet flipped
+  float alb[3]; // tex[texType[texIdx]]
+  int32_t kind; // matType[matIdx]: 0 lambertian, 1 light, 2 dielectric
+  int32_t prim; // original quad index
+  int32_t mat;  // matIdx (HitId M)
+  int32_t texi; // texIdx (HitId T)
+  int32_t gate; // 0: planar quad, no leaf-box gate needed; k>0: must pass slab test of gate box k-1 first
+  int32_t pad[3];
+};
+
+// Leaf AABB of a primitive as the reference's BVH sees it (pathtracing/AABBSurface.h:24-78).  The reference
+// reaches a primitive only if the ray passes this box (one primitive per LinearBVH leaf), which matters for
+// non-planar quads: Lagae-Dutre returns spurious far hits on them that the box culls.
+struct B2GateBox
+{
+  float bmin[3];
+  float bmax[3];
+  float pad[2];
+};
+#define B2PT_SMALL_MAX_GATES 8
+
+struct B2Sphere // 12 words = 48 B
+{
+  float c[3];
+  float r;
+  float alb[3];
+  int32_t kind;
+  int32_t prim; // nQuads + sphere index
+  int32_t mat;
+  int32_t texi;
+  int32_t pad;
+};
+
+struct B2LightQuad // light quad used by QuadWorkletGenerateDir / QuadPDFWorklet
+{
+  B2Quad geo;  // same precomputation as a scene quad
+  float area;  // |r-q| * |t-q| (PdfWorklet.h:236-239)
+  float pt1[3]; // pts[id[1]]
+  float pt2[3]; // pts[id[3]]
+  float pad;
+};
+
+struct B2LightSphere
+{
+  float c[3];
+  float r;
+};
+
+struct B2Camera // RayGen members, pathtracing/Camera.cxx:431-438
+{
+  float nlook[3];
+  float dx[3];
+  float dy[3];
+  float pos[3];
+  int32_t W, H;
+};
+
+struct B2Lights
+{
+  int32_t nLightQuads, nLightSph;
+  float weight; // 1/lightables (PdfWorklet.h:294)
+  float refIdx;
+  B2LightQuad lq[B2PT_MAX_LIGHT_QUADS];
+  B2LightSphere ls[B2PT_MAX_LIGHT_SPH];
+};
+
+struct B2SmallScene
+{
+  int32_t nQuads, nSph;
+  int32_t nGate, pad1;
+  B2GateBox gate[B2PT_SMALL_MAX_GATES];
+  B2Quad quads[B2PT_SMALL_MAX_QUADS];
+  B2Sphere sph[B2PT_SMALL_MAX_SPH];
+};
+
+// BVH scene: global-memory primitive arrays + 32-byte nodes (see b2pt_bvh.h)
+struct B2BvhNode // 32 B, two 16-byte loads
+{
+  float bmin[3];
+  int32_t left;  // inner: index of left child (right = left+1); leaf: first primitive slot
+  float bmax[3];
+  int32_t count; // 0 = inner node, >0 = leaf with `count` primitive slots
+};
+
+struct B2BvhScene
+{
+  const B2BvhNode* nodes;
+  const int32_t* primSlots; // slot -> encoded primitive: >=0 quad index into quads[], <0 sphere ~index
+  const B2Quad* quads;
+  const B2Sphere* sph;
+  const B2GateBox* gate;
+  int32_t nNodes, nQuads, nSph, nGate;
+};
+
+// One ray queue = three planes of uint4.
+struct B2Queue
+{
+  uint4* p0; // ox oy oz dx
+  uint4* p1; // dy dz tr tg
+  uint4* p2; // tb pathId rng aux
+};
+
+struct B2RenderArgs
+{
+  B2Queue qin, qout;
+  uint32_t* counters; // counters[d] = rays written by bounce d (entering bounce d+1)
+  float4* rad;        // per-path radiance, [b*N + pixel]
+  uint32_t* seeds;    // per-pixel persistent RNG state (reference-stream mode)
+  int32_t* primOut;   // optional primary-hit ids (parity hook)
+  float* tOut;
+  int64_t nPaths;     // paths in this batch (N * samplesInBatch)
+  int32_t nPixels;
+  int32_t sampleBase; // global index of the batch's first sample
+  int32_t depth;      // this bounce
+  int32_t maxDepth;
+  uint32_t seedOffset;
+  uint32_t flags;
+};
+
+#endif

@@ -1,0 +1,257 @@
+"""CPU tests of the oracle (oracle/b2pt_oracle.c) against the committed golden vectors and its own modes.
+
+The oracle is "parity unpinned" (no reference tests/goldens exist); the vectors under golden.json["survey"]
+were derived independently of this oracle and are the external pin.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(os.path.join(GOLD, "golden.json")) as f:
+        return json.load(f)
+
+
+def test_wang_chain_survey_vectors(oracle, gold):
+    # wangXor.h:30-38
+    for seed, chain in gold["survey"]["wang_chain"].items():
+        assert oracle.wang_chain(int(seed), 4) == chain
+    assert oracle.wang_chain(12345, 8) == gold["oracle"]["wang_chain_12345"]
+
+
+def test_randf_survey_vectors(oracle, gold):
+    # wangXor.h:55-59; survey prints 8 significant digits
+    got = oracle.randf_chain(0, 4)
+    assert np.allclose(got, gold["survey"]["randf_seed0"], rtol=0, atol=5e-9)
+    # exact definition: float32(t) / float32(4294967295)
+    ch = oracle.wang_chain(0, 4)
+    want = [np.float32(t) / np.float32(4294967295.0) for t in ch]
+    assert [np.float32(x) for x in got] == want
+
+
+def test_randf_can_reach_one(oracle):
+    # getRandF can return exactly 1.0f; state whose hash is 0xFFFFFFFF is not searched for here,
+    # but the float conversion of the largest outputs must round to 1.0
+    assert np.float32(0xFFFFFFFF) / np.float32(4294967295.0) == np.float32(1.0)
+    assert np.float32(0xFFFFFF80) / np.float32(4294967295.0) == np.float32(1.0)
+
+
+def test_wang_init_survey_vectors(oracle, gold):
+    # MapperPathTracer.cxx:60-75
+    assert [oracle.wang_init(i) for i in range(4)] == gold["survey"]["wang_init_0_3"]
+    assert oracle.wang_init(1) != 0  # constant-true CopyIf predicate => seeds[i] = i
+
+
+def test_scene_tables(oracle, gold):
+    sc = oracle.cornell_scene()
+    assert sc.pts.shape == (89, 3) and sc.quadIds.shape == (22, 5)
+    assert hashlib.sha256(sc.pts.tobytes()).hexdigest() == gold["oracle"]["scene_pts_sha256"]
+    assert hashlib.sha256(sc.quadIds.tobytes()).hexdigest() == gold["oracle"]["scene_quadIds_sha256"]
+    # SURVEY A.1 spot values
+    assert np.allclose(sc.pts[8:12] * 555, [[213, 554, 227], [343, 554, 227], [343, 554, 332], [213, 554, 332]])
+    assert np.allclose(sc.pts[48] * 555, [-335, 90, 290])
+    assert np.isclose(sc.pts[40][1] * 555, 333)  # the reference's typo vertex is kept
+    assert sc.matIdxQ.tolist()[:6] == [2, 0, 3, 1, 1, 1] and sc.texIdxQ.tolist()[:6] == [2, 0, 3, 1, 1, 1]
+    assert sc.matType.tolist() == [0, 0, 0, 1, 2] and sc.texType.tolist() == [0, 1, 2, 3, 0]
+    # buildBox emits faces 1,2 again as faces 4,5 (bit-identical duplicates)
+    q = sc.pts[sc.quadIds[:, 1:]]
+    for a, b in ((12, 15), (13, 16), (17, 20), (18, 21)):
+        assert np.array_equal(q[a], q[b])
+    # cell ids skip the sphere's VERTEX cell 12
+    assert sc.quadIds[:, 0].tolist() == list(range(12)) + list(range(13, 23))
+
+
+def test_camera_basis_bits(oracle, gold):
+    a, b, c = oracle.Camera(128, 128).basis()
+    g = gold["oracle"]["camera_basis_128"]
+    assert a.view(np.uint32).tolist() == g["nlook"]
+    assert b.view(np.uint32).tolist() == g["dx"]
+    assert c.view(np.uint32).tolist() == g["dy"]
+    assert np.allclose(a, [0, 0, 1]) and b[0] < 0  # i=0 is world +x (green wall) => delta_x points to -x
+
+
+def test_primary_histogram_matches_survey_probe(oracle, gold):
+    # the surveyor's probe is brute force (no BVH leaf boxes) => compare in NO_AABB_GATE mode
+    prim, t = oracle.primary_hits(oracle.cornell_scene(), oracle.Camera(64, 64), flags=oracle.FLAG_NO_AABB_GATE)
+    u, c = np.unique(prim, return_counts=True)
+    assert {str(k): int(v) for k, v in zip(u, c)} == gold["survey"]["primary_hist_64"]
+
+
+@pytest.mark.parametrize("W", [64, 128])
+def test_primary_ids_fixture(oracle, gold, W):
+    prim, t = oracle.primary_hits(oracle.cornell_scene(), oracle.Camera(W, W))
+    want = np.load(os.path.join(GOLD, "primary_ids_%d.npy" % W)).astype(np.int32)
+    assert np.array_equal(prim, want)
+    assert hashlib.sha256(t.tobytes()).hexdigest() == gold["oracle"]["primary_t_sha256_%d" % W]
+
+
+def test_leaf_box_gate_only_affects_the_nonplanar_quad(oracle):
+    """The reference reaches a primitive only through its BVH leaf box (BVHTraverser.h:35-79 with
+    AABBSurface.h boxes).  For planar quads that gate never changes a hit; for the non-planar tall-box top
+    face (quad 10, CornellBox.cpp:327 typo) it removes the Lagae-Dutre test's spurious far hits."""
+    sc, cam = oracle.cornell_scene(), oracle.Camera(256, 256)
+    p0, t0 = oracle.primary_hits(sc, cam, flags=oracle.FLAG_NO_AABB_GATE)
+    p1, t1 = oracle.primary_hits(sc, cam)
+    diff = p0 != p1
+    assert diff.any()
+    assert set(p0[diff].tolist()) == {10}       # only hits on the non-planar quad are ever removed
+    assert t0[diff].max() > 10.0                # most of them lie far outside the unit box
+    assert (p1[diff] != 10).all()
+    assert np.array_equal(t0[~diff], t1[~diff])
+    # the same holds for incoherent secondary-like rays
+    rng = np.random.default_rng(7)
+    o = rng.uniform(0.05, 0.95, (800, 3)).astype(np.float32)
+    d = rng.normal(size=(800, 3)).astype(np.float32)
+    for k in range(len(o)):
+        a = oracle.closest_hit(sc, o[k], d[k], flags=oracle.FLAG_NO_AABB_GATE)
+        b = oracle.closest_hit(sc, o[k], d[k])
+        if a[0] != b[0]:
+            assert a[0] == 10
+        else:
+            assert a[1][2] == b[1][2]
+
+
+def test_config1_fixture_and_mode_equivalence(oracle, gold):
+    """BASELINE.json configs[0]: 128x128, spp 10, depth 5 (main.cc:56-62)."""
+    sc, cam = oracle.cornell_scene(), oracle.Camera(128, 128)
+    want = np.load(os.path.join(GOLD, "config1_passes_rgb.npy"))
+    img0, st0 = oracle.render(sc, cam, 10, 5, mode=oracle.MODE_PASSES)
+    assert np.array_equal(img0[:, :3], want, equal_nan=True)
+    g = gold["oracle"]["config1"]
+    assert (st0.segments, st0.rngDraws, st0.nanSamples) == (g["segments"], g["rngDraws"], g["nanSamples"])
+    assert [st0.aliveAtDepth[k] for k in range(5)] == g["alive"]
+    assert st0.aliveAtDepth[0] == 128 * 128 * 10
+    # pixel-major evaluation of the same stage functions is bitwise identical
+    img1, st1 = oracle.render(sc, cam, 10, 5, mode=oracle.MODE_FUSED)
+    assert np.array_equal(img0, img1, equal_nan=True)
+    assert (st1.segments, st1.rngDraws) == (st0.segments, st0.rngDraws)
+    # forward form with burned draws follows the same trajectories
+    img2, st2 = oracle.render(sc, cam, 10, 5, mode=oracle.MODE_FORWARD_BURN)
+    assert (st2.segments, st2.rngDraws, st2.nanSamples) == (st0.segments, st0.rngDraws, st0.nanSamples)
+    assert np.array_equal(np.isnan(img0), np.isnan(img2))
+    ok = ~np.isnan(img0)
+    assert np.allclose(img2[ok], img0[ok], rtol=2e-5, atol=1e-6)
+    # thread count must not matter
+    img3, _ = oracle.render(sc, cam, 10, 5, mode=oracle.MODE_PASSES, threads=1)
+    assert np.array_equal(img0, img3, equal_nan=True)
+
+
+def test_fast_stream_fixture_and_sample_ranges(oracle, gold):
+    sc, cam = oracle.cornell_scene(), oracle.Camera(128, 128)
+    want = np.load(os.path.join(GOLD, "config1_fast_rgb.npy"))
+    img, st = oracle.render(sc, cam, 10, 5, mode=oracle.MODE_FORWARD_FAST)
+    assert np.array_equal(img[:, :3], want, equal_nan=True)
+    assert st.segments == gold["oracle"]["config1_fast"]["segments"]
+    # sample ranges are independent streams: [0,10) = [0,4) + [4,10) up to float summation order
+    a, _ = oracle.render(sc, cam, 4, 5, mode=oracle.MODE_FORWARD_FAST, sample_begin=0)
+    b, _ = oracle.render(sc, cam, 6, 5, mode=oracle.MODE_FORWARD_FAST, sample_begin=4)
+    ok = ~np.isnan(img)
+    assert np.allclose((a + b)[ok], img[ok], rtol=1e-5, atol=1e-6)
+
+
+def test_estimator_agreement_between_streams(oracle):
+    """The per-(pixel,sample) stream of the production path estimates the same image as the reference's
+    per-pixel persistent stream: per-channel mean within 2 %, block-averaged relative RMSE within MC noise."""
+    sc, cam = oracle.cornell_scene(), oracle.Camera(96, 96)
+    spp = 96
+    ref, _ = oracle.render(sc, cam, spp, 12, mode=oracle.MODE_FUSED)
+    fast, _ = oracle.render(sc, cam, spp, 12, mode=oracle.MODE_FORWARD_FAST)
+    fast2, _ = oracle.render(sc, cam, spp, 12, mode=oracle.MODE_FORWARD_FAST, seed_offset=777)
+
+    def blocks(x):
+        x = np.nan_to_num(x[:, :3] / spp).reshape(96, 96, 3)
+        return x.reshape(12, 8, 12, 8, 3).mean((1, 3))
+    r, f, f2 = blocks(ref), blocks(fast), blocks(fast2)
+    assert np.allclose(f.mean((0, 1)), r.mean((0, 1)), rtol=0.02)
+    # the radiance distribution is heavy-tailed (fireflies), so use a robust block statistic:
+    # median relative block error against the reference stream is no worse than between two
+    # independent production-stream renders (plus slack)
+    med = lambda a, b: float(np.median(np.abs(a - b) / np.maximum(b, 1e-3)))
+    assert med(f, r) < 2.0 * med(f2, f) + 0.01
+    assert med(f, r) < 0.05
+
+
+def test_kill_zero_throughput_changes_nothing_finite(oracle):
+    sc, cam = oracle.cornell_scene(), oracle.Camera(64, 64)
+    a, sa = oracle.render(sc, cam, 16, 50, mode=oracle.MODE_FORWARD_FAST)
+    b, sb = oracle.render(sc, cam, 16, 50, mode=oracle.MODE_FORWARD_FAST, flags=oracle.FLAG_KILL_ZERO_THROUGHPUT)
+    ok = ~np.isnan(a) & ~np.isnan(b)
+    assert np.array_equal(a[ok], b[ok])
+    assert sb.segments < sa.segments and sb.zeroKilled > 0
+
+
+def test_edge_cases(oracle):
+    sc = oracle.cornell_scene()
+    # spp = 0: empty render
+    img, st = oracle.render(sc, oracle.Camera(16, 16), 0, 5)
+    assert not img.any() and st.paths == 0 and st.segments == 0
+    # depth 1: only directly visible emitters contribute (L = e[0])
+    cam = oracle.Camera(64, 64)
+    img, st = oracle.render(sc, cam, 3, 1, mode=oracle.MODE_FUSED)
+    assert st.segments == 64 * 64 * 3
+    vals = np.unique(img[:, 0])
+    assert set(vals.tolist()) <= {0.0, 15.0, 30.0, 45.0}
+    # ragged canvas (fovX = fovY quirk, Camera.cxx:936-938): W != H still renders and indexes j*W+i
+    cam = oracle.Camera(96, 40)
+    prim, _ = oracle.primary_hits(sc, cam)
+    assert prim.shape == (96 * 40,) and (prim >= 0).any()
+    # 1x1 canvas
+    img, st = oracle.render(sc, oracle.Camera(1, 1), 5, 4, mode=oracle.MODE_PASSES)
+    assert img.shape == (1, 4) and st.paths == 5
+    # invalid arguments
+    with pytest.raises(RuntimeError):
+        oracle.render(sc, cam, 4, 0)
+    with pytest.raises(RuntimeError):
+        oracle.render(sc, cam, 4, 5, mode=oracle.MODE_PASSES, sample_begin=2)
+
+
+def test_quad_hit_known_answers(oracle):
+    import ctypes as C
+    f = lambda *v: np.array(v, np.float32)
+    q, r, s, t = f(0, 0, 0), f(1, 0, 0), f(1, 1, 0), f(0, 1, 0)
+    L = oracle.lib()
+    def hit(o, d):
+        u, v, tt = (C.c_float() for _ in range(3))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        h = L.orc_quad_hit(p(o), p(d), p(q), p(r), p(s), p(t), C.byref(u), C.byref(v), C.byref(tt))
+        return h, u.value, v.value, tt.value
+    h, u, v, tt = hit(f(0.25, 0.5, -2), f(0, 0, 1))
+    assert h == 1 and tt == 2.0 and abs(u - 0.25) < 1e-6 and abs(v - 0.5) < 1e-6
+    assert hit(f(0.9, 0.9, -1), f(0, 0, 1))[0] == 1       # second-triangle branch (alpha+beta > 1)
+    assert hit(f(1.5, 0.5, -1), f(0, 0, 1))[0] == 0       # outside
+    assert hit(f(0.5, 0.5, 1), f(0, 0, 1))[0] == 0        # behind the origin (t < 0)
+    assert hit(f(0.5, 0.5, -1), f(1, 0, 0))[0] == 0       # parallel (|det| < 1e-5)
+    assert hit(f(0.5, 0.5, -1), f(0, 0, 2))[3] == 0.5     # unnormalised direction: t is parametric
+
+
+def test_light_pdf_known_answers(oracle):
+    sc = oracle.cornell_scene()
+    import ctypes as C
+    p = lambda a: np.ascontiguousarray(a, np.float32).ctypes.data_as(C.c_void_p)
+    q, r, s, t = (sc.pts[k] for k in (8, 9, 10, 11))
+    centre = (q + s) / 2
+    o = centre - np.array([0, 0.5, 0], np.float32)
+    v = np.array([0, 2.0, 0], np.float32)  # unnormalised on purpose
+    val = oracle.lib().orc_quad_pdf_value(p(o), p(v), p(q), p(r), p(s), p(t))
+    area = np.linalg.norm(r - q) * np.linalg.norm(t - q)
+    assert np.isclose(val, 0.25 / area, rtol=1e-5)  # dist^2 / (cos * area), cos = 1
+    assert oracle.lib().orc_quad_pdf_value(p(o), p(-v), p(q), p(r), p(s), p(t)) == 0.0
+    c, rad = sc.pts[48], float(sc.sphR[0])
+    o = c + np.array([0.5, 0, 0], np.float32)
+    val = oracle.lib().orc_sphere_pdf_value(p(o), p(np.array([-1, 0, 0], np.float32)), p(c), rad)
+    want = 1.0 / (2 * np.pi * (1 - np.sqrt(1 - rad * rad / 0.25)))
+    assert np.isclose(val, want, rtol=1e-5)
+    assert oracle.lib().orc_sphere_pdf_value(p(o), p(np.array([1, 0, 0], np.float32)), p(c), rad) == 0.0
+
+
+def test_normalize(oracle):
+    x = np.array([[4.0, np.nan, 16.0, 0.0], [1.0, 9.0, 0.0, 0.0]], np.float32)
+    out = oracle.normalize(x, 4)
+    assert np.allclose(out[:, :3], [[1.0, 0.0, 2.0], [0.5, 1.5, 0.0]])
