@@ -117,6 +117,10 @@ int b2pt_write_color(b2pt_ctx* ctx, const float* rgba);
 int b2pt_normalize(b2pt_ctx* ctx, int spp);
 int b2pt_synchronize(b2pt_ctx* ctx);
 int b2pt_get_stats(b2pt_ctx* ctx, b2pt_stats* out);
+/* Per-launch CUDA-event durations (ms, on the context's stream) and input ray counts of the first bounce
+ * launches of the last render's first sample batch; returns the number of entries written (<= maxEntries,
+ * <= 16) or a negative status.  Feeds the live roofline measurement of bench.py. */
+int b2pt_get_bounce_profile(b2pt_ctx* ctx, int maxEntries, float* ms, int64_t* raysIn);
 
 /* ---- parity hooks and stage-level entry points --------------------------------------------- */
 /* Sample-0 primary rays with seeds[i] = i + seedOffset through the production raygen + trace device

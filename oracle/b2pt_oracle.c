@@ -530,6 +530,16 @@ static void sphere_aabb(v3 c, float r, float* bb6)
   /* the reference also mins/maxes the un-offset coordinates of the other axes: same result */
 }
 
+/* planar within 1e-5 of the largest edge: both out-of-triangle vertices' distances to the (q,r,s) plane */
+static int quad_is_planar(v3 q, v3 r, v3 s, v3 t)
+{
+  v3 n = vnormalize(vcross(vsub(r, q), vsub(s, q)));
+  v3 e1 = vsub(r, q), e2 = vsub(s, q), e3 = vsub(t, q);
+  float scale = fmaxf(fmaxf(vmag(e1), vmag(e2)), vmag(e3));
+  float dev = fmaxf(fabsf(vdot(n, e2)), fabsf(vdot(n, e3)));
+  return dev <= 1e-5f * scale;
+}
+
 static inline void quad_pts(const orc_scene* sc, int64_t q, v3* a, v3* b, v3* c, v3* d)
 {
   const int64_t* id = sc->quadIds + 5 * q;
@@ -553,26 +563,36 @@ static int64_t closest_hit(const orc_scene* sc, v3 ro, v3 rd, float tmin, float 
   int64_t prim = -1;
   float closest = tmax;
   float tmp[9];
-  for (int64_t q = 0; q < sc->nQuads; q++)
-  {
-    v3 a, b, c, d;
-    quad_pts(sc, q, &a, &b, &c, &d);
-    if (!(flags & ORC_FLAG_NO_AABB_GATE))
+  /* Two passes over the quads: planar quads first, then non-planar ones.  In the reference's near-child-first
+   * traversal a leaf is visited only if its box entry does not lie beyond the closest hit found so far; for
+   * legitimate (on-surface) hits that never matters, but the spurious off-surface hits of a non-planar quad
+   * are accepted only if nothing closer than the box entry was found among the other primitives -- which
+   * this order reproduces independently of tree topology (DESIGN.md "leaf-box gate"). */
+  for (int pass = 0; pass < 2; pass++)
+    for (int64_t q = 0; q < sc->nQuads; q++)
     {
-      float bb[6];
-      quad_aabb(a, b, c, d, bb);
-      if (!aabb_gate(bb, ro, rd, tmin, closest))
+      v3 a, b, c, d;
+      quad_pts(sc, q, &a, &b, &c, &d);
+      if (!(flags & ORC_FLAG_NO_AABB_GATE))
+      {
+        if (quad_is_planar(a, b, c, d) != (pass == 0))
+          continue;
+        float bb[6];
+        quad_aabb(a, b, c, d, bb);
+        if (!aabb_gate(bb, ro, rd, tmin, closest))
+          continue;
+      }
+      else if (pass == 1)
         continue;
+      if (quad_intersect(ro, rd, tmp, tmin, closest, a, b, c, d))
+      {
+        memcpy(hrec9, tmp, sizeof(tmp));
+        closest = tmp[HR_T];
+        hid2[0] = (int)sc->matIdxQ[q];
+        hid2[1] = (int)sc->texIdxQ[q];
+        prim = q;
+      }
     }
-    if (quad_intersect(ro, rd, tmp, tmin, closest, a, b, c, d))
-    {
-      memcpy(hrec9, tmp, sizeof(tmp));
-      closest = tmp[HR_T];
-      hid2[0] = (int)sc->matIdxQ[q];
-      hid2[1] = (int)sc->texIdxQ[q];
-      prim = q;
-    }
-  }
   for (int64_t s = 0; s < sc->nSph; s++)
   {
     v3 c = ld3(sc->pts + 3 * sc->sphPt[s]);

@@ -63,6 +63,7 @@ SIGNATURES = {
     "b2pt_normalize": (_i32, [_vp, _i32]),
     "b2pt_synchronize": (_i32, [_vp]),
     "b2pt_get_stats": (_i32, [_vp, C.POINTER(Stats)]),
+    "b2pt_get_bounce_profile": (_i32, [_vp, _i32, _vp, _vp]),
     "b2pt_primary_hits": (_i32, [_vp, _vp, _vp]),
     "b2pt_create_rays": (_i32, [_vp] * 9),
     "b2pt_intersect": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
@@ -252,6 +253,14 @@ class Context:
         st = Stats()
         _check(lib().b2pt_get_stats(self._h, C.byref(st)))
         return st
+
+    def bounce_profile(self, n=16):
+        """[(ms, rays_in)] of the first bounce launches of the last render's first batch (CUDA events)."""
+        ms, rays = np.zeros(n, np.float32), np.zeros(n, np.int64)
+        k = lib().b2pt_get_bounce_profile(self._h, n, _p(ms), _p(rays))
+        if k < 0:
+            _check(k)
+        return [(float(ms[i]), int(rays[i])) for i in range(k)]
 
     def primary_hits(self):
         n = self.W * self.H

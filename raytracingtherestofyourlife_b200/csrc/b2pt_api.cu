@@ -94,6 +94,10 @@ struct b2pt_ctx
   cudaStream_t ownStream = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t evStart = nullptr, evStop = nullptr;
+  static constexpr int kProfDepths = 16;
+  cudaEvent_t evBounce[kProfDepths + 1] = {}; // batch 0: event before each of the first bounces + one after
+  int profDepths = 0;
+  int64_t profPaths = 0;
   b2pt::LaunchCfg cfg{};
 
   // scene (host)
@@ -192,7 +196,8 @@ void quad_leaf_box(B2GateBox& G, H3 q, H3 r, H3 s, H3 t)
     G.bmin[c] = lo - eps;
     G.bmax[c] = hi + eps;
   }
-  G.pad[0] = G.pad[1] = 0.f;
+  G.quad = -1;
+  G.pad = 0;
 }
 
 // A quad needs the leaf-box gate unless it is planar: for planar quads every hit the Lagae-Dutre test accepts
@@ -292,6 +297,9 @@ void b2pt_destroy(b2pt_ctx* ctx)
     cudaEventDestroy(ctx->evStart);
   if (ctx->evStop)
     cudaEventDestroy(ctx->evStop);
+  for (cudaEvent_t ev : ctx->evBounce)
+    if (ev)
+      cudaEventDestroy(ev);
   if (ctx->ownStream)
     cudaStreamDestroy(ctx->ownStream);
   delete ctx;
@@ -362,6 +370,7 @@ int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t*
     {
       B2GateBox G;
       quad_leaf_box(G, P(id[1]), P(id[2]), P(id[3]), P(id[4]));
+      G.quad = (int32_t)q;
       gates.push_back(G);
       Q.gate = (int32_t)gates.size();
     }
@@ -459,28 +468,38 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
     ctx->small.nGate = (int32_t)ctx->gates.size();
     for (size_t g = 0; g < ctx->gates.size(); ++g)
       ctx->small.gate[g] = ctx->gates[g];
-    for (size_t k = 0; k < keptQuads.size(); ++k)
-      ctx->small.quads[k] = ctx->quads[(size_t)keptQuads[k]];
+    // planar quads first, gated (non-planar) quads last: see DESIGN.md "leaf-box gate"
+    size_t slot = 0;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int32_t k : keptQuads)
+        if ((ctx->quads[(size_t)k].gate > 0) == (pass == 1))
+          ctx->small.quads[slot++] = ctx->quads[(size_t)k];
     for (int64_t s = 0; s < ctx->nSph; ++s)
       ctx->small.sph[s] = ctx->sph[(size_t)s];
     return B2PT_OK;
   }
   std::vector<B2BvhNode> nodes;
   std::vector<int32_t> slots;
-  if (!b2pt::build_bvh(ctx->quads, keptQuads, ctx->sph, nodes, slots))
+  std::vector<int32_t> treeQuads; // gated quads stay out of the tree (tested after the traversal)
+  for (int32_t k : keptQuads)
+    if (ctx->quads[(size_t)k].gate == 0)
+      treeQuads.push_back(k);
+  if (!b2pt::build_bvh(ctx->quads, treeQuads, ctx->sph, nodes, slots))
     return fail(B2PT_ERR_UNSUPPORTED, "scene too large for the 24-bit BVH index packing");
-  CU(ctx->dNodes.reserve(nodes.size()));
-  CU(ctx->dSlots.reserve(slots.size()));
+  CU(ctx->dNodes.reserve(std::max<size_t>(nodes.size(), 1)));
+  CU(ctx->dSlots.reserve(std::max<size_t>(slots.size(), 1)));
   CU(ctx->dQuads.reserve(std::max<size_t>(ctx->quads.size(), 1)));
   CU(ctx->dSph.reserve(std::max<size_t>(ctx->sph.size(), 1)));
   CU(ctx->dGates.reserve(std::max<size_t>(ctx->gates.size(), 1)));
   if (!ctx->gates.empty())
     CU(cudaMemcpyAsync(ctx->dGates.p, ctx->gates.data(), ctx->gates.size() * sizeof(B2GateBox),
                        cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->dNodes.p, nodes.data(), nodes.size() * sizeof(B2BvhNode), cudaMemcpyHostToDevice,
-                     ctx->stream));
-  CU(cudaMemcpyAsync(ctx->dSlots.p, slots.data(), slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
-                     ctx->stream));
+  if (!nodes.empty())
+    CU(cudaMemcpyAsync(ctx->dNodes.p, nodes.data(), nodes.size() * sizeof(B2BvhNode), cudaMemcpyHostToDevice,
+                       ctx->stream));
+  if (!slots.empty())
+    CU(cudaMemcpyAsync(ctx->dSlots.p, slots.data(), slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                       ctx->stream));
   if (!ctx->quads.empty())
     CU(cudaMemcpyAsync(ctx->dQuads.p, ctx->quads.data(), ctx->quads.size() * sizeof(B2Quad), cudaMemcpyHostToDevice,
                        ctx->stream));
@@ -659,6 +678,9 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
   }
 
   int64_t launches = refStream ? 1 : 0;
+  const int profDepths = std::min(maxDepth - 1, (int)b2pt_ctx::kProfDepths); // events 0..profDepths bracket that many bounces
+  ctx->profDepths = nBatches > 0 ? profDepths : 0;
+  ctx->profPaths = nBatches > 0 ? N * std::min<int64_t>(B, sampleCount) : 0;
   for (int64_t batch = 0; batch < nBatches; ++batch)
   {
     const int64_t s0 = batch * B;
@@ -675,6 +697,12 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
     A.flags = flags;
     for (int depth = 0; depth < maxDepth; ++depth)
     {
+      if (batch == 0 && depth <= b2pt_ctx::kProfDepths && depth <= profDepths)
+      { // per-launch CUDA events of the first bounces of batch 0 (b2pt_get_bounce_profile)
+        if (!ctx->evBounce[depth])
+          CU(cudaEventCreate(&ctx->evBounce[depth]));
+        CU(cudaEventRecord(ctx->evBounce[depth], ctx->stream));
+      }
       A.depth = depth;
       const int in = (depth + 1) & 1, out = depth & 1;
       A.qin = { ctx->queue[in][0].p, ctx->queue[in][1].p, ctx->queue[in][2].p };
@@ -752,6 +780,24 @@ int b2pt_get_stats(b2pt_ctx* ctx, b2pt_stats* out)
   }
   *out = ctx->stats;
   return B2PT_OK;
+}
+
+int b2pt_get_bounce_profile(b2pt_ctx* ctx, int maxEntries, float* ms, int64_t* raysIn)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (maxEntries < 0 || (maxEntries > 0 && (!ms || !raysIn)))
+    return fail(B2PT_ERR_BAD_VALUE, "null profile output");
+  b2pt_stats st;
+  if (int rc = b2pt_get_stats(ctx, &st)) // synchronises and fetches the counters
+    return rc;
+  const int n = std::min(maxEntries, ctx->profDepths);
+  for (int d = 0; d < n; ++d)
+  {
+    CU(cudaEventElapsedTime(&ms[d], ctx->evBounce[d], ctx->evBounce[d + 1]));
+    raysIn[d] = d == 0 ? ctx->profPaths : (int64_t)ctx->hCounters[(size_t)(d - 1)];
+  }
+  return n;
 }
 
 int b2pt_read_color(b2pt_ctx* ctx, float* rgba)

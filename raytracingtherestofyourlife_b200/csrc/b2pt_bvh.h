@@ -98,6 +98,8 @@ inline bool build_bvh(const std::vector<B2Quad>& quads, const std::vector<int32_
 
   nodes.clear();
   slots.clear();
+  if (items.empty())
+    return true; // nothing for the tree (all primitives gated): traversal is skipped when nNodes == 0
   nodes.reserve(items.size());
   slots.reserve(items.size());
   struct Work

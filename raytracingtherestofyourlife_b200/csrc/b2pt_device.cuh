@@ -249,7 +249,8 @@ __device__ __forceinline__ bool trace_small(const B2SmallScene& S, f3 o, f3 d, f
     float t;
     const int gate = S.quads[q].gate;
     if (gate > 0)
-    { // leaf-box gate of the reference's BVH for non-planar quads (warp-uniform branch)
+    { // leaf-box gate of the reference's BVH for non-planar quads (warp-uniform branch); the host orders
+      // gated quads after all planar ones
       float tn;
       if (!slab_hit(S.gate[gate - 1].bmin, S.gate[gate - 1].bmax, inv, od, tmin, closest, tn))
         continue;
@@ -320,8 +321,8 @@ __device__ __forceinline__ bool trace_bvh(const B2BvhScene& S, f3 o, f3 d, float
   uint32_t stack[64];
   int sp = 0;
   const float4* root = reinterpret_cast<const float4*>(S.nodes);
-  uint32_t cur = bvh_pack(__ldg(root).w, __ldg(root + 1).w);
-  while (true)
+  uint32_t cur = S.nNodes > 0 ? bvh_pack(__ldg(root).w, __ldg(root + 1).w) : 0u;
+  while (S.nNodes > 0)
   {
     const uint32_t count = cur >> 24;
     const uint32_t left = cur & 0xffffffu;
@@ -333,13 +334,6 @@ __device__ __forceinline__ bool trace_bvh(const B2BvhScene& S, f3 o, f3 d, float
         float t;
         if (enc >= 0)
         {
-          const int gate = S.quads[enc].gate;
-          if (gate > 0)
-          {
-            float tn;
-            if (!slab_hit(S.gate[gate - 1].bmin, S.gate[gate - 1].bmax, inv, od, tmin, closest, tn))
-              continue;
-          }
           if (quad_accept(S.quads[enc], o, d, tmin, closest, t))
           {
             closest = t;
@@ -389,6 +383,22 @@ __device__ __forceinline__ bool trace_bvh(const B2BvhScene& S, f3 o, f3 d, float
           break;
         cur = stack[--sp];
       }
+    }
+  }
+  // Non-planar quads are kept out of the tree and tested last, each behind the slab test of its own leaf box
+  // with the closest distance of everything else: the acceptance rule of the reference's near-first
+  // traversal, independent of tree topology (DESIGN.md "leaf-box gate").
+  for (int g = 0; g < S.nGate; ++g)
+  {
+    float tn, t;
+    if (!slab_hit(S.gate[g].bmin, S.gate[g].bmax, inv, od, tmin, closest, tn))
+      continue;
+    const int q = S.gate[g].quad;
+    if (quad_accept(S.quads[q], o, d, tmin, closest, t))
+    {
+      closest = t;
+      best = q;
+      found = true;
     }
   }
   h.t = closest;

@@ -47,7 +47,8 @@ struct B2GateBox
 {
   float bmin[3];
   float bmax[3];
-  float pad[2];
+  int32_t quad; // index of the gated quad in the scene's quad array (BVH path: tested after the traversal)
+  int32_t pad;
 };
 #define B2PT_SMALL_MAX_GATES 8
 
