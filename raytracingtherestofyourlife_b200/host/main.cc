@@ -1,0 +1,136 @@
+// main.cc -- command-line driver with the reference's flags (main.cc:54-113) for the path-traced image:
+//   ./CornellBox_b2pt -x 128 -y 128 -samplecount 10 -raydepth 5
+// Builds the Cornell box, renders it through MapperPathTracer (GPU), normalises with the reference's
+// NormalizeFunctor semantics and writes output.pnm (ASCII P3, bottom row first) like main.cc:361-384.
+// The -direct G-buffer modes and the -hemisphere camera sweep are outside the hot path.
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <string>
+
+#include "CornellBox.h"
+#include "MapperPathTracer.h"
+#include "b2pt_facade.h"
+
+namespace
+{
+
+struct Options
+{
+  int x = 128, y = 128, samples = 10, depth = 5; // reference defaults, main.cc:56-62
+  std::string out = "output";
+  bool stats = false;
+};
+
+Options parse(int argc, char** argv)
+{
+  Options o;
+  for (int i = 1; i < argc; ++i)
+  {
+    auto next = [&](int& dst) {
+      if (i + 1 < argc)
+        dst = std::atoi(argv[++i]);
+    };
+    if (!std::strcmp(argv[i], "-x"))
+      next(o.x);
+    else if (!std::strcmp(argv[i], "-y"))
+      next(o.y);
+    else if (!std::strcmp(argv[i], "-samplecount"))
+      next(o.samples);
+    else if (!std::strcmp(argv[i], "-raydepth"))
+      next(o.depth);
+    else if (!std::strcmp(argv[i], "-o") && i + 1 < argc)
+      o.out = argv[++i];
+    else if (!std::strcmp(argv[i], "-stats"))
+      o.stats = true;
+    else if (!std::strcmp(argv[i], "-hemisphere") || !std::strcmp(argv[i], "-direct"))
+      std::cerr << "note: " << argv[i] << " is outside the path-tracing hot path and is ignored\n";
+  }
+  return o;
+}
+
+// the reference's runPath (main.cc:289-323): this body is what a reference user already has
+void runPath(CornellBox& cb, int samplecount, int depthcount, vtkm::rendering::Canvas& canvas,
+             vtkm::rendering::Camera& cam, bool stats)
+{
+  vtkm::rendering::MapperPathTracer mapper(samplecount, depthcount, cb.matIdx, cb.texIdx, cb.matType, cb.texType,
+                                           cb.tex);
+  mapper.SetCanvas(&canvas);
+  vtkm::cont::Field field;
+  vtkm::cont::ColorTable ct;
+  vtkm::Range sr;
+  mapper.RenderCells(cb.ds.GetCellSet(), cb.coord, field, ct, cam, sr);
+  if (stats)
+    std::cout << " GPU render ms = " << mapper.GetLastRenderMilliseconds()
+              << "  path samples/s = " << double(canvas.GetWidth()) * canvas.GetHeight() * samplecount /
+        (mapper.GetLastRenderMilliseconds() * 1e-3)
+              << "  segments = " << mapper.GetLastSegments() << std::endl;
+  // NormalizeFunctor (main.cc:253-287): sqrt(de_nan(sum) / samplecount), alpha through the same sqrt
+  auto cols = canvas.GetColorBuffer().WritePortal();
+  const float sc = static_cast<float>(samplecount);
+  for (vtkm::Id i = 0; i < cols.GetNumberOfValues(); ++i)
+  {
+    auto c = cols.Get(i);
+    for (int k = 0; k < 3; ++k)
+      if (!(c[k] == c[k]))
+        c[k] = 0;
+    for (int k = 0; k < 4; ++k)
+      c[k] = std::sqrt(c[k] / sc);
+    cols.Set(i, c);
+  }
+}
+
+void savePnm(const std::string& stem, int nx, int ny, vtkm::rendering::Canvas& canvas)
+{
+  std::ofstream fs(stem + ".pnm");
+  if (!fs)
+  {
+    std::cout << "Couldn't save pnm." << std::endl;
+    return;
+  }
+  fs << "P3\n" << nx << " " << ny << " 255" << std::endl;
+  auto cols = canvas.GetColorBuffer().ReadPortal();
+  for (vtkm::Id i = 0; i < cols.GetNumberOfValues(); ++i)
+  {
+    auto col = cols.Get(i);
+    if ((col[0] != col[0]) || (col[1] != col[1]) || (col[2] != col[2]))
+      col = 0.0f;
+    fs << int(255.99 * col[0]) << " " << int(255.99 * col[1]) << " " << int(255.99 * col[2]) << std::endl;
+  }
+}
+
+} // namespace
+
+int main(int argc, char* argv[])
+{
+  const Options o = parse(argc, argv);
+  const auto t0 = std::chrono::steady_clock::now();
+  try
+  {
+    auto cb = std::make_unique<CornellBox>();
+    cb->buildDataSet();
+    vtkm::rendering::CanvasRayTracer canvas(o.x, o.y);
+    vtkm::rendering::Camera cam; // main.cc:616-622
+    cam.SetClippingRange(0.1f, 5.f);
+    cam.SetPosition(vec3(278 / 555.0, 278 / 555.0, -800 / 555.0));
+    cam.SetFieldOfView(40.);
+    cam.SetViewUp(vec3(0, 1, 0));
+    cam.SetLookAt(vec3(278 / 555.0, 278 / 555.0, 278 / 555.0));
+    runPath(*cb, o.samples, o.depth, canvas, cam, o.stats);
+    savePnm(o.out, o.x, o.y, canvas);
+  }
+  catch (const vtkm::cont::Error& e)
+  {
+    std::cerr << "error: " << e.GetMessage() << std::endl;
+    b2pt_facade::ReleaseContext();
+    return 1;
+  }
+  b2pt_facade::ReleaseContext();
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  std::cout << " Elapsed time         = " << dt << std::endl;
+  return 0;
+}

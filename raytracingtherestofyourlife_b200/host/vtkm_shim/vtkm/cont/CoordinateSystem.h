@@ -1,0 +1,2 @@
+// forwarding header of the minimal VTK-m stand-in (see vtkm/Types.h)
+#include <vtkm/cont/DataSet.h>
