@@ -47,6 +47,7 @@ typedef enum b2pt_status
                                                with B2PT_FLAG_REFERENCE_STREAM */
 #define B2PT_FLAG_NO_DEDUP 0x4u             /* keep bit-identical duplicate quads in the trace list */
 #define B2PT_FLAG_FORCE_BVH 0x8u            /* use the BVH traversal kernels even for small scenes */
+#define B2PT_FLAG_NO_AA 0x10u               /* do not use the axis-aligned quad specialisation (A/B parity checks) */
 
 typedef struct b2pt_stats
 {

@@ -14,13 +14,14 @@ import numpy as np
 from . import _build
 
 __all__ = ["lib", "Scene", "Camera", "Context", "B2ptError", "Stats", "FLAG_REFERENCE_STREAM",
-           "FLAG_KILL_ZERO_THROUGHPUT", "FLAG_NO_DEDUP", "FLAG_FORCE_BVH", "LIB_PATH"]
+           "FLAG_KILL_ZERO_THROUGHPUT", "FLAG_NO_DEDUP", "FLAG_FORCE_BVH", "FLAG_NO_AA", "LIB_PATH"]
 
 LIB_PATH = _build.LIB
 FLAG_REFERENCE_STREAM = 0x1
 FLAG_KILL_ZERO_THROUGHPUT = 0x2
 FLAG_NO_DEDUP = 0x4
 FLAG_FORCE_BVH = 0x8
+FLAG_NO_AA = 0x10
 
 ERR_BAD_VALUE, ERR_CUDA, ERR_STATE, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 

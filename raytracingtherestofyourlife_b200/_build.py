@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libb2pt.so")
+LIB = os.environ.get("B2PT_LIB") or os.path.join(HERE, "libb2pt.so")  # B2PT_LIB: experiment builds
 SOURCES = ["b2pt_kernels.cu", "b2pt_api.cu", "b2pt_scene.cpp"]
 HEADERS = ["b2pt_device.cuh", "b2pt_kernels.h", "b2pt_types.h", "b2pt_bvh.h", "../../include/b2pt.h"]
 NVCC = os.environ.get("B2PT_NVCC", "/usr/local/cuda/bin/nvcc")
@@ -34,6 +34,8 @@ def _stale():
 
 def build_lib(force=False, verbose=False):
     """Compile libb2pt.so if sources are newer than the library. Returns its path."""
+    if os.environ.get("B2PT_LIB"):
+        return LIB
     if not force and not _stale():
         return LIB
     objs = []

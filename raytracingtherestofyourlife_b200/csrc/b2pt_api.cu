@@ -106,6 +106,7 @@ struct b2pt_ctx
   std::vector<B2Quad> quads; // by original index
   std::vector<B2Sphere> sph;
   std::vector<B2GateBox> gates; // leaf boxes of non-planar quads (B2Quad::gate indexes this, 1-based)
+  std::vector<B2GateBox> boxes; // leaf box of every quad (AABBSurface.h), by original index
   B2Lights lights{};
   // trace structures
   bool useBvh = false;
@@ -127,7 +128,10 @@ struct b2pt_ctx
   DevBuf<float4> colorOwn;
   float4* colorExt = nullptr;
   int64_t colorPixels = 0;
-  DevBuf<uint4> queue[2][3];
+  DevBuf<uint4> queue[3];  // the compact ray queue (three 16-byte planes)
+  DevBuf<uint4> bins[3];   // sorted hit queues: 4 bins x pathsPerBatch records per plane
+  DevBuf<uint32_t> binCode;
+  DevBuf<uint32_t> regionCounts; // qCount[numWarps] + binCount[4*numWarps]
   DevBuf<float4> rad;
   DevBuf<uint32_t> counters;
   DevBuf<uint32_t> seeds;
@@ -213,6 +217,46 @@ bool quad_is_planar(H3 q, H3 r, H3 s, H3 t, const float* unitNormal)
   return dev <= 1e-5f * scale;
 }
 
+// Axis-aligned rectangle detection for the bit-identical specialised test (B2AAQuad, aa_quad_hit): E01 and E23
+// must have exactly one non-zero component u, E03 and E21 exactly one non-zero component v != u.
+bool classify_axis_aligned(const B2Quad& Q, int slot, B2AAQuad& A)
+{
+  std::memset(&A, 0, sizeof(A));
+  A.cls = -1;
+  A.slot = slot;
+  A.prim = Q.prim;
+  auto single_axis = [](const float* e) -> int {
+    int axis = -1;
+    for (int c = 0; c < 3; ++c)
+      if (e[c] != 0.f)
+      {
+        if (axis >= 0)
+          return -1;
+        axis = c;
+      }
+    return axis;
+  };
+  const int u = single_axis(Q.e01), v = single_axis(Q.e03);
+  if (u < 0 || v < 0 || u == v || single_axis(Q.e23) != u || single_axis(Q.e21) != v)
+    return false;
+  const int n = 3 - u - v;
+  static const int clsOf[3][3] = { { -1, 0, 4 }, { 3, -1, 1 }, { 2, 5, -1 } }; // [u][v]
+  A.cls = clsOf[u][v];
+  const float eps = (A.cls < 3) ? 1.f : -1.f; // +1 for cyclic (u,v,n)
+  const float a = Q.e01[u], b = Q.e03[v], a2 = Q.e23[u], b2 = Q.e21[v];
+  A.v00u = Q.v00[u], A.v00v = Q.v00[v], A.v00n = Q.v00[n];
+  A.v11u = Q.v11[u], A.v11v = Q.v11[v], A.v11n = Q.v11[n];
+  A.a = a, A.b = b, A.a2 = a2;
+  A.bPu = -eps * b, A.bPn = eps * b, A.aQv = eps * a, A.aQn = -eps * a;
+  A.b2Pu = -eps * b2, A.b2Pn = eps * b2, A.a2Qv = eps * a2, A.a2Qn = -eps * a2;
+  // consistent rectangle: the second triangle's frame is the first one's mirrored about the centre
+  const bool rect = a2 == -a && b2 == -b && std::fabs((Q.v00[u] + a) - Q.v11[u]) <= 2e-6f * std::fabs(a) &&
+    std::fabs((Q.v00[v] + b) - Q.v11[v]) <= 2e-6f * std::fabs(b) && Q.v00[n] == Q.v11[n];
+  if (rect)
+    A.cls |= 8;
+  return true;
+}
+
 bool same_vertices(const B2Quad& a, const B2Quad& b)
 {
   return std::memcmp(a.v00, b.v00, 12) == 0 && std::memcmp(a.e01, b.e01, 12) == 0 &&
@@ -289,9 +333,12 @@ void b2pt_destroy(b2pt_ctx* ctx)
   cudaStreamSynchronize(ctx->stream);
   ctx->dNodes.release(), ctx->dSlots.release(), ctx->dQuads.release(), ctx->dSph.release(), ctx->dGates.release();
   ctx->colorOwn.release();
-  for (auto& q : ctx->queue)
-    for (auto& p : q)
-      p.release();
+  for (auto& p : ctx->queue)
+    p.release();
+  for (auto& p : ctx->bins)
+    p.release();
+  ctx->binCode.release();
+  ctx->regionCounts.release();
   ctx->rad.release(), ctx->counters.release(), ctx->seeds.release(), ctx->nanCounter.release();
   if (ctx->evStart)
     cudaEventDestroy(ctx->evStart);
@@ -355,6 +402,7 @@ int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t*
 
   std::vector<B2Quad> quads((size_t)nQuads);
   std::vector<B2GateBox> gates;
+  std::vector<B2GateBox> boxes((size_t)nQuads);
   for (int64_t q = 0; q < nQuads; ++q)
   {
     const int64_t* id = quadIds + 5 * q;
@@ -366,13 +414,15 @@ int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t*
     precompute_quad(Q, P(id[1]), P(id[2]), P(id[3]), P(id[4]));
     Q.gate = 0;
     Q.pad[0] = Q.pad[1] = Q.pad[2] = 0;
+    B2GateBox G;
+    quad_leaf_box(G, P(id[1]), P(id[2]), P(id[3]), P(id[4]));
+    G.quad = (int32_t)q;
+    boxes[(size_t)q] = G;
     if (!quad_is_planar(P(id[1]), P(id[2]), P(id[3]), P(id[4]), Q.nrm))
     {
-      B2GateBox G;
-      quad_leaf_box(G, P(id[1]), P(id[2]), P(id[3]), P(id[4]));
-      G.quad = (int32_t)q;
       gates.push_back(G);
       Q.gate = (int32_t)gates.size();
+      Q.pad[0] = 1; // non-planar: the leaf box is part of the acceptance rule
     }
     if (!material(matIdxQuad[q], texIdxQuad[q], Q.kind, Q.alb))
       return fail(B2PT_ERR_BAD_VALUE, "quad %lld has material/texture index out of range", (long long)q);
@@ -412,6 +462,7 @@ int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t*
     precompute_quad(LQ.geo, q, r, s, t);
     LQ.geo.prim = -1;
     LQ.geo.gate = 0; // QuadPDFWorklet calls the leaf intersector directly, no BVH (PdfWorklet.h:238)
+    classify_axis_aligned(LQ.geo, 0, LQ.aa);
     H3 rq = hsub(r, q), tq = hsub(t, q);
     LQ.area = std::sqrt(hdot(rq, rq)) * std::sqrt(hdot(tq, tq)); // PdfWorklet.h:236-239
     hst(LQ.pt1, q);                                              // PdfWorklet.h:124-125
@@ -427,6 +478,7 @@ int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t*
   ctx->quads.swap(quads);
   ctx->sph.swap(sph);
   ctx->gates.swap(gates);
+  ctx->boxes.swap(boxes);
   ctx->lights = L;
   ctx->nQuads = nQuads;
   ctx->nSph = nSpheres;
@@ -437,7 +489,7 @@ int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t*
 
 static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
 {
-  ctx->builtFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP);
+  ctx->builtFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA);
   // Drop bit-identical duplicate quads: a later copy computes the same t and loses the strict t<tmax
   // comparison (Surface.h:178-179), so removing it cannot change any result.
   std::vector<int32_t> keptQuads;
@@ -456,24 +508,51 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
   }
   ctx->tracedQuads = (int32_t)keptQuads.size();
   ctx->tracedSph = (int32_t)ctx->nSph;
+  // classify: axis-aligned rectangles get the specialised test; every other quad is traced behind its leaf box
+  std::vector<B2AAQuad> aa;
+  std::vector<int32_t> boxedPlanar, boxedNonPlanar;
+  for (int32_t k : keptQuads)
+  {
+    B2AAQuad A;
+    const B2Quad& Q = ctx->quads[(size_t)k];
+    if (Q.pad[0] == 0 && !(flags & B2PT_FLAG_NO_AA_DEV) && classify_axis_aligned(Q, 0, A))
+      aa.push_back(A);
+    else
+      (Q.pad[0] ? boxedNonPlanar : boxedPlanar).push_back(k);
+  }
+  const size_t nBoxed = boxedPlanar.size() + boxedNonPlanar.size();
   const bool fitsSmall = keptQuads.size() <= B2PT_SMALL_MAX_QUADS && ctx->nSph <= B2PT_SMALL_MAX_SPH &&
-    ctx->gates.size() <= B2PT_SMALL_MAX_GATES;
+    nBoxed <= B2PT_SMALL_MAX_GATES;
   ctx->useBvh = !fitsSmall || (flags & B2PT_FLAG_FORCE_BVH);
   ctx->bvhNodes = 0;
   if (!ctx->useBvh)
   {
-    std::memset(&ctx->small, 0, sizeof(ctx->small));
-    ctx->small.nQuads = (int32_t)keptQuads.size();
-    ctx->small.nSph = (int32_t)ctx->nSph;
-    ctx->small.nGate = (int32_t)ctx->gates.size();
-    for (size_t g = 0; g < ctx->gates.size(); ++g)
-      ctx->small.gate[g] = ctx->gates[g];
-    // planar quads first, gated (non-planar) quads last: see DESIGN.md "leaf-box gate"
-    size_t slot = 0;
-    for (int pass = 0; pass < 2; ++pass)
-      for (int32_t k : keptQuads)
-        if ((ctx->quads[(size_t)k].gate > 0) == (pass == 1))
-          ctx->small.quads[slot++] = ctx->quads[(size_t)k];
+    B2SmallScene& S = ctx->small;
+    std::memset(&S, 0, sizeof(S));
+    S.nQuads = (int32_t)keptQuads.size();
+    S.nSph = (int32_t)ctx->nSph;
+    S.nAA = (int32_t)aa.size();
+    S.firstBoxed = (int32_t)aa.size();
+    std::stable_sort(aa.begin(), aa.end(),
+                     [](const B2AAQuad& x, const B2AAQuad& y) { return (x.cls & 7) < (y.cls & 7); });
+    for (size_t k = 0; k < aa.size(); ++k)
+    {
+      S.quads[k] = ctx->quads[(size_t)aa[k].prim]; // attributes (normal, material) of the AA quad, same slot
+      aa[k].slot = (int32_t)k;
+      S.aa[k] = aa[k];
+      for (int c = aa[k].cls & 7; c < 6; ++c)
+        S.aaEnd[c] = (int32_t)k + 1;
+    }
+    size_t slot = aa.size();
+    for (int pass = 0; pass < 2; ++pass) // planar boxed quads first, non-planar last (DESIGN.md "leaf-box gate")
+      for (int32_t k : (pass == 0 ? boxedPlanar : boxedNonPlanar))
+      {
+        S.quads[slot] = ctx->quads[(size_t)k];
+        S.gate[S.nGate] = ctx->boxes[(size_t)k];
+        S.gate[S.nGate].quad = (int32_t)slot;
+        S.quads[slot].gate = ++S.nGate;
+        ++slot;
+      }
     for (int64_t s = 0; s < ctx->nSph; ++s)
       ctx->small.sph[s] = ctx->sph[(size_t)s];
     return B2PT_OK;
@@ -621,7 +700,7 @@ static int64_t batch_target_paths()
     if (v > 0)
       return v;
   }
-  return (int64_t)1 << 25; // 32 Mi paths in flight: 2 queues x 48 B + 16 B radiance = 3.6 GB of the 180 GB HBM
+  return (int64_t)1 << 25; // 32 Mi paths in flight: queue 48 B + 4 bins x 52 B + radiance 16 B = 9.1 GB of 180 GB HBM
 }
 
 int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDepth, uint32_t flags)
@@ -643,7 +722,7 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
     return fail(B2PT_ERR_BAD_VALUE, "REFERENCE_STREAM renders samples from 0 (one persistent stream per pixel)");
   // MapperPathTracer::RenderCellsImpl builds its acceleration structures on every call (:275-276); here
   // they are rebuilt only when the scene or the build-affecting flags changed.
-  const uint32_t buildFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP);
+  const uint32_t buildFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA);
   if (!ctx->haveBvh || ctx->builtFlags != buildFlags)
   {
     if (int rc = build_trace_structures(ctx, buildFlags))
@@ -661,11 +740,24 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
   const int64_t nBatches = sampleCount == 0 ? 0 : (sampleCount + B - 1) / B;
   const int64_t pathsPerBatch = N * B;
 
-  for (int k = 0; k < 2; ++k)
-    for (int p = 0; p < 3; ++p)
-      CU(ctx->queue[k][p].reserve((size_t)pathsPerBatch));
+  // Static partition of the queue and the bins into one region per persistent warp (b2pt_types.h).
+  const int blocksPerSM = std::min(ctx->cfg.traceBlocksPerSM[0][ctx->useBvh ? 1 : 0],
+                                   ctx->cfg.shadeBlocksPerSM[0][ctx->useBvh ? 1 : 0]);
+  const int wpb = b2pt::warps_per_block();
+  int64_t numWarps = (int64_t)ctx->cfg.numSMs * blocksPerSM * wpb;
+  numWarps = std::max<int64_t>(wpb, std::min<int64_t>(numWarps, ((pathsPerBatch + 31) / 32 + wpb - 1) / wpb * wpb));
+  int64_t regionCap = (pathsPerBatch + numWarps - 1) / numWarps;
+  regionCap = std::max<int64_t>(32, (regionCap + 31) / 32 * 32);
+  const int64_t queueCap = numWarps * regionCap;
+  for (int p = 0; p < 3; ++p)
+  {
+    CU(ctx->queue[p].reserve((size_t)queueCap));
+    CU(ctx->bins[p].reserve((size_t)queueCap * 4));
+  }
+  CU(ctx->binCode.reserve((size_t)queueCap * 4));
+  CU(ctx->regionCounts.reserve((size_t)numWarps * 5));
   CU(ctx->rad.reserve((size_t)pathsPerBatch));
-  const int64_t nCounters = std::max<int64_t>(1, nBatches * maxDepth);
+  const int64_t nCounters = std::max<int64_t>(1, nBatches * maxDepth); // rays entering bounce d+1, per batch
   CU(ctx->counters.reserve((size_t)nCounters));
   CU(ctx->nanCounter.reserve(1));
   CU(cudaEventRecord(ctx->evStart, ctx->stream));
@@ -686,8 +778,16 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
     const int64_t s0 = batch * B;
     const int64_t nb = std::min<int64_t>(B, sampleCount - s0);
     B2RenderArgs A{};
-    A.counters = ctx->counters.p + batch * maxDepth;
+    A.depthTotals = ctx->counters.p + batch * maxDepth;
     A.rad = ctx->rad.p;
+    A.bin0 = ctx->bins[0].p, A.bin1 = ctx->bins[1].p, A.bin2 = ctx->bins[2].p;
+    A.binCode = ctx->binCode.p;
+    A.binStride = queueCap;
+    A.q = { ctx->queue[0].p, ctx->queue[1].p, ctx->queue[2].p };
+    A.qCount = ctx->regionCounts.p;
+    A.binCount = ctx->regionCounts.p + numWarps;
+    A.numWarps = (int32_t)numWarps;
+    A.regionCap = (int32_t)regionCap;
     A.seeds = ctx->seeds.p;
     A.nPaths = N * nb;
     A.nPixels = (int32_t)N;
@@ -704,12 +804,9 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
         CU(cudaEventRecord(ctx->evBounce[depth], ctx->stream));
       }
       A.depth = depth;
-      const int in = (depth + 1) & 1, out = depth & 1;
-      A.qin = { ctx->queue[in][0].p, ctx->queue[in][1].p, ctx->queue[in][2].p };
-      A.qout = { ctx->queue[out][0].p, ctx->queue[out][1].p, ctx->queue[out][2].p };
       CU(b2pt::launch_bounce(ctx->cfg, depth == 0, ctx->cam, ctx->useBvh ? nullptr : &ctx->small,
                              ctx->useBvh ? &ctx->bvh : nullptr, ctx->lights, A, A.nPaths, ctx->stream));
-      ++launches;
+      launches += 2;
     }
     CU(b2pt::launch_accumulate(ctx->color(), ctx->rad.p, (int)N, (int)nb, ctx->nanCounter.p, ctx->stream));
     ++launches;
@@ -769,10 +866,11 @@ int b2pt_get_stats(b2pt_ctx* ctx, b2pt_stats* out)
                     cudaMemcpyDeviceToHost));
     int64_t seg = ctx->stats.paths; // every path traces its primary segment
     for (int64_t k = 0; k < ctx->pendingCounters; ++k)
-      seg += ctx->hCounters[(size_t)k]; // counters[d] = rays entering bounce d+1 (0 for the last depth)
+      seg += ctx->hCounters[(size_t)k]; // rays entering bounce d+1 (0 for the last depth)
     ctx->stats.segments = seg;
-    // queue traffic: each survivor is written once (48 B) and read once (48 B); radiance 16 B written + read per path
-    ctx->stats.queueBytes = (seg - ctx->stats.paths) * 96 + ctx->stats.paths * 32;
+    // queue traffic: a survivor is written (48 B) and read (48 B) on the ray queue and once more as a binned
+    // ray+hit record (52 B written, 52 B read); radiance 16 B written + read per path
+    ctx->stats.queueBytes = (seg - ctx->stats.paths) * 96 + seg * 104 + ctx->stats.paths * 32;
     unsigned long long nan = 0;
     CU(cudaMemcpy(&nan, ctx->nanCounter.p, sizeof(nan), cudaMemcpyDeviceToHost));
     ctx->stats.nanSamples = (int64_t)nan;

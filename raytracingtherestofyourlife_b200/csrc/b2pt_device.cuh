@@ -126,14 +126,16 @@ __device__ __forceinline__ f3 raygen(const B2Camera& cam, int pixel, uint32_t& s
 // downstream and are not computed).  Returns true iff the reference's hit() returns true; t is valid then.
 __device__ __forceinline__ bool quad_hit(const B2Quad& Q, f3 o, f3 d, float& t)
 {
-  f3 E03 = ld3(Q.e03);
+  const float4* q4 = reinterpret_cast<const float4*>(&Q);
+  const float4 c0 = q4[0], c1 = q4[1], c2 = q4[2]; // v00 e01 | e01 e03 | e03 v11
+  const f3 E03 = mk3(c1.z, c1.w, c2.x);
   f3 P = cross3(d, E03);
-  f3 E01 = ld3(Q.e01);
+  const f3 E01 = mk3(c0.w, c1.x, c1.y);
   float det = dot3(E01, P);
   if (fabsf(det) < 1e-5f) // vtkm::Epsilon<Float32>()
     return false;
   float inv_det = 1.0f / det;
-  f3 T = o - ld3(Q.v00);
+  f3 T = o - mk3(c0.x, c0.y, c0.z);
   float alpha = dot3(T, P) * inv_det;
   if (alpha < 0.0f)
     return false;
@@ -143,14 +145,15 @@ __device__ __forceinline__ bool quad_hit(const B2Quad& Q, f3 o, f3 d, float& t)
     return false;
   if ((alpha + beta) > 1.0f)
   {
-    f3 E23 = ld3(Q.e23);
-    f3 E21 = ld3(Q.e21);
+    const float4 c3 = q4[3], c4 = q4[4]; // v11 e21 | e21 e23 nrm
+    const f3 E23 = mk3(c3.w, c4.x, c4.y);
+    const f3 E21 = mk3(c3.x, c3.y, c3.z);
     f3 Pp = cross3(d, E21);
     float detp = dot3(E23, Pp);
     if (fabsf(detp) < 1e-5f)
       return false;
     float inv_detp = 1.0f / detp;
-    f3 Tp = o - ld3(Q.v11);
+    f3 Tp = o - mk3(c2.y, c2.z, c2.w);
     float alphap = dot3(Tp, Pp) * inv_detp;
     if (alphap < 0.0f)
       return false;
@@ -231,34 +234,131 @@ struct Hit
   int mat, texi;
 };
 
+// Lagae-Dutre test of an axis-aligned rectangle in its permuted frame (u,v,n): the operations of quad_hit
+// that do not multiply by an exact zero, in the same order, so the result is bit-identical (see B2AAQuad).
+// Branch-free up to the second-triangle part.  NaN handling follows the reference's comparisons.
+__device__ __forceinline__ bool aa_quad_hit(const B2AAQuad& Q, float du, float dv, float dn, float ou, float ov,
+                                            float on, float& t)
+{
+  // three broadcast 16-byte loads (LDS.128 when the scene is staged in shared memory)
+  const float4* q4 = reinterpret_cast<const float4*>(&Q);
+  const float4 c0 = q4[0]; // v00u v00v v00n bPu
+  const float4 c1 = q4[1]; // v11u v11v v11n bPn
+  const float4 c2 = q4[2]; // a aQv aQn b
+  const float Pu = dn * c0.w, Pn = du * c1.w;
+  const float det = c2.x * Pu;
+  const float Tu = ou - c0.x, Tv = ov - c0.y, Tn = on - c0.z;
+  const float x1 = Tu * Pu, x2 = Tn * Pn;
+  const float TP = x1 + x2;
+  const float Qv = Tn * c2.y, Qn = Tv * c2.z;
+  const float y1 = dv * Qv, y2 = dn * Qn;
+  const float DQ = y1 + y2;
+  const float inv_det = 1.0f / det;
+  const float alpha = TP * inv_det;
+  const float beta = DQ * inv_det;
+  t = (c2.w * Qv) * inv_det;
+  bool ok = !(fabsf(det) < 1e-5f) && !(alpha < 0.0f) && !(beta < 0.0f) && !(t < 0.0f);
+  if (ok && (alpha + beta) > 1.0f)
+  {
+    // Second-triangle test (Surface.h:72-98).  For a consistent rectangle (host-verified: a2 = -a, b2 = -b,
+    // v11 = v00 + E01 + E03 to 2e-6) its barycentrics are alpha' = 1 - alpha, beta' = 1 - beta in exact
+    // arithmetic, and the float evaluations of alpha, beta, alpha', beta' are each within
+    // u*(4R+14), u = 2^-24, of their exact values, R = (|x1|+|x2|)/|det| resp. (|y1|+|y2|)/|det| (standard
+    // forward error of the two-term sums and the division).  Outside a band E = 1e-6*R + 1e-5 > 2x that
+    // bound around 1 the outcome of the exact test is therefore known; only inside the band is it evaluated.
+    const float ainv = fabsf(inv_det);
+    const float Ea = __fmaf_rn(1e-6f, (fabsf(x1) + fabsf(x2)) * ainv, 1e-5f);
+    const float Eb = __fmaf_rn(1e-6f, (fabsf(y1) + fabsf(y2)) * ainv, 1e-5f);
+    const bool rect = Q.cls >= 8;
+    const bool sureOut = rect && (alpha > 1.0f + Ea || beta > 1.0f + Eb);
+    const bool sureIn = rect && alpha < 1.0f - Ea && beta < 1.0f - Eb && fabsf(det) > 1.1e-5f;
+    if (sureOut)
+      ok = false;
+    else if (!sureIn)
+    {
+      const float4 c3 = q4[3]; // a2 b2Pu b2Pn a2Qv
+      const float a2Qn = Q.a2Qn;
+      const float Ppu = dn * c3.y, Ppn = du * c3.z;
+      const float detp = c3.x * Ppu;
+      const float Tpu = ou - c1.x, Tpv = ov - c1.y, Tpn = on - c1.z;
+      const float inv_detp = 1.0f / detp;
+      const float alphap = (Tpu * Ppu + Tpn * Ppn) * inv_detp;
+      const float betap = (dv * (Tpn * c3.w) + dn * (Tpv * a2Qn)) * inv_detp;
+      ok = !(fabsf(detp) < 1e-5f) && !(alphap < 0.0f) && !(betap < 0.0f);
+    }
+  }
+  return ok;
+}
+
+// (u,v,n) component selection for class c (B2AAQuad::cls & 7); c is warp-uniform.
+__device__ __forceinline__ void aa_permute(int c, f3 a, float& u, float& v, float& n)
+{
+  switch (c & 7)
+  {
+    case 0: u = a.x, v = a.y, n = a.z; break;
+    case 1: u = a.y, v = a.z, n = a.x; break;
+    case 2: u = a.z, v = a.x, n = a.y; break;
+    case 3: u = a.y, v = a.x, n = a.z; break;
+    case 4: u = a.x, v = a.z, n = a.y; break;
+    default: u = a.z, v = a.y, n = a.x; break;
+  }
+}
+
 // Closest hit over a kernel-parameter-resident scene.  MapperPathTracer.cxx:410-435: quads first
 // (QuadIntersector.cxx:59-71), then spheres continuing from the quads' closest distance
-// (SphereIntersector.cxx:88-100); strict t<tmax keeps the first-tested primitive on exact ties.
-__device__ __forceinline__ bool trace_small(const B2SmallScene& S, f3 o, f3 d, float tmin, float tmax, Hit& h)
+// (SphereIntersector.cxx:88-100).  The reference's strict t<tmax keeps the first-tested primitive on an
+// exact-t tie; quads are tested here in a different order (axis-aligned classes, then boxed quads), so a tie
+// is resolved explicitly in favour of the lower original index -- the same winner as index order.
+#define B2PT_MISS 0x7fffffff
+__device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, float tmin, float tmax, float& tHit)
 {
   float closest = tmax;
   int slot = -1;
-  f3 inv = mk3(0.f, 0.f, 0.f), od = mk3(0.f, 0.f, 0.f);
-  if (S.nGate > 0)
-  { // BVHTraverser.h:143-157
-    inv = mk3(rcp_safe(d.x), rcp_safe(d.y), rcp_safe(d.z));
-    od = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
-  }
-  for (int q = 0; q < S.nQuads; ++q)
+  int bestPrim = 0x7fffffff;
+  // ---- axis-aligned rectangles: specialised bit-identical test, one class (component permutation) at a time
+  int qb = 0;
+  for (int c = 0; c < 6; ++c)
   {
-    float t;
-    const int gate = S.quads[q].gate;
-    if (gate > 0)
-    { // leaf-box gate of the reference's BVH for non-planar quads (warp-uniform branch); the host orders
-      // gated quads after all planar ones
-      float tn;
-      if (!slab_hit(S.gate[gate - 1].bmin, S.gate[gate - 1].bmax, inv, od, tmin, closest, tn))
-        continue;
-    }
-    if (quad_accept(S.quads[q], o, d, tmin, closest, t))
+    const int qe = S.aaEnd[c];
+    if (qe > qb)
     {
-      closest = t;
-      slot = q;
+      float du, dv, dn, ou, ov, on;
+      aa_permute(c, d, du, dv, dn);
+      aa_permute(c, o, ou, ov, on);
+      for (int q = qb; q < qe; ++q)
+      {
+        const B2AAQuad& Q = S.aa[q];
+        float t;
+        const bool hit = aa_quad_hit(Q, du, dv, dn, ou, ov, on, t);
+        if (hit && t > tmin && (t < closest || (t == closest && Q.prim < bestPrim)))
+        {
+          closest = t;
+          slot = Q.slot;
+          bestPrim = Q.prim;
+        }
+      }
+    }
+    qb = qe;
+  }
+  // ---- remaining quads behind the slab test of their own leaf box (BVHTraverser.h:35-79, 143-157)
+  if (S.firstBoxed < S.nQuads)
+  {
+    const f3 inv = mk3(rcp_safe(d.x), rcp_safe(d.y), rcp_safe(d.z));
+    const f3 od = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+    for (int q = S.firstBoxed; q < S.nQuads; ++q)
+    {
+      const B2Quad& Q = S.quads[q];
+      float tn, t;
+      if (!slab_hit(S.gate[Q.gate - 1].bmin, S.gate[Q.gate - 1].bmax, inv, od, tmin, closest, tn))
+        continue;
+      // non-planar quads (pad[0] != 0) come last and only win with a strictly smaller t, like the oracle
+      if (quad_hit(Q, o, d, t) && t > tmin &&
+          (t < closest || (t == closest && Q.pad[0] == 0 && Q.prim < bestPrim)))
+      {
+        closest = t;
+        slot = q;
+        bestPrim = Q.prim;
+      }
     }
   }
   for (int s = 0; s < S.nSph; ++s)
@@ -270,12 +370,12 @@ __device__ __forceinline__ bool trace_small(const B2SmallScene& S, f3 o, f3 d, f
       slot = S.nQuads + s;
     }
   }
-  if (slot < 0)
-  {
-    h.prim = -1;
-    h.t = closest;
-    return false;
-  }
+  tHit = closest;
+  return slot < 0 ? B2PT_MISS : slot;
+}
+// Hit record of the winning primitive (Surface.h:180-192, :334-345): point, normal, material.
+__device__ __forceinline__ void fill_small(const B2SmallScene& S, int slot, f3 o, f3 d, float closest, Hit& h)
+{
   h.t = closest;
   h.p = o + d * closest; // Surface.h:187, :334
   if (slot < S.nQuads)
@@ -299,7 +399,6 @@ __device__ __forceinline__ bool trace_small(const B2SmallScene& S, f3 o, f3 d, f
     h.mat = SP.mat;
     h.texi = SP.texi;
   }
-  return true;
 }
 
 // Closest hit by stack traversal of the 32-byte-node BVH (one tree for quads and spheres).  A stack entry
@@ -311,7 +410,7 @@ __device__ __forceinline__ uint32_t bvh_pack(float leftBits, float countBits)
 {
   return ((uint32_t)__float_as_int(countBits) << 24) | (uint32_t)__float_as_int(leftBits);
 }
-__device__ __forceinline__ bool trace_bvh(const B2BvhScene& S, f3 o, f3 d, float tmin, float tmax, Hit& h)
+__device__ __forceinline__ int closest_bvh(const B2BvhScene& S, f3 o, f3 d, float tmin, float tmax, float& tHit)
 {
   f3 inv = mk3(rcp_safe(d.x), rcp_safe(d.y), rcp_safe(d.z));
   f3 od = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
@@ -401,12 +500,12 @@ __device__ __forceinline__ bool trace_bvh(const B2BvhScene& S, f3 o, f3 d, float
       found = true;
     }
   }
+  tHit = closest;
+  return found ? best : B2PT_MISS;
+}
+__device__ __forceinline__ void fill_bvh(const B2BvhScene& S, int best, f3 o, f3 d, float closest, Hit& h)
+{
   h.t = closest;
-  if (!found)
-  {
-    h.prim = -1;
-    return false;
-  }
   h.p = o + d * closest;
   if (best >= 0)
   {
@@ -429,16 +528,47 @@ __device__ __forceinline__ bool trace_bvh(const B2BvhScene& S, f3 o, f3 d, float
     h.mat = SP.mat;
     h.texi = SP.texi;
   }
-  return true;
 }
 
-__device__ __forceinline__ bool trace(const B2SmallScene& S, f3 o, f3 d, float tmin, float tmax, Hit& h)
+__device__ __forceinline__ int closest_hit(const B2SmallScene& S, f3 o, f3 d, float tmin, float tmax, float& t)
 {
-  return trace_small(S, o, d, tmin, tmax, h);
+  return closest_small(S, o, d, tmin, tmax, t);
 }
-__device__ __forceinline__ bool trace(const B2BvhScene& S, f3 o, f3 d, float tmin, float tmax, Hit& h)
+__device__ __forceinline__ int closest_hit(const B2BvhScene& S, f3 o, f3 d, float tmin, float tmax, float& t)
 {
-  return trace_bvh(S, o, d, tmin, tmax, h);
+  return closest_bvh(S, o, d, tmin, tmax, t);
+}
+__device__ __forceinline__ void fill_hit(const B2SmallScene& S, int code, f3 o, f3 d, float t, Hit& h)
+{
+  fill_small(S, code, o, d, t, h);
+}
+__device__ __forceinline__ void fill_hit(const B2BvhScene& S, int code, f3 o, f3 d, float t, Hit& h)
+{
+  fill_bvh(S, code, o, d, t, h);
+}
+// material kind (matType) of the primitive behind a closest-hit code
+__device__ __forceinline__ int hit_kind(const B2SmallScene& S, int slot)
+{
+  return slot < S.nQuads ? S.quads[slot].kind : S.sph[slot - S.nQuads].kind;
+}
+__device__ __forceinline__ int hit_kind(const B2BvhScene& S, int code)
+{
+  return code >= 0 ? S.quads[code].kind : S.sph[~code].kind;
+}
+// closest hit + hit record in one call (stage-level kernels)
+template <class SceneT>
+__device__ __forceinline__ bool trace(const SceneT& S, f3 o, f3 d, float tmin, float tmax, Hit& h)
+{
+  float t;
+  const int code = closest_hit(S, o, d, tmin, tmax, t);
+  if (code == B2PT_MISS)
+  {
+    h.prim = -1;
+    h.t = t;
+    return false;
+  }
+  fill_hit(S, code, o, d, t, h);
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------ shading
@@ -487,7 +617,17 @@ __device__ __forceinline__ f3 random_to_sphere(float radius, float dist2, float 
 __device__ __forceinline__ float quad_pdf_value(const B2LightQuad& L, f3 o, f3 v)
 {
   float t;
-  if (!quad_accept(L.geo, o, v, 0.001f, FLT_MAX, t))
+  bool h;
+  if (L.aa.cls >= 0)
+  { // axis-aligned light quad: bit-identical specialised test (warp-uniform branch)
+    float du, dv, dn, ou, ov, on;
+    aa_permute(L.aa.cls, v, du, dv, dn);
+    aa_permute(L.aa.cls, o, ou, ov, on);
+    h = aa_quad_hit(L.aa, du, dv, dn, ou, ov, on, t);
+  }
+  else
+    h = quad_hit(L.geo, o, v, t);
+  if (!(h && t < FLT_MAX && t > 0.001f))
     return 0.f;
   f3 n = quad_normal(L.geo, v);
   float dist2 = t * t * dot3(v, v);
@@ -549,38 +689,14 @@ enum BounceResult
   BOUNCE_DONE = 1
 };
 
-// One bounce of one live path in forward (throughput) form: the reference's per-depth worklet chain
-//   intersect + CollectIntersect (MapperPathTracer.cxx:410-435, SurfaceWorklets.h:98-111)
-//   Lambertian / DiffuseLight / Dielectric (EmitWorklet.h:46-73, 112-135, 244-272)
-//   Which / Cosine / Quad / Sphere generators (PdfWorklet.h:19-21, 63-79, 112-137, 193-213)
-//   QuadPDF / SpherePDF / PDFCosine (PdfWorklet.h:274-316, 374-399; ScatterWorklet.h:67-117)
-// fused, with the depth-layer compositing of MapperPathTracer.cxx:328-348 carried as throughput T.
-// Draw order while alive is the reference's (SURVEY A.3).  On BOUNCE_DONE, L holds the path's radiance.
-template <class SceneT>
-__device__ __forceinline__ BounceResult bounce(const SceneT& scene, const B2Lights& lights, f3& o, f3& d, f3& T,
-                                               uint32_t& rng, uint32_t flags, f3& L, Hit& hit)
+// Lambertian bounce: strategy choice, direction generator, light pdfs, mixture pdf, throughput, next ray
+// (PdfWorklet.h:19-21, 63-79, 112-137, 193-213, 274-316, 374-399; ScatterWorklet.h:67-117).
+// `which` is re-drawn here from the path's RNG state; when the caller binned rays by strategy (k_trace) it is
+// the same for the whole warp and the three generator branches do not diverge.
+__device__ __forceinline__ BounceResult shade_lambert(const B2Lights& lights, const Hit& hit, f3& o, f3& d, f3& T,
+                                                      uint32_t& rng, uint32_t flags, f3& L)
 {
-  if (!trace(scene, o, d, 0.001f, FLT_MAX, hit))
-  {
-    L = T * 0.f; // a[d]=1, e[d]=0: radiance 0, NaN/Inf throughput still poisons the pixel like the reference
-    return BOUNCE_DONE;
-  }
-  if (hit.kind == 1)
-  { // DiffuseLightWorklet::emit: front face only, but the normal was already flipped -> two-sided
-    f3 em = (dot3(hit.n, d) < 0.0f) ? hit.alb : mk3(0.f, 0.f, 0.f);
-    L = mul3(T, em);
-    return BOUNCE_DONE;
-  }
-  bool specular = false;
-  f3 sdir = mk3(0.f, 0.f, 0.f);
-  if (hit.kind == 2)
-  {
-    float r = randf(rng);
-    sdir = dielectric_scatter(d, hit.n, lights.refIdx, r);
-    specular = true;
-  }
-  // direction generators (always consume their draws, even for specular hits)
-  int which = draw_which(rng);
+  const int which = draw_which(rng);
   f3 g;
   if (which <= 1)
   {
@@ -619,12 +735,6 @@ __device__ __forceinline__ BounceResult bounce(const SceneT& scene, const B2Ligh
     }
   }
   wang32(rng); // SpherePDFWorklet's unused index draw (PdfWorklet.h:393)
-  if (specular)
-  { // ScatterWorklet.h:82-92: attenuation = srec.A = 1
-    o = hit.p;
-    d = sdir;
-    return BOUNCE_CONTINUE;
-  }
   // light pdfs: sum = weight*quad + weight*sphere (no occlusion test in either)
   float sum = 0.f;
   for (int l = 0; l < lights.nLightQuads; ++l)
@@ -648,6 +758,44 @@ __device__ __forceinline__ BounceResult bounce(const SceneT& scene, const B2Ligh
     return BOUNCE_DONE;
   }
   return BOUNCE_CONTINUE;
+}
+
+// One bounce of one live path in forward (throughput) form: the reference's per-depth worklet chain
+//   intersect + CollectIntersect (MapperPathTracer.cxx:410-435, SurfaceWorklets.h:98-111)
+//   Lambertian / DiffuseLight / Dielectric (EmitWorklet.h:46-73, 112-135, 244-272)
+//   Which / Cosine / Quad / Sphere generators (PdfWorklet.h:19-21, 63-79, 112-137, 193-213)
+//   QuadPDF / SpherePDF / PDFCosine (PdfWorklet.h:274-316, 374-399; ScatterWorklet.h:67-117)
+// fused, with the depth-layer compositing of MapperPathTracer.cxx:328-348 carried as throughput T.
+// Draw order while alive is the reference's (SURVEY A.3).  On BOUNCE_DONE, L holds the path's radiance.
+__device__ __forceinline__ BounceResult shade(const B2Lights& lights, bool found, const Hit& hit, f3& o, f3& d, f3& T,
+                                              uint32_t& rng, uint32_t flags, f3& L)
+{
+  if (!found)
+  {
+    L = T * 0.f; // a[d]=1, e[d]=0: radiance 0, NaN/Inf throughput still poisons the pixel like the reference
+    return BOUNCE_DONE;
+  }
+  if (hit.kind == 1)
+  { // DiffuseLightWorklet::emit: front face only, but the normal was already flipped -> two-sided
+    f3 em = (dot3(hit.n, d) < 0.0f) ? hit.alb : mk3(0.f, 0.f, 0.f);
+    L = mul3(T, em);
+    return BOUNCE_DONE;
+  }
+  if (hit.kind == 2)
+  { // DielectricWorklet (EmitWorklet.h:244-272): one draw, specular ray, attenuation 1.  The direction
+    // generators and the sphere-pdf worklet still run for such a pixel and consume their draws
+    // (which 1, generator 2 / 3 per light quad / 2 per light sphere, pdf index 1); their outputs are unused.
+    const float r = randf(rng);
+    const f3 sdir = dielectric_scatter(d, hit.n, lights.refIdx, r);
+    const int which = draw_which(rng);
+    const int burn = (which <= 1) ? 2 : (which == 2 ? 3 * lights.nLightQuads : 2 * lights.nLightSph);
+    for (int k = 0; k < burn + 1; ++k)
+      wang32(rng);
+    o = hit.p;
+    d = sdir;
+    return BOUNCE_CONTINUE;
+  }
+  return shade_lambert(lights, hit, o, d, T, rng, flags, L);
 }
 
 } // namespace b2pt

@@ -23,107 +23,279 @@ namespace b2pt
 
 constexpr int kBlock = 256;
 constexpr int kWarps = kBlock / 32;
+#ifndef B2PT_MIN_BLOCKS
+#define B2PT_MIN_BLOCKS 4
+#endif
+constexpr int kMinBlocksPerSM = B2PT_MIN_BLOCKS; // register cap = 65536 / (256 * blocks)
+#ifndef B2PT_TRACE_MIN_BLOCKS
+#define B2PT_TRACE_MIN_BLOCKS 4
+#endif
+constexpr int kTraceMinBlocksPerSM = B2PT_TRACE_MIN_BLOCKS;
 
 struct PeerPtrs
 {
   const float4* p[8];
 };
 
-__device__ __forceinline__ void store_ray(const B2Queue& q, uint32_t pos, f3 o, f3 d, f3 T, uint32_t pid, uint32_t rng)
+__device__ __forceinline__ void store_ray(const B2Queue& q, int64_t pos, f3 o, f3 d, f3 T, uint32_t pid, uint32_t rng)
 {
   q.p0[pos] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
   q.p1[pos] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
   q.p2[pos] = make_uint4(__float_as_uint(T.z), pid, rng, 0u);
 }
 
-template <bool PRIMARY, class SceneT>
-__global__ void __launch_bounds__(kBlock)
-  k_bounce(const __grid_constant__ B2Camera cam, const __grid_constant__ SceneT scene,
-           const __grid_constant__ B2Lights lights, const __grid_constant__ B2RenderArgs A)
+// Shared-memory staging of the per-launch tables.  The small scene (about 11 KB) and the light tables are
+// copied; a BVH scene is a handful of pointers and stays in the parameter bank.
+template <class SceneT>
+struct StageArea
 {
-  __shared__ uint32_t sWarp[kWarps];
-  __shared__ uint32_t sBase;
+  B2Lights lights;
+};
+template <>
+struct StageArea<B2SmallScene>
+{
+  B2SmallScene scene;
+  B2Lights lights;
+};
+template <class T>
+__device__ __forceinline__ void stage_copy(T& dst, const T& src)
+{
+  static_assert(sizeof(T) % 16 == 0, "staged tables are multiples of 16 bytes");
+  uint4* d = reinterpret_cast<uint4*>(&dst);
+  const uint4* s = reinterpret_cast<const uint4*>(&src);
+  for (int i = threadIdx.x; i < (int)(sizeof(T) / 16); i += blockDim.x)
+    d[i] = s[i];
+}
+__device__ __forceinline__ const B2SmallScene& stage_scene(const B2SmallScene& scene, StageArea<B2SmallScene>& a)
+{
+  stage_copy(a.scene, scene);
+  return a.scene;
+}
+__device__ __forceinline__ const B2BvhScene& stage_scene(const B2BvhScene& scene, StageArea<B2BvhScene>&)
+{
+  return scene;
+}
+template <class SceneT>
+__device__ __forceinline__ const B2Lights& stage_lights(const B2Lights& lights, StageArea<SceneT>& a)
+{
+  stage_copy(a.lights, lights);
+  return a.lights;
+}
 
-  const int64_t nIn = PRIMARY ? A.nPaths : (int64_t)A.counters[A.depth - 1];
-  const bool lastDepth = (A.depth == A.maxDepth - 1);
-  const bool refStream = (A.flags & B2PT_FLAG_REFERENCE_STREAM_DEV) != 0;
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-
-  for (int64_t tile = blockIdx.x; tile * kBlock < nIn; tile += gridDim.x)
+// Ray `idx` of the warp's region.  PRIMARY: generated from (pixel, sample) -- idx is the path id.
+template <bool PRIMARY>
+__device__ __forceinline__ void load_ray(const B2Camera& cam, const B2RenderArgs& A, int64_t idx, f3& o, f3& d, f3& T,
+                                         uint32_t& pid, uint32_t& rng)
+{
+  if (PRIMARY)
   {
-    const int64_t idx = tile * kBlock + threadIdx.x;
-    bool survive = false;
+    pid = (uint32_t)idx; // path id chosen by the caller (tile-interleaved over the warps' regions)
+    const uint32_t pixel = pid % (uint32_t)A.nPixels;
+    const uint32_t b = pid / (uint32_t)A.nPixels;
+    // MapperPathTracer.cxx:265-267: seeds[i] = i.  Production stream: one stream per (pixel, sample).
+    rng = (A.flags & B2PT_FLAG_REFERENCE_STREAM_DEV)
+      ? A.seeds[pixel]
+      : pixel + A.seedOffset + (uint32_t)(A.sampleBase + (int)b) * B2PT_GOLDEN;
+    d = raygen(cam, (int)pixel, rng);
+    o = ld3(cam.pos);
+    T = mk3(1.f, 1.f, 1.f);
+  }
+  else
+  {
+    const uint4 a = A.q.p0[idx];
+    const uint4 b = A.q.p1[idx];
+    const uint4 c = A.q.p2[idx];
+    o = mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
+    d = mk3(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
+    T = mk3(__uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(c.x));
+    pid = c.y;
+    rng = c.z;
+  }
+}
+
+// Finished path: radiance written once; in reference-stream mode the pixel's persistent RNG state is advanced
+// past the draws the reference still consumes for a dead pixel.
+__device__ __forceinline__ void finish_path(const B2RenderArgs& A, uint32_t pid, f3 L, uint32_t rng, bool refStream,
+                                            int depthsToBurn)
+{
+  A.rad[pid] = make_float4(L.x, L.y, L.z, 0.f);
+  if (refStream)
+  {
+    burn_depths(rng, depthsToBurn);
+    A.seeds[pid % (uint32_t)A.nPixels] = rng;
+  }
+}
+
+// K1+K2 (+ the sorting half of K5): closest hit of every ray of the warp's queue region (PRIMARY: of freshly
+// generated camera rays).  Paths that miss or land on an emitter finish here (their radiance is final); every
+// other hit is binned by what the shade stage will do with it -- bin 0: specular (dielectric) hit, bins 1..3:
+// lambertian hit whose strategy draw selects the cosine / light-quad / sphere generator -- so that k_shade runs
+// warp-uniform work with all 32 lanes alive.  The ray AND its hit (t, primitive) are appended to the warp's
+// region of the bin as one dense 52-byte record (coalesced 16-byte stores): ballot + popcount prefix on top of
+// a register counter, no atomics.
+template <bool PRIMARY, class SceneT>
+__global__ void __launch_bounds__(kBlock, kTraceMinBlocksPerSM)
+  k_trace(const __grid_constant__ B2Camera cam, const __grid_constant__ SceneT scene,
+          const __grid_constant__ B2RenderArgs A)
+{
+  const int w = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int64_t base = (int64_t)w * A.regionCap;
+  // PRIMARY: the batch's 32-path tiles are dealt round-robin to the warps (tile j of warp w is global tile
+  // j*numWarps + w), so every region samples the whole image and the regions shrink at the same rate;
+  // contiguous pixel ranges would leave the regions that cover the image border (rays that miss) empty.
+  const int64_t tilesTotal = (A.nPaths + 31) >> 5;
+  int64_t nIn;
+  if (PRIMARY)
+    nIn = w < A.numWarps && tilesTotal > w ? ((tilesTotal - 1 - w) / A.numWarps + 1) * 32 : 0;
+  else
+    nIn = w < A.numWarps ? (int64_t)A.qCount[w] : 0;
+  // CTAs whose eight regions are all empty (deep bounces) leave before staging the scene.
+  if (!__syncthreads_or(nIn > 0))
+  {
+    if (w < A.numWarps && lane == 0)
+      for (int k = 0; k < 4; ++k)
+        A.binCount[k * A.numWarps + w] = 0;
+    return;
+  }
+  __shared__ StageArea<SceneT> sStage;
+  const SceneT& S = stage_scene(scene, sStage);
+  __syncthreads();
+  if (w >= A.numWarps)
+    return;
+  const bool refStream = (A.flags & B2PT_FLAG_REFERENCE_STREAM_DEV) != 0;
+  uint32_t cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
+  for (int64_t i0 = 0; i0 < nIn; i0 += 32)
+  {
+    const int64_t i = i0 + lane;
+    int bin = -1;
     f3 o, d, T;
     uint32_t pid = 0, rng = 0;
-    if (idx < nIn)
+    float t = 0.f;
+    int code = B2PT_MISS;
+    const int64_t idx = PRIMARY ? (((i0 >> 5) * A.numWarps + w) << 5) + lane : base + i;
+    if (PRIMARY ? idx < A.nPaths : i < nIn)
     {
-      if (PRIMARY)
-      {
-        pid = (uint32_t)idx;
-        const uint32_t pixel = pid % (uint32_t)A.nPixels;
-        const uint32_t b = pid / (uint32_t)A.nPixels;
-        // MapperPathTracer.cxx:265-267: seeds[i] = i.  Production stream: one stream per (pixel, sample).
-        rng = refStream ? A.seeds[pixel] : pixel + A.seedOffset + (uint32_t)(A.sampleBase + (int)b) * B2PT_GOLDEN;
-        d = raygen(cam, (int)pixel, rng);
-        o = ld3(cam.pos);
-        T = mk3(1.f, 1.f, 1.f);
-      }
+      load_ray<PRIMARY>(cam, A, idx, o, d, T, pid, rng);
+      code = closest_hit(S, o, d, 0.001f, FLT_MAX, t);
+      if (code == B2PT_MISS)
+        finish_path(A, pid, T * 0.f, rng, refStream, A.maxDepth - A.depth); // a[d]=1, e[d]=0
       else
       {
-        const uint4 a = A.qin.p0[idx];
-        const uint4 b = A.qin.p1[idx];
-        const uint4 c = A.qin.p2[idx];
+        const int kind = hit_kind(S, code);
+        if (kind == 1)
+        { // DiffuseLightWorklet::emit: front face only, but the normal was already flipped -> two-sided
+          Hit hit;
+          fill_hit(S, code, o, d, t, hit);
+          const f3 em = (dot3(hit.n, d) < 0.0f) ? hit.alb : mk3(0.f, 0.f, 0.f);
+          finish_path(A, pid, mul3(T, em), rng, refStream, A.maxDepth - A.depth);
+        }
+        else
+        {
+          uint32_t peek = rng;
+          bin = (kind == 2) ? 0 : draw_which(peek);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      const unsigned ballot = __ballot_sync(0xffffffffu, bin == k);
+      uint32_t& cnt = (k == 0 ? cnt0 : (k == 1 ? cnt1 : (k == 2 ? cnt2 : cnt3)));
+      if (bin == k)
+      {
+        const int64_t j = (int64_t)k * A.binStride + base + cnt + __popc(ballot & ((1u << lane) - 1u));
+        A.bin0[j] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
+        A.bin1[j] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
+        A.bin2[j] = make_uint4(__float_as_uint(T.z), pid, rng, __float_as_uint(t));
+        A.binCode[j] = (uint32_t)code;
+      }
+      cnt += __popc(ballot);
+    }
+  }
+  if (lane == 0)
+  {
+    A.binCount[0 * A.numWarps + w] = cnt0;
+    A.binCount[1 * A.numWarps + w] = cnt1;
+    A.binCount[2 * A.numWarps + w] = cnt2;
+    A.binCount[3 * A.numWarps + w] = cnt3;
+  }
+}
+
+// K3+K5: material response, direction generator, light pdfs, mixture pdf and the next ray for every binned hit
+// of the warp's regions; survivors are compacted into the warp's region of the ray queue.  A warp works on 32
+// consecutive records of ONE bin, so the strategy branch is warp-uniform.
+template <class SceneT>
+__global__ void __launch_bounds__(kBlock, kMinBlocksPerSM)
+  k_shade(const __grid_constant__ SceneT scene, const __grid_constant__ B2Lights lights,
+          const __grid_constant__ B2RenderArgs A)
+{
+  const int w = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int64_t base = (int64_t)w * A.regionCap;
+  uint32_t nAny = 0;
+  if (w < A.numWarps)
+    nAny = A.binCount[w] | A.binCount[A.numWarps + w] | A.binCount[2 * A.numWarps + w] | A.binCount[3 * A.numWarps + w];
+  if (!__syncthreads_or(nAny != 0))
+  { // nothing binned for any warp of this CTA: its queue regions become empty, no staging needed
+    if (w < A.numWarps && lane == 0)
+      A.qCount[w] = 0;
+    return;
+  }
+  __shared__ StageArea<SceneT> sStage;
+  const SceneT& S = stage_scene(scene, sStage);
+  const B2Lights& LT = stage_lights(lights, sStage);
+  __syncthreads();
+  if (w >= A.numWarps)
+    return;
+  const bool lastDepth = (A.depth == A.maxDepth - 1);
+  const bool refStream = (A.flags & B2PT_FLAG_REFERENCE_STREAM_DEV) != 0;
+  uint32_t qcnt = 0;
+  for (int k = 0; k < 4; ++k)
+  {
+    const int64_t nk = A.binCount[k * A.numWarps + w];
+    const int64_t binBase = (int64_t)k * A.binStride + base;
+    for (int64_t i0 = 0; i0 < nk; i0 += 32)
+    {
+      const int64_t i = i0 + lane;
+      bool survive = false;
+      f3 o, d, T;
+      uint32_t pid = 0, rng = 0;
+      if (i < nk)
+      {
+        const int64_t j = binBase + i;
+        const uint4 a = A.bin0[j], b = A.bin1[j], c = A.bin2[j];
         o = mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
         d = mk3(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
         T = mk3(__uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(c.x));
         pid = c.y;
         rng = c.z;
+        Hit hit;
+        fill_hit(S, (int)A.binCode[j], o, d, __uint_as_float(c.w), hit);
+        f3 L;
+        BounceResult r = (k == 0) ? shade(LT, true, hit, o, d, T, rng, A.flags, L)
+                                  : shade_lambert(LT, hit, o, d, T, rng, A.flags, L);
+        if (r == BOUNCE_CONTINUE && lastDepth)
+        { // still alive after maxDepth bounces: e[D-1] = 0 (MapperPathTracer.cxx:328-331); no draws left to burn
+          finish_path(A, pid, T * 0.f, rng, refStream, 0);
+        }
+        else if (r == BOUNCE_DONE) // zero-throughput kill (never in reference-stream mode)
+          finish_path(A, pid, L, rng, false, 0);
+        else
+          survive = true;
       }
-      f3 L;
-      Hit hit;
-      BounceResult r = bounce(scene, lights, o, d, T, rng, A.flags, L, hit);
-      if (r == BOUNCE_CONTINUE && lastDepth)
-      {
-        L = T * 0.f; // still alive after maxDepth bounces: e[D-1] = 0 (MapperPathTracer.cxx:328-331)
-        r = BOUNCE_DONE;
-        if (refStream)
-          A.seeds[pid % (uint32_t)A.nPixels] = rng;
-      }
-      else if (r == BOUNCE_DONE && refStream)
-      {
-        burn_depths(rng, A.maxDepth - A.depth);
-        A.seeds[pid % (uint32_t)A.nPixels] = rng;
-      }
-      if (r == BOUNCE_DONE)
-        A.rad[pid] = make_float4(L.x, L.y, L.z, 0.f);
-      else
-        survive = true;
+      // ---- K5: compaction of survivors into the warp's queue region: ballot + popcount prefix
+      const unsigned ballot = __ballot_sync(0xffffffffu, survive);
+      if (survive)
+        store_ray(A.q, base + qcnt + __popc(ballot & ((1u << lane) - 1u)), o, d, T, pid, rng);
+      qcnt += __popc(ballot);
     }
-    // ---- K5: compaction of survivors into the next queue -------------------------------------
-    const unsigned ballot = __ballot_sync(0xffffffffu, survive);
-    if (lane == 0)
-      sWarp[warp] = __popc(ballot);
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-      uint32_t run = 0;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w)
-      {
-        uint32_t c = sWarp[w];
-        sWarp[w] = run;
-        run += c;
-      }
-      sBase = run ? atomicAdd(&A.counters[A.depth], run) : 0u;
-    }
-    __syncthreads();
-    if (survive)
-    {
-      const uint32_t pos = sBase + sWarp[warp] + __popc(ballot & ((1u << lane) - 1u));
-      store_ray(A.qout, pos, o, d, T, pid, rng);
-    }
-    __syncthreads();
+  }
+  if (lane == 0)
+  {
+    A.qCount[w] = qcnt;
+    if (qcnt)
+      atomicAdd(&A.depthTotals[A.depth], qcnt); // statistics only: one add per warp per launch
   }
 }
 
@@ -266,52 +438,50 @@ cudaError_t query_launch_cfg(LaunchCfg* cfg)
   e = cudaDeviceGetAttribute(&cfg->numSMs, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess)
     return e;
-  int n = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_bounce<true, B2SmallScene>, kBlock, 0);
-  if (e != cudaSuccess)
+  auto occ = [&](const void* fn, int& out) -> cudaError_t {
+    int n = 0;
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, kBlock, 0);
+    out = n > 0 ? n : 1;
+    return err;
+  };
+  if ((e = occ((const void*)k_trace<true, B2SmallScene>, cfg->traceBlocksPerSM[1][0])) != cudaSuccess ||
+      (e = occ((const void*)k_trace<false, B2SmallScene>, cfg->traceBlocksPerSM[0][0])) != cudaSuccess ||
+      (e = occ((const void*)k_trace<true, B2BvhScene>, cfg->traceBlocksPerSM[1][1])) != cudaSuccess ||
+      (e = occ((const void*)k_trace<false, B2BvhScene>, cfg->traceBlocksPerSM[0][1])) != cudaSuccess ||
+      (e = occ((const void*)k_shade<B2SmallScene>, cfg->shadeBlocksPerSM[0][0])) != cudaSuccess ||
+      (e = occ((const void*)k_shade<B2BvhScene>, cfg->shadeBlocksPerSM[0][1])) != cudaSuccess)
     return e;
-  cfg->bounceBlocksPerSM[1][0] = n > 0 ? n : 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_bounce<false, B2SmallScene>, kBlock, 0);
-  if (e != cudaSuccess)
-    return e;
-  cfg->bounceBlocksPerSM[0][0] = n > 0 ? n : 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_bounce<true, B2BvhScene>, kBlock, 0);
-  if (e != cudaSuccess)
-    return e;
-  cfg->bounceBlocksPerSM[1][1] = n > 0 ? n : 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_bounce<false, B2BvhScene>, kBlock, 0);
-  if (e != cudaSuccess)
-    return e;
-  cfg->bounceBlocksPerSM[0][1] = n > 0 ? n : 1;
   return cudaSuccess;
 }
 
+// One bounce = k_trace then k_shade on the same stream, both on the fixed persistent grid that owns the
+// args.numWarps regions (cfg.persistentBlocks CTAs of kWarps warps).
 cudaError_t launch_bounce(const LaunchCfg& cfg, bool primary, const B2Camera& cam, const B2SmallScene* small,
-                          const B2BvhScene* bvh, const B2Lights& lights, const B2RenderArgs& args, int64_t maxRaysIn,
+                          const B2BvhScene* bvh, const B2Lights& lights, const B2RenderArgs& args, int64_t,
                           cudaStream_t stream)
 {
-  const int useBvh = bvh ? 1 : 0;
-  int64_t tiles = (maxRaysIn + kBlock - 1) / kBlock;
-  int64_t persistent = (int64_t)cfg.numSMs * cfg.bounceBlocksPerSM[primary ? 1 : 0][useBvh];
-  int grid = (int)(tiles < persistent ? tiles : persistent);
-  if (grid < 1)
-    grid = 1;
+  const int grid = (args.numWarps + kWarps - 1) / kWarps;
+  (void)cfg;
   if (bvh)
   {
     if (primary)
-      k_bounce<true, B2BvhScene><<<grid, kBlock, 0, stream>>>(cam, *bvh, lights, args);
+      k_trace<true, B2BvhScene><<<grid, kBlock, 0, stream>>>(cam, *bvh, args);
     else
-      k_bounce<false, B2BvhScene><<<grid, kBlock, 0, stream>>>(cam, *bvh, lights, args);
+      k_trace<false, B2BvhScene><<<grid, kBlock, 0, stream>>>(cam, *bvh, args);
+    k_shade<B2BvhScene><<<grid, kBlock, 0, stream>>>(*bvh, lights, args);
   }
   else
   {
     if (primary)
-      k_bounce<true, B2SmallScene><<<grid, kBlock, 0, stream>>>(cam, *small, lights, args);
+      k_trace<true, B2SmallScene><<<grid, kBlock, 0, stream>>>(cam, *small, args);
     else
-      k_bounce<false, B2SmallScene><<<grid, kBlock, 0, stream>>>(cam, *small, lights, args);
+      k_trace<false, B2SmallScene><<<grid, kBlock, 0, stream>>>(cam, *small, args);
+    k_shade<B2SmallScene><<<grid, kBlock, 0, stream>>>(*small, lights, args);
   }
   return cudaGetLastError();
 }
+
+int warps_per_block() { return kWarps; }
 
 cudaError_t launch_accumulate(float4* color, const float4* rad, int nPixels, int samplesInBatch,
                               unsigned long long* nanCounter, cudaStream_t stream)

@@ -12,18 +12,21 @@ namespace b2pt
 struct LaunchCfg
 {
   int numSMs;
-  int bounceBlocksPerSM[2][2]; // [primary][bvh]
+  int traceBlocksPerSM[2][2]; // [primary][bvh]
+  int shadeBlocksPerSM[2][2];
 };
 
 // Queries occupancy of the bounce kernels on the current device.
 cudaError_t query_launch_cfg(LaunchCfg* cfg);
 
-// K1+K2+K3+K5 fused: one bounce of every ray of the input queue (or, primary=true, of freshly generated
-// camera rays), survivors compacted into the output queue.  scene is B2SmallScene or B2BvhScene.
+// One bounce of every ray of the input queue (or, primary=true, of freshly generated camera rays): k_trace
+// (K1+K2: raygen + closest hit -> 8-byte hit records) then k_shade (K3+K5: fused shading, survivors compacted
+// into the output queue).  scene is B2SmallScene or B2BvhScene.
 cudaError_t launch_bounce(const LaunchCfg& cfg, bool primary, const B2Camera& cam, const B2SmallScene* small,
                           const B2BvhScene* bvh, const B2Lights& lights, const B2RenderArgs& args,
                           int64_t maxRaysIn, cudaStream_t stream);
 // K4: color[p] += sum_b rad[b*N + p] in sample order; counts NaN samples into *nanCounter.
+int warps_per_block();
 cudaError_t launch_accumulate(float4* color, const float4* rad, int nPixels, int samplesInBatch,
                               unsigned long long* nanCounter, cudaStream_t stream);
 cudaError_t launch_primary_hits(const B2Camera& cam, const B2SmallScene* small, const B2BvhScene* bvh,

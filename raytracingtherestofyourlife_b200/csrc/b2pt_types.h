@@ -21,8 +21,9 @@
 // device-side copies of the public render flags (include/b2pt.h)
 #define B2PT_FLAG_REFERENCE_STREAM_DEV 0x1u
 #define B2PT_FLAG_KILL_ZERO_THROUGHPUT_DEV 0x2u
+#define B2PT_FLAG_NO_AA_DEV 0x10u // build-time: trace every quad with the general Lagae-Dutre test
 
-struct B2Quad // 32 words = 128 B, 16-byte aligned
+struct alignas(16) B2Quad // 32 words = 128 B, 16-byte aligned
 {
   float v00[3]; // q
   float e01[3]; // r - q   (Surface.h:58  E01 = v10 - v00)
@@ -43,16 +44,36 @@ struct B2Quad // 32 words = 128 B, 16-byte aligned
 // Leaf AABB of a primitive as the reference's BVH sees it (pathtracing/AABBSurface.h:24-78).  The reference
 // reaches a primitive only if the ray passes this box (one primitive per LinearBVH leaf), which matters for
 // non-planar quads: Lagae-Dutre returns spurious far hits on them that the box culls.
-struct B2GateBox
+struct alignas(16) B2GateBox
 {
   float bmin[3];
   float bmax[3];
   int32_t quad; // index of the gated quad in the scene's quad array (BVH path: tested after the traversal)
   int32_t pad;
 };
-#define B2PT_SMALL_MAX_GATES 8
+#define B2PT_SMALL_MAX_GATES 24
 
-struct B2Sphere // 12 words = 48 B
+// Axis-aligned rectangle (E01 = a*e_u, E03 = b*e_v, E23 = a2*e_u, E21 = b2*e_v with exact zeros elsewhere),
+// stored in the permuted frame (u,v,n).  Every product of the Lagae-Dutre test that multiplies by one of those
+// exact zeros contributes +-0 to its sum, so the test below performs only the remaining operations and is
+// bit-identical to the general form for finite inputs (DESIGN.md "axis-aligned specialisation").  The
+// permutation sign eps is folded into the constants:
+//   P_u = d_n*bPu, P_n = d_u*bPn, det = a*P_u, Q_v = T_n*aQv, Q_n = T_v*aQn, E03.Q = b*Q_v   (first triangle)
+//   P'_u = d_n*b2Pu, P'_n = d_u*b2Pn, det' = a2*P'_u, Q'_v = T'_n*a2Qv, Q'_n = T'_v*a2Qn      (second triangle)
+struct alignas(16) B2AAQuad // 20 words = 80 B, read as five 16-byte chunks
+{
+  float v00u, v00v, v00n, bPu;
+  float v11u, v11v, v11n, bPn;
+  float a, aQv, aQn, b;
+  float a2, b2Pu, b2Pn, a2Qv;
+  float a2Qn;
+  int32_t cls;  // bits 0-2: 0..5 = (u,v,n) = xyz, yzx, zxy, yxz, xzy, zyx; bit 3: consistent rectangle
+                // (second-triangle shortcut allowed); -1: not axis-aligned
+  int32_t slot; // index into the quad array holding normal / material / ids
+  int32_t prim; // original quad index (tie-break: lowest index wins an exact-t tie)
+};
+
+struct alignas(16) B2Sphere // 12 words = 48 B
 {
   float c[3];
   float r;
@@ -64,13 +85,14 @@ struct B2Sphere // 12 words = 48 B
   int32_t pad;
 };
 
-struct B2LightQuad // light quad used by QuadWorkletGenerateDir / QuadPDFWorklet
+struct alignas(16) B2LightQuad // light quad used by QuadWorkletGenerateDir / QuadPDFWorklet
 {
   B2Quad geo;  // same precomputation as a scene quad
   float area;  // |r-q| * |t-q| (PdfWorklet.h:236-239)
   float pt1[3]; // pts[id[1]]
   float pt2[3]; // pts[id[3]]
   float pad;
+  B2AAQuad aa; // aa.cls >= 0: the light quad is an axis-aligned rectangle (fast pdf test)
 };
 
 struct B2LightSphere
@@ -88,7 +110,7 @@ struct B2Camera // RayGen members, pathtracing/Camera.cxx:431-438
   int32_t W, H;
 };
 
-struct B2Lights
+struct alignas(16) B2Lights
 {
   int32_t nLightQuads, nLightSph;
   float weight; // 1/lightables (PdfWorklet.h:294)
@@ -97,11 +119,18 @@ struct B2Lights
   B2LightSphere ls[B2PT_MAX_LIGHT_SPH];
 };
 
-struct B2SmallScene
+struct alignas(16) B2SmallScene
 {
   int32_t nQuads, nSph;
-  int32_t nGate, pad1;
+  int32_t nGate, nAA;
+  // Trace order: axis-aligned quads aa[0..nAA) grouped by class (aaEnd[c] = end of class c); then the other
+  // quads, quads[firstBoxed..nQuads), each behind the slab test of its own leaf box gate[quad.gate-1] --
+  // planar ones first (the box is a conservative filter there), non-planar ones last (the box is part of the
+  // acceptance rule); then the spheres.  quads[] holds every traced quad (attributes by slot).
+  int32_t aaEnd[6];
+  int32_t firstBoxed, pad1;
   B2GateBox gate[B2PT_SMALL_MAX_GATES];
+  B2AAQuad aa[B2PT_SMALL_MAX_QUADS];
   B2Quad quads[B2PT_SMALL_MAX_QUADS];
   B2Sphere sph[B2PT_SMALL_MAX_SPH];
 };
@@ -133,18 +162,31 @@ struct B2Queue
   uint4* p2; // tb pathId rng aux
 };
 
+// Launch arguments of the bounce kernels.  The ray queue and the four sorted hit bins are statically
+// partitioned into one REGION per persistent warp (numWarps regions of regionCap entries, regionCap a multiple
+// of 32): warp w consumes and refills only region w, with register counters -- no atomics on the data path.
 struct B2RenderArgs
 {
-  B2Queue qin, qout;
-  uint32_t* counters; // counters[d] = rays written by bounce d (entering bounce d+1)
-  float4* rad;        // per-path radiance, [b*N + pixel]
-  uint32_t* seeds;    // per-pixel persistent RNG state (reference-stream mode)
-  int32_t* primOut;   // optional primary-hit ids (parity hook)
-  float* tOut;
-  int64_t nPaths;     // paths in this batch (N * samplesInBatch)
+  B2Queue q;            // compact ray queue: entry [w*regionCap + i], i < qCount[w]
+  // sorted hit bins written by k_trace, read by k_shade: bin k (0 specular hits, 1..3 lambertian hits by
+  // sampling strategy), entry [k*binStride + w*regionCap + i], i < binCount[k*numWarps + w]; a record is three
+  // 16-byte planes (ox oy oz dx) (dy dz Tr Tg) (Tb pathId rng t) plus the primitive code
+  uint4* bin0;
+  uint4* bin1;
+  uint4* bin2;
+  uint32_t* binCode;
+  uint32_t* qCount;     // [numWarps]
+  uint32_t* binCount;   // [4*numWarps]
+  uint32_t* depthTotals; // [maxDepth] of this batch: rays entering bounce d+1 (statistics only)
+  float4* rad;          // per-path radiance, [b*N + pixel]
+  uint32_t* seeds;      // per-pixel persistent RNG state (reference-stream mode)
+  int64_t binStride;    // numWarps * regionCap
+  int64_t nPaths;       // paths in this batch (N * samplesInBatch)
+  int32_t numWarps;
+  int32_t regionCap;
   int32_t nPixels;
-  int32_t sampleBase; // global index of the batch's first sample
-  int32_t depth;      // this bounce
+  int32_t sampleBase;   // global index of the batch's first sample
+  int32_t depth;        // this bounce
   int32_t maxDepth;
   uint32_t seedOffset;
   uint32_t flags;

@@ -6,6 +6,7 @@ attributed to its innermost inlined source line; --outer attributes it to the li
 `bounce` body (or the kernel) that the inline chain passes through, which groups whole stages.
 """
 import collections
+import os
 import csv
 import re
 import subprocess
@@ -76,3 +77,27 @@ print("total warp-instr %d thread-instr %d avg active %.2f samples %d" % (totE, 
 for key, (e, t, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     print("%-28s inst %6.2f%%  active %5.2f  stall-samples %5.2f%%" % (
         str(key), 100.0 * e / totE, t / max(e, 1), 100.0 * s / max(totS, 1)))
+
+# ---- optional: attribute to the innermost NON-helper function (helpers = vector math lines < 100)
+if "--func" in sys.argv:
+    import bisect
+    src = open(os.path.join(os.path.dirname(cubin), "..", "..", "raytracingtherestofyourlife_b200", "csrc",
+                            "b2pt_device.cuh")).read().splitlines() if False else None
+    funcs = [(105, "raygen"), (127, "quad_hit"), (167, "quad_accept/normal"), (186, "sphere_accept"), (213, "slab_hit/rcp_safe"),
+             (225, "Hit"), (237, "aa_quad_hit"), (265, "aa_permute"), (283, "trace_small"), (384, "trace_bvh"),
+             (520, "onb_from_w"), (536, "random_cosine/to_sphere"), (557, "quad_pdf_value"), (578, "sphere_pdf_value"),
+             (595, "dielectric"), (640, "bounce")]
+    starts = [f[0] for f in funcs]
+    agg2 = collections.defaultdict(lambda: [0, 0])
+    for k, r in enumerate(data):
+        chain = chains[k] if k < len(chains) else []
+        name = "kernel/other"
+        for loc in chain:
+            if loc[0] == "b2pt_device.cuh" and loc[1] >= 100:
+                name = funcs[bisect.bisect_right(starts, loc[1]) - 1][1]
+                break
+        agg2[name][0] += int(r[iE])
+        agg2[name][1] += int(r[iT])
+    print("---- by function (helpers attributed to their caller)")
+    for name, (e, t) in sorted(agg2.items(), key=lambda kv: -kv[1][0]):
+        print("%-26s inst %6.2f%%  active %5.2f" % (name, 100.0 * e / totE, t / max(e, 1)))

@@ -150,6 +150,22 @@ def test_dedup_of_identical_quads_changes_nothing(gpu_ctx, b2pt):
     gpu_ctx.render(1, 1, 0)
 
 
+def test_axis_aligned_specialisation_is_bit_identical(gpu_ctx, b2pt):
+    """The axis-aligned rectangle test skips only multiplications by exact zeros of the Lagae-Dutre test, and
+    the leaf-box filter of the other planar quads is conservative: both must reproduce the general path bitwise."""
+    gpu_ctx.set_camera(b2pt.Camera(160, 128))
+    gpu_ctx.render(24, 50, 0)
+    a, sa = gpu_ctx.read_color(), gpu_ctx.stats()
+    p0, t0 = gpu_ctx.primary_hits()
+    gpu_ctx.render(24, 50, b2pt.FLAG_NO_AA)
+    b, sb = gpu_ctx.read_color(), gpu_ctx.stats()
+    p1, t1 = gpu_ctx.primary_hits()
+    assert np.array_equal(p0, p1) and np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
+    assert sa.segments == sb.segments
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    gpu_ctx.render(1, 1, 0)
+
+
 def test_edge_cases(gpu_ctx, b2pt):
     gpu_ctx.set_camera(b2pt.Camera(16, 16))
     gpu_ctx.render(0, 5, 0)  # empty render
