@@ -7,11 +7,16 @@
  * cpu_baseline / --impl reference legs may load this library; the product
  * (libb2pt.so) never links, imports or calls it.
  *
- * PARITY STATUS: "parity unpinned".  The reference ships no tests, golden
- * vectors or fixtures for this path and cannot be built here (it needs VTK-m,
- * which is absent).  The oracle is pinned only by the derived
- * known-answer vectors in tests/golden/ (wang-hash chains, WangInit values)
- * and by self-consistency of its four execution modes.
+ * PARITY STATUS: pinned to the reference's own code at worklet level; the residue is "parity unpinned".
+ * The reference ships no tests, golden vectors or fixtures for this path and cannot be built as a whole here
+ * (it needs VTK-m, which is absent).  But its hot-path arithmetic lives in header-only worklets;
+ * oracle/ref_harness.cxx compiles those from /root/reference against a minimal VTK-m stand-in
+ * (oracle/vtkm_min/) and runs them in the reference's launch order.  This oracle's PASSES mode is bit-identical
+ * to that harness (images, segment counts, primary distances; tests/test_ref_harness.py and the committed
+ * "refworklets" vectors in tests/golden/).  Still unpinned, because they live in .cxx files that need all of
+ * VTK-m: camera ray generation (Camera.cxx:438-524), VTK-m's own math (Cross/Normalize/Min/Max, restated in
+ * vtkm_min from its documented semantics) and VTK-m's LinearBVH tree shape (affects 1 of 65536 primary rays
+ * through the non-planar quad's leaf box).
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference).

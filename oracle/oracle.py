@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs; the product package never imports this module.
-Parity status: unpinned (see b2pt_oracle.h).
+Parity status: pinned to the reference's worklet code through oracle/ref_harness.cxx (see b2pt_oracle.h).
 """
 import ctypes as C
 import os

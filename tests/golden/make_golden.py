@@ -1,8 +1,12 @@
-"""Generates the committed golden fixtures of tests/golden/ from the CPU oracle.
+"""Generates the committed golden fixtures of tests/golden/.
 
-Provenance: the reference ships no tests or golden vectors and cannot be built here (VTK-m absent), so these
-are ORACLE outputs ("parity unpinned").  The entries under "survey" were derived independently by the
-surveyor's throwaway numpy probe and are the only vectors not produced by this oracle.
+Provenance of each group:
+  "survey"      derived independently by the surveyor's throwaway numpy probe.
+  "refworklets" outputs of the REFERENCE'S OWN header-only worklets, compiled from /root/reference against the
+                VTK-m stand-in of oracle/vtkm_min/ and driven in the reference's launch order by
+                oracle/ref_harness.cxx (only generated when /root/reference is present; the reference as a whole
+                needs VTK-m and cannot be built here).  These pin the C oracle to the reference's code.
+  "oracle"      outputs of the C oracle (oracle/b2pt_oracle.c) itself.
 Run:  python tests/golden/make_golden.py
 """
 import hashlib
@@ -51,6 +55,28 @@ def main():
     a, b, c = cam.basis()
     o["camera_basis_128"] = {"nlook": a.view(np.uint32).tolist(), "dx": b.view(np.uint32).tolist(),
                              "dy": c.view(np.uint32).tolist()}
+    from oracle import refharness as R
+    if R.available():
+        r = g["refworklets"] = {}
+        r["wang_chain_12345"] = R.wang_chain(12345, 8)
+        r["randf_seed0_bits"] = np.array(R.randf_chain(0, 8), np.float32).view(np.uint32).tolist()
+        # BASELINE.json configs[0] through the reference's worklets (median-split stand-in BVH)
+        rimg, rseg, rt0, rhit0 = R.render(sc, O.Camera(128, 128), 10, 5)
+        np.save(os.path.join(HERE, "config1_refworklets_rgb.npy"), rimg[:, :3].copy())
+        r["config1"] = {"segments": rseg, "t0_sha256": hashlib.sha256(rt0.tobytes()).hexdigest(),
+                        "hit0_sha256": hashlib.sha256(rhit0.tobytes()).hexdigest()}
+        # deep paths: 64x64, 8 spp, depth 50
+        rimg, rseg, rt0, rhit0 = R.render(sc, O.Camera(64, 64), 8, 50)
+        np.save(os.path.join(HERE, "deep64_refworklets_rgb.npy"), rimg[:, :3].copy())
+        r["deep64"] = {"segments": rseg, "t0_sha256": hashlib.sha256(rt0.tobytes()).hexdigest()}
+        # primary-ray closest distances at 256x256 (45 rays depend on the leaf-box gate, 1 on tree shape)
+        _, _, rt0, rhit0 = R.render(sc, O.Camera(256, 256), 1, 1)
+        np.save(os.path.join(HERE, "primary_t_256_refworklets.npy"), rt0)
+    else:
+        with open(os.path.join(HERE, "golden.json")) as f:
+            old = json.load(f)
+        if "refworklets" in old:
+            g["refworklets"] = old["refworklets"]
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(g, f, indent=1)
     print("wrote golden fixtures to", HERE)
