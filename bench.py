@@ -13,8 +13,10 @@ value  = path samples/s over all ranks, device-timed (CUDA events on the launchi
 e2e    = same metric through the C-ABI with HOST buffers inside the timed region: b2pt_set_scene (H2D of the
          scene arrays) + b2pt_build_bvh + b2pt_set_camera + b2pt_render + b2pt_read_color (D2H of the W*H*16 B
          radiance sum into pinned host memory).
---impl reference  times the reference's CPU structure (oracle PASSES mode: one full-canvas loop per worklet,
-         full depth, no early exit; VTK-m itself cannot be built here) on the box's host cores.
+--impl reference  times the reference's own CPU code on the box's host cores: its header-only worklets compiled
+         from the reference sources (oracle/_ref, built by oracle/Makefile against a minimal VTK-m stand-in) and
+         launched in the reference's order, one OpenMP parallel-for per worklet launch (kind "reference").  When
+         that library is absent the C restatement (oracle PASSES mode) is timed instead (kind "port").
 """
 import argparse
 import json
@@ -101,29 +103,51 @@ def ncu_traffic():
     return None
 
 
-def cpu_reference_step(O, osc, ocam, spp, depth, threads):
-    t0 = time.perf_counter()
-    img, st = O.render(osc, ocam, spp, depth, mode=O.MODE_PASSES, threads=threads)
-    dt = time.perf_counter() - t0
-    return st.paths / dt, dt, st
+def cpu_reference_arm():
+    """(kind, description, step) of the CPU arm: the reference's own worklets when oracle/_ref is available, else
+    the C restatement.  step(W, spp, depth, threads) -> (paths_per_s, seconds, paths)."""
+    from oracle import oracle as O
+    O.build()
+    try:
+        from oracle import refharness as R
+        have_ref = R.available()
+    except Exception:
+        have_ref = False
+    if have_ref:
+        def step(W, spp, depth, threads):
+            os.environ["OMP_NUM_THREADS"] = str(threads)
+            t0 = time.perf_counter()
+            R.render(O.cornell_scene(), O.Camera(W, W), spp, depth)
+            dt = time.perf_counter() - t0
+            return W * W * spp / dt, dt, W * W * spp
+        return "reference", ("the reference's own worklets (Surface.h, BVHTraverser.h, EmitWorklet.h, PdfWorklet.h, "
+                             "ScatterWorklet.h ...) compiled from its sources against a minimal VTK-m stand-in, launched "
+                             "in the order of MapperPathTracer.cxx:276-351, one OpenMP parallel-for per worklet launch "
+                             "(VTK-m itself is not installable here)"), step
+
+    def step(W, spp, depth, threads):
+        t0 = time.perf_counter()
+        img, st = O.render(O.cornell_scene(), O.Camera(W, W), spp, depth, mode=O.MODE_PASSES, threads=threads)
+        dt = time.perf_counter() - t0
+        return st.paths / dt, dt, st.paths
+    return "port", ("CPU restatement (VTK-m-structured): oracle PASSES mode, OpenMP, all host cores; the reference "
+                    "itself needs VTK-m, which is not installable here"), step
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation structure on the host cores (rank 0 only)."""
+    """Reference arm: the reference's own CPU implementation of the path on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as O
-    O.build()
     cores = os.cpu_count() or 1
-    osc, ocam = O.cornell_scene(), O.Camera(args.size, args.size)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    kind, desc, step = cpu_reference_arm()
     for _ in range(args.warmup):
-        cpu_reference_step(O, osc, ocam, args.ref_spp, args.depth, cores)
+        step(args.size, args.ref_spp, args.depth, cores)
     t0 = time.perf_counter()
     paths = 0
     for _ in range(args.steps):
-        _, _, st = cpu_reference_step(O, osc, ocam, args.ref_spp, args.depth, cores)
-        paths += st.paths
+        paths += step(args.size, args.ref_spp, args.depth, cores)[2]
     dt = time.perf_counter() - t0
     val = paths / dt
     sample = "%dx%d, depth %d, %d spp per step (cost is exactly linear in spp; full workload is %d spp)" % (
@@ -133,10 +157,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "Cornell box %dx%d, %d spp, max depth %d (BASELINE.json configs[1])" % (
-            args.size, args.size, args.spp, args.depth),
-            "reference_arm": "CPU restatement (VTK-m-structured): oracle PASSES mode, OpenMP, all host cores; "
-                             "the reference itself needs VTK-m, which is not installable here"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            args.size, args.size, args.spp, args.depth), "reference_arm": desc},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -226,7 +248,7 @@ def main():
     sampler.join()
     ms = ev0.elapsed_time(ev1)
     st = ctx.stats()
-    ctx_profile = ctx.bounce_profile(16)  # first batch of the last timed step
+    ctx_profile = ctx.stage_profile(16)  # first batch of the last timed step: (trace ms, shade ms, rays in)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     seg = torch.tensor([float(st.segments)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -271,19 +293,21 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        # Dominant kernel = the k_bounce launch with the longest duration (bounce 1 of a sample batch).
-        # Per-launch CUDA events on the launching stream, recorded inside the timed steps by the library
-        # (b2pt_get_bounce_profile); algorithmic bytes = 88 B x rays entering that launch.
+        # Dominant launches = the bounce with the longest duration (bounce 1 of a sample batch): its k_trace and
+        # k_shade launch, timed separately by CUDA events on the launching stream inside the timed steps
+        # (b2pt_get_stage_profile).  Algorithmic bytes = 88 B per live segment of that bounce (SURVEY.md 8d:
+        # 44 B ray record read + 44 B written per bounce), charged against BOTH launches' time.
         prof = ctx_profile
-        top = max(range(len(prof)), key=lambda k: prof[k][0]) if prof else None
-        if top is not None and prof[top][0] > 0:
-            top_ms, top_rays = prof[top]
-            achieved = top_rays * ALGO_BYTES_PER_SEGMENT / (top_ms * 1e-3) / 1e9
-            top_desc = "k_bounce<%s>, bounce %d of a %d-sample batch: %d rays in, %.3f ms (CUDA events)" % (
-                "primary" if top == 0 else "queue", top, st.samplesPerBatch, top_rays, top_ms)
+        top = max(range(len(prof)), key=lambda k: prof[k][0] + prof[k][1]) if prof else None
+        if top is not None and prof[top][0] + prof[top][1] > 0:
+            tr_ms, sh_ms, top_rays = prof[top]
+            achieved = top_rays * ALGO_BYTES_PER_SEGMENT / ((tr_ms + sh_ms) * 1e-3) / 1e9
+            top_desc = ("bounce %d of a %d-sample batch = k_trace<%s> launch (%.3f ms) + k_shade launch (%.3f ms), "
+                        "%d rays in (CUDA events on the launching stream)" % (
+                            top, st.samplesPerBatch, "primary" if top == 0 else "queue", tr_ms, sh_ms, top_rays))
         else:
             achieved = segments_per_step * args.steps * ALGO_BYTES_PER_SEGMENT / (ms * 1e-3) / 1e9 / world
-            top_desc = "all k_bounce launches of a step (aggregate)"
+            top_desc = "all bounce launches of a step (aggregate)"
         step_gbs = segments_per_step * args.steps * ALGO_BYTES_PER_SEGMENT / (ms * 1e-3) / 1e9 / world
         traffic = ncu_traffic()
         line = {
@@ -301,7 +325,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
                          "kernel": top_desc, "algorithmic_bytes_per_segment": ALGO_BYTES_PER_SEGMENT,
-                         "whole_step_achieved": step_gbs, "bounce_profile_ms_rays": prof[:8],
+                         "whole_step_achieved": step_gbs, "stage_profile_trace_ms_shade_ms_rays": prof[:8],
                          "note": "per GPU; FP32-issue bound in practice, see DESIGN.md and profiles/"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(scene.nbytes()),
                     "d2h_bytes_per_step": int(N * 16)},
@@ -314,13 +338,12 @@ def main():
             except Exception as e:  # the check must never hide the measurement
                 line["image_check"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1:
-            from oracle import oracle as O
             cores = os.cpu_count() or 1
-            val, dt, _ = cpu_reference_step(O, O.cornell_scene(), O.Camera(W, H), 2, args.depth, cores)
-            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%dx%d, depth %d, 2 of %d spp in %.1f s, oracle PASSES mode "
-                                              "(VTK-m-structured CPU restatement, OpenMP)" % (W, H, args.depth,
-                                                                                             args.spp, dt)}
+            kind, desc, cstep = cpu_reference_arm()
+            val, dt, _ = cstep(W, 2, args.depth, cores)
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": "%dx%d, depth %d, 2 of %d spp in %.1f s; %s" % (W, H, args.depth,
+                                                                                             args.spp, dt, desc)}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

@@ -122,6 +122,8 @@ int b2pt_get_stats(b2pt_ctx* ctx, b2pt_stats* out);
  * launches of the last render's first sample batch; returns the number of entries written (<= maxEntries,
  * <= 16) or a negative status.  Feeds the live roofline measurement of bench.py. */
 int b2pt_get_bounce_profile(b2pt_ctx* ctx, int maxEntries, float* ms, int64_t* raysIn);
+/* Same launches split by stage: duration of the k_trace launch and of the k_shade launch of each bounce. */
+int b2pt_get_stage_profile(b2pt_ctx* ctx, int maxEntries, float* traceMs, float* shadeMs, int64_t* raysIn);
 
 /* ---- parity hooks and stage-level entry points --------------------------------------------- */
 /* Sample-0 primary rays with seeds[i] = i + seedOffset through the production raygen + trace device

@@ -198,7 +198,8 @@ int b2ref_sphere_hit(const float* o, const float* d, float tmin, float tmax, con
   return h ? 1 : 0;
 }
 
-// The whole depth loop of MapperPathTracer.cxx:276-351 with the reference's worklets.
+// The whole depth loop of MapperPathTracer.cxx:276-351 with the reference's worklets.  Every per-pixel launch is an
+// OpenMP parallel-for (the stand-in for VTK-m's OpenMP device adapter; OMP_NUM_THREADS=1 = its Serial adapter).
 // rgba: un-normalised sum over samples (alpha lane 0); segments: live rays entering `intersect`, summed.
 // primId0/t0 (optional): per pixel, sample 0 / depth 0: hit material id pair is not a primitive id, so the
 // harness reports the closest distance (Distance array after intersect) and whether the pixel stayed alive.
@@ -298,6 +299,7 @@ int b2ref_render(const orc_scene* sc, const orc_camera* cam, int spp, int maxDep
   for (int s = 0; s < spp; ++s)
   {
     // rayCam.CreateRays (Camera.cxx:880-960; restated by the C oracle) + Status = 1<<3 (MapperPathTracer.cxx:283)
+    _Pragma("omp parallel for schedule(static)")
     for (Id i = 0; i < N; ++i)
     {
       float d3[3];
@@ -312,6 +314,7 @@ int b2ref_render(const orc_scene* sc, const orc_camera* cam, int spp, int maxDep
     for (int depth = 0; depth < D; ++depth)
     {
       // MapperPathTracer.cxx:287 and ::intersect (:410-435)
+      _Pragma("omp parallel for schedule(static) reduction(+ : segs)")
       for (Id i = 0; i < N; ++i)
       {
         sum_values[i] = 0.f;
@@ -325,6 +328,7 @@ int b2ref_render(const orc_scene* sc, const orc_camera* cam, int spp, int maxDep
         const FlatTree& tree = pass == 0 ? quadTree : sphereTree;
         if (tree.flat.GetNumberOfValues() == 0)
           continue;
+        _Pragma("omp parallel for schedule(static)")
         for (Id i = 0; i < N; ++i)
         {
           // FieldInOut arguments are loaded into locals, passed by reference, and stored back in order:
@@ -342,6 +346,7 @@ int b2ref_render(const orc_scene* sc, const orc_camera* cam, int spp, int maxDep
         }
       }
       if (s == 0 && depth == 0 && t0 && hit0)
+        _Pragma("omp parallel for schedule(static)")
         for (Id i = 0; i < N; ++i)
         {
           t0[i] = hrec[i][static_cast<Id>(HR::T)];
@@ -350,6 +355,7 @@ int b2ref_render(const orc_scene* sc, const orc_camera* cam, int spp, int maxDep
       {
         CollectIntersecttWorklet collect(N, depth);
         auto ep = emitted.Portal(), ap = attenuation.Portal();
+        _Pragma("omp parallel for schedule(static)")
         for (Id i = 0; i < N; ++i)
           collect(i, status[i], ep, ap);
       }
@@ -359,12 +365,15 @@ int b2ref_render(const orc_scene* sc, const orc_camera* cam, int spp, int maxDep
         DiffuseLightWorklet dl(N, depth);
         DielectricWorklet de(N, depth, 1.5, static_cast<vtkm::UInt32>(N));
         (void)sc->refIdx; // the reference hard-codes 1.5 (MapperPathTracer.cxx:467)
+        _Pragma("omp parallel for schedule(static)")
         for (Id i = 0; i < N; ++i)
           lmb(i, origin[i], dir[i], hrec[i], hid[i], srec[i], status[i], Tex.Portal(), MatType.Portal(),
               TexType.Portal(), emitted.Portal());
+        _Pragma("omp parallel for schedule(static)")
         for (Id i = 0; i < N; ++i)
           dl(i, origin[i], dir[i], hrec[i], hid[i], srec[i], status[i], Tex.Portal(), MatType.Portal(),
              TexType.Portal(), emitted.Portal());
+        _Pragma("omp parallel for schedule(static)")
         for (Id i = 0; i < N; ++i)
           de(i, seeds[i], origin[i], dir[i], hrec[i], hid[i], srec[i], status[i], Tex.Portal(), MatType.Portal(),
              TexType.Portal(), emitted.Portal());
@@ -372,16 +381,20 @@ int b2ref_render(const orc_scene* sc, const orc_camera* cam, int spp, int maxDep
       // ::generateRays (:481-503)
       {
         WorketletGenerateDir genDir(3); // WhichGenerateDir.cxx:10
+        _Pragma("omp parallel for schedule(static)")
         for (Id i = 0; i < N; ++i)
           genDir(seeds[i], which[i]);
         CosineWorketletGenerateDir cosGen(1); // CosineGenerateDir.h:18
+        _Pragma("omp parallel for schedule(static)")
         for (Id i = 0; i < N; ++i)
           cosGen(which[i], hrec[i], generated[i], seeds[i]);
         QuadWorkletGenerateDir quadGen(2); // QuadGenerateDir.h:22
+        _Pragma("omp parallel for schedule(static)")
         for (Id i = 0; i < N; ++i)
           quadGen(which[i], hrec[i], generated[i], seeds[i], light_box_pointids.Portal(), light_box_indices.Portal(),
                   coords.Portal());
         SphereWorkletGenerateDir sphGen(3); // SphereGenerateDir.h:24
+        _Pragma("omp parallel for schedule(static)")
         for (Id i = 0; i < N; ++i)
           sphGen(i, which[i], hrec[i], generated[i], seeds[i], light_sphere_pointids.Portal(),
                  light_sphere_indices.Portal(), coords.Portal(), light_sphere_radii.Portal());
@@ -389,15 +402,18 @@ int b2ref_render(const orc_scene* sc, const orc_camera* cam, int spp, int maxDep
       // ::applyPDFs (:507-538)
       {
         QuadPDFWorklet quadPdf(lightables);
+        _Pragma("omp parallel for schedule(static)")
         for (Id i = 0; i < N; ++i)
           quadPdf(i, origin[i], dir[i], hrec[i], status[i], sum_values[i], generated[i], seeds[i], quadLeaf,
                   light_box_pointids.Portal(), light_box_indices.Portal(), coords.Portal());
         SpherePDFWorklet sphPdf(lightables);
+        _Pragma("omp parallel for schedule(static)")
         for (Id i = 0; i < N; ++i)
           sphPdf(i, origin[i], dir[i], hrec[i], status[i], sum_values[i], generated[i], seeds[i], sphereLeaf,
                  light_sphere_pointids.Portal(), light_sphere_indices.Portal(), coords.Portal(),
                  light_sphere_radii.Portal());
         PDFCosineWorklet pdfW(static_cast<int>(N), depth, static_cast<vtkm::UInt32>(N), lightables);
+        _Pragma("omp parallel for schedule(static)")
         for (Id i = 0; i < N; ++i)
         {
           // rays.Origin / rays.Dir are passed twice (in: _1,_2; out: _8,_9); the later store wins
@@ -411,6 +427,7 @@ int b2ref_render(const orc_scene* sc, const orc_camera* cam, int spp, int maxDep
     // compositing (MapperPathTracer.cxx:328-350): sumtotl = e[D-1] + 0; then a[d]*sumtotl, e[d]+sumtotl; cols += sumtotl
     const std::vector<vec3>& E = emitted.Vector();
     const std::vector<vec3>& A = attenuation.Vector();
+    _Pragma("omp parallel for schedule(static)")
     for (Id i = 0; i < N; ++i)
     {
       sumtotl[i] = E[static_cast<size_t>((D - 1) * N + i)] + vec3(0.0f);

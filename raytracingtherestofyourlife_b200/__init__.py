@@ -65,6 +65,7 @@ SIGNATURES = {
     "b2pt_synchronize": (_i32, [_vp]),
     "b2pt_get_stats": (_i32, [_vp, C.POINTER(Stats)]),
     "b2pt_get_bounce_profile": (_i32, [_vp, _i32, _vp, _vp]),
+    "b2pt_get_stage_profile": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "b2pt_primary_hits": (_i32, [_vp, _vp, _vp]),
     "b2pt_create_rays": (_i32, [_vp] * 9),
     "b2pt_intersect": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
@@ -262,6 +263,14 @@ class Context:
         if k < 0:
             _check(k)
         return [(float(ms[i]), int(rays[i])) for i in range(k)]
+
+    def stage_profile(self, n=16):
+        """[(trace_ms, shade_ms, rays_in)] of the same launches, split into the k_trace and k_shade launch."""
+        tr, sh, rays = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.int64)
+        k = lib().b2pt_get_stage_profile(self._h, n, _p(tr), _p(sh), _p(rays))
+        if k < 0:
+            _check(k)
+        return [(float(tr[i]), float(sh[i]), int(rays[i])) for i in range(k)]
 
     def primary_hits(self):
         n = self.W * self.H

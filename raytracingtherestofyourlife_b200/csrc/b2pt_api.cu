@@ -96,6 +96,7 @@ struct b2pt_ctx
   cudaEvent_t evStart = nullptr, evStop = nullptr;
   static constexpr int kProfDepths = 16;
   cudaEvent_t evBounce[kProfDepths + 1] = {}; // batch 0: event before each of the first bounces + one after
+  cudaEvent_t evMid[kProfDepths + 1] = {};    // batch 0: event between k_trace and k_shade of those bounces
   int profDepths = 0;
   int64_t profPaths = 0;
   b2pt::LaunchCfg cfg{};
@@ -347,6 +348,9 @@ void b2pt_destroy(b2pt_ctx* ctx)
   for (cudaEvent_t ev : ctx->evBounce)
     if (ev)
       cudaEventDestroy(ev);
+  for (cudaEvent_t ev : ctx->evMid)
+    if (ev)
+      cudaEventDestroy(ev);
   if (ctx->ownStream)
     cudaStreamDestroy(ctx->ownStream);
   delete ctx;
@@ -508,16 +512,135 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
   }
   ctx->tracedQuads = (int32_t)keptQuads.size();
   ctx->tracedSph = (int32_t)ctx->nSph;
-  // classify: axis-aligned rectangles get the specialised test; every other quad is traced behind its leaf box
-  std::vector<B2AAQuad> aa;
+  // classify: planar quads normal to an axis of one of up to B2PT_MAX_FRAMES frames go through the candidate
+  // filter (b2pt_types.h B2FiltQuad); every other quad is traced behind its leaf box
+  struct FiltEntry
+  {
+    int frame, axis;
+    B2FiltQuad fq;
+    int32_t quad;
+  };
+  std::vector<FiltEntry> filt;
+  std::vector<B2Frame> frames;
   std::vector<int32_t> boxedPlanar, boxedNonPlanar;
+  float sceneAbs = 0.f;
   for (int32_t k : keptQuads)
   {
-    B2AAQuad A;
     const B2Quad& Q = ctx->quads[(size_t)k];
-    if (Q.pad[0] == 0 && !(flags & B2PT_FLAG_NO_AA_DEV) && classify_axis_aligned(Q, 0, A))
-      aa.push_back(A);
-    else
+    for (int c = 0; c < 3; ++c)
+    {
+      const float vs[4] = { Q.v00[c], Q.v00[c] + Q.e01[c], Q.v11[c], Q.v00[c] + Q.e03[c] };
+      for (float v : vs)
+        sceneAbs = std::fmax(sceneAbs, std::fabs(v));
+    }
+  }
+  for (const B2Sphere& sp : ctx->sph)
+    for (int c = 0; c < 3; ++c)
+      sceneAbs = std::fmax(sceneAbs, std::fabs(sp.c[c]) + std::fabs(sp.r));
+  {
+    B2Frame F0{};
+    F0.R[0] = F0.R[4] = F0.R[8] = 1.f;
+    F0.identity = 1;
+    frames.push_back(F0);
+  }
+  auto quad_vertices = [&](const B2Quad& Q, double v[4][3]) {
+    for (int c = 0; c < 3; ++c)
+    {
+      v[0][c] = Q.v00[c];
+      v[1][c] = (double)Q.v00[c] + (double)Q.e01[c];
+      v[2][c] = Q.v11[c];
+      v[3][c] = (double)Q.v00[c] + (double)Q.e03[c];
+    }
+  };
+  // frame coordinates of the four vertices; fits if the extent along one frame axis is <= 1e-6 * scale
+  auto try_frame = [&](const B2Frame& F, const B2Quad& Q, FiltEntry& E) -> bool {
+    double v[4][3], w[4][3];
+    quad_vertices(Q, v);
+    for (int k = 0; k < 4; ++k)
+      for (int a = 0; a < 3; ++a)
+        w[k][a] = (double)F.R[3 * a + 0] * (v[k][0] - F.org[0]) + (double)F.R[3 * a + 1] * (v[k][1] - F.org[1]) +
+          (double)F.R[3 * a + 2] * (v[k][2] - F.org[2]);
+    const double scale = std::max<double>(sceneAbs, 1e-30);
+    for (int n = 0; n < 3; ++n)
+    {
+      double lo[3], hi[3];
+      for (int a = 0; a < 3; ++a)
+      {
+        lo[a] = hi[a] = w[0][a];
+        for (int k = 1; k < 4; ++k)
+          lo[a] = std::min(lo[a], w[k][a]), hi[a] = std::max(hi[a], w[k][a]);
+      }
+      if (hi[n] - lo[n] > 1e-6 * scale)
+        continue;
+      const int u = (n + 1) % 3, vv = (n + 2) % 3;
+      // static margin: the exact test's own edge tolerance (1e-5 of the edge length) and the
+      // plane-offset spread, doubled
+      const double mu = 2e-5 * (hi[u] - lo[u]) + 2e-6 * scale, mv = 2e-5 * (hi[vv] - lo[vv]) + 2e-6 * scale;
+      E.axis = n;
+      E.fq = B2FiltQuad{};
+      E.fq.c = (float)(0.5 * (lo[n] + hi[n]));
+      E.fq.uc = (float)(0.5 * (lo[u] + hi[u]));
+      E.fq.hu = (float)(0.5 * (hi[u] - lo[u]) + mu);
+      E.fq.vc = (float)(0.5 * (lo[vv] + hi[vv]));
+      E.fq.hv = (float)(0.5 * (hi[vv] - lo[vv]) + mv);
+      return true;
+    }
+    return false;
+  };
+  for (int32_t k : keptQuads)
+  {
+    const B2Quad& Q = ctx->quads[(size_t)k];
+    bool placed = false;
+    const double area2 = (double)hdot({ Q.e01[0], Q.e01[1], Q.e01[2] }, { Q.e01[0], Q.e01[1], Q.e01[2] }) *
+      (double)hdot({ Q.e03[0], Q.e03[1], Q.e03[2] }, { Q.e03[0], Q.e03[1], Q.e03[2] });
+    const bool sane = area2 > 0.0 && area2 < 1e30 && std::isfinite(area2);
+    if (Q.pad[0] == 0 && sane && !(flags & B2PT_FLAG_NO_AA_DEV) && filt.size() < B2PT_MAX_FILT)
+    {
+      FiltEntry E{};
+      E.quad = k;
+      for (size_t f = 0; f < frames.size() && !placed; ++f)
+        if (try_frame(frames[f], Q, E))
+        {
+          E.frame = (int)f;
+          placed = true;
+        }
+      if (!placed && frames.size() < B2PT_MAX_FRAMES)
+      { // new frame from this quad: n = unit normal, u = E01 direction, v = n x u
+        const double n[3] = { Q.nrm[0], Q.nrm[1], Q.nrm[2] };
+        double u[3] = { Q.e01[0], Q.e01[1], Q.e01[2] };
+        const double un = u[0] * n[0] + u[1] * n[1] + u[2] * n[2];
+        for (int c = 0; c < 3; ++c)
+          u[c] -= un * n[c];
+        const double ul = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        const double nl = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        if (ul > 0 && nl > 0)
+        {
+          B2Frame Fn{};
+          double w[3];
+          for (int c = 0; c < 3; ++c)
+            u[c] /= ul;
+          w[0] = (n[1] * u[2] - n[2] * u[1]) / nl, w[1] = (n[2] * u[0] - n[0] * u[2]) / nl,
+          w[2] = (n[0] * u[1] - n[1] * u[0]) / nl;
+          for (int c = 0; c < 3; ++c)
+          {
+            Fn.R[c] = (float)(n[c] / nl);
+            Fn.R[3 + c] = (float)u[c];
+            Fn.R[6 + c] = (float)w[c];
+            Fn.org[c] = Q.v00[c];
+          }
+          Fn.identity = 0;
+          if (try_frame(Fn, Q, E))
+          {
+            frames.push_back(Fn);
+            E.frame = (int)frames.size() - 1;
+            placed = true;
+          }
+        }
+      }
+      if (placed)
+        filt.push_back(E);
+    }
+    if (!placed)
       (Q.pad[0] ? boxedNonPlanar : boxedPlanar).push_back(k);
   }
   const size_t nBoxed = boxedPlanar.size() + boxedNonPlanar.size();
@@ -531,19 +654,32 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
     std::memset(&S, 0, sizeof(S));
     S.nQuads = (int32_t)keptQuads.size();
     S.nSph = (int32_t)ctx->nSph;
-    S.nAA = (int32_t)aa.size();
-    S.firstBoxed = (int32_t)aa.size();
-    std::stable_sort(aa.begin(), aa.end(),
-                     [](const B2AAQuad& x, const B2AAQuad& y) { return (x.cls & 7) < (y.cls & 7); });
-    for (size_t k = 0; k < aa.size(); ++k)
+    S.nFilt = (int32_t)filt.size();
+    S.firstBoxed = (int32_t)filt.size();
+    S.sceneAbs = sceneAbs;
+    std::stable_sort(filt.begin(), filt.end(), [](const FiltEntry& x, const FiltEntry& y) {
+      return x.frame != y.frame ? x.frame < y.frame : x.axis < y.axis;
+    });
+    // frames without quads are dropped (frame 0 may be empty)
+    std::vector<int> frameMap(frames.size(), -1);
+    S.nFrames = 0;
+    for (size_t k = 0; k < filt.size(); ++k)
     {
-      S.quads[k] = ctx->quads[(size_t)aa[k].prim]; // attributes (normal, material) of the AA quad, same slot
-      aa[k].slot = (int32_t)k;
-      S.aa[k] = aa[k];
-      for (int c = aa[k].cls & 7; c < 6; ++c)
-        S.aaEnd[c] = (int32_t)k + 1;
+      int& fm = frameMap[(size_t)filt[k].frame];
+      if (fm < 0)
+      {
+        fm = S.nFrames++;
+        S.frames[fm] = frames[(size_t)filt[k].frame];
+        for (int a = 0; a < 3; ++a)
+          S.frames[fm].axisEnd[a] = (int32_t)k;
+      }
+      S.quads[k] = ctx->quads[(size_t)filt[k].quad];
+      S.filt[k] = filt[k].fq;
+      S.filt[k].slot = (int32_t)k;
+      for (int a = filt[k].axis; a < 3; ++a)
+        S.frames[fm].axisEnd[a] = (int32_t)k + 1;
     }
-    size_t slot = aa.size();
+    size_t slot = filt.size();
     for (int pass = 0; pass < 2; ++pass) // planar boxed quads first, non-planar last (DESIGN.md "leaf-box gate")
       for (int32_t k : (pass == 0 ? boxedPlanar : boxedNonPlanar))
       {
@@ -803,9 +939,16 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
           CU(cudaEventCreate(&ctx->evBounce[depth]));
         CU(cudaEventRecord(ctx->evBounce[depth], ctx->stream));
       }
+      cudaEvent_t mid = nullptr;
+      if (batch == 0 && depth < profDepths)
+      {
+        if (!ctx->evMid[depth])
+          CU(cudaEventCreate(&ctx->evMid[depth]));
+        mid = ctx->evMid[depth];
+      }
       A.depth = depth;
       CU(b2pt::launch_bounce(ctx->cfg, depth == 0, ctx->cam, ctx->useBvh ? nullptr : &ctx->small,
-                             ctx->useBvh ? &ctx->bvh : nullptr, ctx->lights, A, A.nPaths, ctx->stream));
+                             ctx->useBvh ? &ctx->bvh : nullptr, ctx->lights, A, A.nPaths, ctx->stream, mid));
       launches += 2;
     }
     CU(b2pt::launch_accumulate(ctx->color(), ctx->rad.p, (int)N, (int)nb, ctx->nanCounter.p, ctx->stream));
@@ -893,6 +1036,25 @@ int b2pt_get_bounce_profile(b2pt_ctx* ctx, int maxEntries, float* ms, int64_t* r
   for (int d = 0; d < n; ++d)
   {
     CU(cudaEventElapsedTime(&ms[d], ctx->evBounce[d], ctx->evBounce[d + 1]));
+    raysIn[d] = d == 0 ? ctx->profPaths : (int64_t)ctx->hCounters[(size_t)(d - 1)];
+  }
+  return n;
+}
+
+int b2pt_get_stage_profile(b2pt_ctx* ctx, int maxEntries, float* traceMs, float* shadeMs, int64_t* raysIn)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (maxEntries < 0 || (maxEntries > 0 && (!traceMs || !shadeMs || !raysIn)))
+    return fail(B2PT_ERR_BAD_VALUE, "null profile output");
+  b2pt_stats st;
+  if (int rc = b2pt_get_stats(ctx, &st)) // synchronises and fetches the counters
+    return rc;
+  const int n = std::min(maxEntries, ctx->profDepths);
+  for (int d = 0; d < n; ++d)
+  {
+    CU(cudaEventElapsedTime(&traceMs[d], ctx->evBounce[d], ctx->evMid[d]));
+    CU(cudaEventElapsedTime(&shadeMs[d], ctx->evMid[d], ctx->evBounce[d + 1]));
     raysIn[d] = d == 0 ? ctx->profPaths : (int64_t)ctx->hCounters[(size_t)(d - 1)];
   }
   return n;

@@ -304,41 +304,135 @@ __device__ __forceinline__ void aa_permute(int c, f3 a, float& u, float& v, floa
   }
 }
 
+// ---- phase 1 of the small-scene trace: candidate filter (B2FiltQuad).  All 32 lanes run the same
+// straight-line code per quad (no divergence); the output per lane is the candidate bit mask, the candidate
+// with the smallest LOWER BOUND of its hit distance and the second-smallest lower bound.
+struct FiltState
+{
+  uint32_t mask; // candidate quads (bit = filt index)
+  float tbl;     // smallest lower bound of t over the candidates
+  float t2;      // second smallest
+  int qb;        // candidate holding tbl
+};
+__device__ __forceinline__ float rcp_fast(float x)
+{
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// One axis group: quads [qb,qe) are normal to the frame axis whose ray components are (on,dn); (ou,du),(ov,dv)
+// are the components on the two other axes.  Error model (u = 2^-24, S = coordinate scale, D = |d|_1/|dn| >= 1):
+// the filter's t' = c*rcp(dn) - on*rcp(dn) and the exact test's t both lie within  t*(4e-6*D) + 4e-6*S/|dn|  of the
+// true plane distance (>= 20x the forward error of either evaluation, incl. the rotation into the frame), and
+// the hit point within  S*(2e-5 + 2e-5*D)  of the true one plus the exact test's own edge tolerance (static
+// part folded into hu/hv on the host).  A quad the exact test could accept therefore always passes.
+__device__ __forceinline__ void filt_axis(const B2SmallScene& S, int qBegin, int qEnd, float on, float dn, float ou,
+                                          float du, float ov, float dv, float dabs, float Sr, float tmin, FiltState& F)
+{
+  if (qEnd <= qBegin)
+    return;
+  const float inf = __int_as_float(0x7f800000);
+  const bool axisOk = fabsf(dn) > 1e-30f; // below that the exact test rejects on |det| < 1e-5
+  const float rdn = rcp_fast(dn);
+  const float odn = on * rdn;
+  const float D = dabs * fabsf(rdn);
+  const float marg = Sr * __fmaf_rn(2e-5f, D, 2e-5f);
+  const float er = 4e-6f * D;                // relative error bound of t' (and of the exact t)
+  const float ea = 4e-6f * Sr * fabsf(rdn);  // absolute part
+  // candidate iff  t' + |t'|*er + ea > tmin  (upper bound of the true distance beyond tmin); as a threshold on t':
+  const float bt = tmin - ea;
+  const float tlo = !axisOk ? inf : (bt > 0.f ? bt * (1.0f - er) : (er < 0.5f ? bt * __fmaf_rn(2.0f, er, 1.0f) : -inf));
+  // lower bound of the true distance used for ordering / pruning:  t'*(1-er) - 3*ea  (valid for either sign of t'
+  // that passes the threshold); extreme grazing (er >= 0.5) gets -inf, i.e. is never pruned
+  const float cLo = er < 0.5f ? 1.0f - er : 0.f;
+  const float off = er < 0.5f ? 3.0f * ea : inf;
+#pragma unroll 2
+  for (int q = qBegin; q < qEnd; ++q)
+  {
+    const float4 a = *reinterpret_cast<const float4*>(&S.filt[q]); // c uc hu vc
+    const float hv = S.filt[q].hv;
+    const float tp = __fmaf_rn(a.x, rdn, -odn);
+    const float up = __fmaf_rn(tp, du, ou), vp = __fmaf_rn(tp, dv, ov);
+    const bool pass = (tp > tlo) & (fabsf(up - a.y) <= a.z + marg) & (fabsf(vp - a.w) <= hv + marg); // no short circuit
+    const float tl = pass ? __fmaf_rn(tp, cLo, -off) : inf;
+    F.t2 = fminf(F.t2, fmaxf(F.tbl, tl));
+    if (tl < F.tbl)
+      F.qb = q;
+    F.tbl = fminf(F.tbl, tl);
+    const uint32_t bit = 1u << q;
+    if (pass)
+      F.mask |= bit;
+  }
+}
+__device__ __forceinline__ void filt_frame(const B2SmallScene& S, int f, int& qBegin, f3 o, f3 d, float Sr, float tmin,
+                                           FiltState& F)
+{
+  const B2Frame& Fr = S.frames[f];
+  f3 ol = o, dl = d;
+  float Sf = Sr;
+  if (!Fr.identity)
+  {
+    const f3 r = mk3(o.x - Fr.org[0], o.y - Fr.org[1], o.z - Fr.org[2]);
+    ol = mk3(__fmaf_rn(Fr.R[0], r.x, __fmaf_rn(Fr.R[1], r.y, Fr.R[2] * r.z)),
+             __fmaf_rn(Fr.R[3], r.x, __fmaf_rn(Fr.R[4], r.y, Fr.R[5] * r.z)),
+             __fmaf_rn(Fr.R[6], r.x, __fmaf_rn(Fr.R[7], r.y, Fr.R[8] * r.z)));
+    dl = mk3(__fmaf_rn(Fr.R[0], d.x, __fmaf_rn(Fr.R[1], d.y, Fr.R[2] * d.z)),
+             __fmaf_rn(Fr.R[3], d.x, __fmaf_rn(Fr.R[4], d.y, Fr.R[5] * d.z)),
+             __fmaf_rn(Fr.R[6], d.x, __fmaf_rn(Fr.R[7], d.y, Fr.R[8] * d.z)));
+    Sf = 4.0f * Sr; // frame coordinates are relative to org: |.| <= 2*sqrt(3)*Sr
+  }
+  const float dabs = fabsf(dl.x) + fabsf(dl.y) + fabsf(dl.z);
+  filt_axis(S, qBegin, Fr.axisEnd[0], ol.x, dl.x, ol.y, dl.y, ol.z, dl.z, dabs, Sf, tmin, F);
+  filt_axis(S, max(qBegin, Fr.axisEnd[0]), Fr.axisEnd[1], ol.y, dl.y, ol.z, dl.z, ol.x, dl.x, dabs, Sf, tmin, F);
+  filt_axis(S, max(qBegin, Fr.axisEnd[1]), Fr.axisEnd[2], ol.z, dl.z, ol.x, dl.x, ol.y, dl.y, dabs, Sf, tmin, F);
+  qBegin = max(qBegin, Fr.axisEnd[2]);
+}
+
 // Closest hit over a kernel-parameter-resident scene.  MapperPathTracer.cxx:410-435: quads first
 // (QuadIntersector.cxx:59-71), then spheres continuing from the quads' closest distance
 // (SphereIntersector.cxx:88-100).  The reference's strict t<tmax keeps the first-tested primitive on an
-// exact-t tie; quads are tested here in a different order (axis-aligned classes, then boxed quads), so a tie
-// is resolved explicitly in favour of the lower original index -- the same winner as index order.
+// exact-t tie; quads are tested here in a different order (filter candidates nearest first, then boxed quads),
+// so a tie is resolved explicitly in favour of the lower original index -- the same winner as index order.
 #define B2PT_MISS 0x7fffffff
 __device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, float tmin, float tmax, float& tHit)
 {
   float closest = tmax;
   int slot = -1;
   int bestPrim = 0x7fffffff;
-  // ---- axis-aligned rectangles: specialised bit-identical test, one class (component permutation) at a time
-  int qb = 0;
-  for (int c = 0; c < 6; ++c)
-  {
-    const int qe = S.aaEnd[c];
-    if (qe > qb)
+  auto test_quad = [&](int q) {
+    const B2Quad& Q = S.quads[q];
+    float t;
+    if (quad_hit(Q, o, d, t) && t > tmin && (t < closest || (t == closest && Q.prim < bestPrim)))
     {
-      float du, dv, dn, ou, ov, on;
-      aa_permute(c, d, du, dv, dn);
-      aa_permute(c, o, ou, ov, on);
-      for (int q = qb; q < qe; ++q)
-      {
-        const B2AAQuad& Q = S.aa[q];
-        float t;
-        const bool hit = aa_quad_hit(Q, du, dv, dn, ou, ov, on, t);
-        if (hit && t > tmin && (t < closest || (t == closest && Q.prim < bestPrim)))
-        {
-          closest = t;
-          slot = Q.slot;
-          bestPrim = Q.prim;
-        }
-      }
+      closest = t;
+      slot = q;
+      bestPrim = Q.prim;
     }
-    qb = qe;
+  };
+  // ---- phase 1: candidate filter over the frame-aligned planar quads (uniform control flow)
+  if (S.nFilt > 0)
+  {
+    FiltState F;
+    F.mask = 0u;
+    F.tbl = F.t2 = __int_as_float(0x7f800000);
+    F.qb = 0;
+    const float Sr = fmaxf(S.sceneAbs, fmaxf(fabsf(o.x), fmaxf(fabsf(o.y), fabsf(o.z))));
+    int qBegin = 0;
+    for (int f = 0; f < S.nFrames; ++f)
+      filt_frame(S, f, qBegin, o, d, Sr, tmin, F);
+    // ---- phase 2: the reference's exact test on the candidates, nearest lower bound first.  Every other
+    // candidate's exact t is >= its lower bound >= t2, so once the nearest one is accepted with closest < t2
+    // none of them can win or tie.
+    uint32_t rest = F.mask;
+    int q = F.qb;
+    while (rest)
+    {
+      rest &= ~(1u << q);
+      test_quad(q);
+      if (slot >= 0 && F.t2 > closest) // valid from the first iteration on: F.qb is tested first
+        break;
+      q = __ffs((int)rest) - 1;
+    }
   }
   // ---- remaining quads behind the slab test of their own leaf box (BVHTraverser.h:35-79, 143-157)
   if (S.firstBoxed < S.nQuads)
@@ -708,8 +802,11 @@ __device__ __forceinline__ BounceResult shade_lambert(const B2Lights& lights, co
   else if (which == 2)
   {
     g = mk3(0.f, 0.f, 0.f);
-    for (int l = 0; l < lights.nLightQuads; ++l)
+#pragma unroll
+    for (int l = 0; l < B2PT_MAX_LIGHT_QUADS; ++l)
     {
+      if (l >= lights.nLightQuads)
+        break;
       const B2LightQuad& LQ = lights.lq[l];
       float r1 = randf(rng);
       float r2 = randf(rng);
@@ -722,8 +819,11 @@ __device__ __forceinline__ BounceResult shade_lambert(const B2Lights& lights, co
   else
   {
     g = mk3(0.f, 0.f, 0.f);
-    for (int l = 0; l < lights.nLightSph; ++l)
+#pragma unroll
+    for (int l = 0; l < B2PT_MAX_LIGHT_SPH; ++l)
     {
+      if (l >= lights.nLightSph)
+        break;
       // PdfWorklet.h:210: argument evaluation order of GCC x86-64 (right to left): r2 is drawn first
       float r2 = randf(rng);
       float r1 = randf(rng);
@@ -737,10 +837,14 @@ __device__ __forceinline__ BounceResult shade_lambert(const B2Lights& lights, co
   wang32(rng); // SpherePDFWorklet's unused index draw (PdfWorklet.h:393)
   // light pdfs: sum = weight*quad + weight*sphere (no occlusion test in either)
   float sum = 0.f;
-  for (int l = 0; l < lights.nLightQuads; ++l)
-    sum += lights.weight * quad_pdf_value(lights.lq[l], hit.p, g);
-  for (int l = 0; l < lights.nLightSph; ++l)
-    sum += lights.weight * sphere_pdf_value(lights.ls[l], hit.p, g);
+#pragma unroll
+  for (int l = 0; l < B2PT_MAX_LIGHT_QUADS; ++l)
+    if (l < lights.nLightQuads)
+      sum += lights.weight * quad_pdf_value(lights.lq[l], hit.p, g);
+#pragma unroll
+  for (int l = 0; l < B2PT_MAX_LIGHT_SPH; ++l)
+    if (l < lights.nLightSph)
+      sum += lights.weight * sphere_pdf_value(lights.ls[l], hit.p, g);
   // ScatterWorklet.h:20-28, 52-58, 95-110
   f3 ug = unit3(g);
   float cosw = dot3(ug, unit3(hit.n));

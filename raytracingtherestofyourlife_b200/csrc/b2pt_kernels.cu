@@ -197,21 +197,22 @@ __global__ void __launch_bounds__(kBlock, kTraceMinBlocksPerSM)
         }
       }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
+    // destination of this lane's record: rank among the lanes of its bin on top of the bin's register counter;
+    // the four ballots are warp-uniform work, the stores happen once (no per-bin divergent blocks)
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned b0 = __ballot_sync(0xffffffffu, bin == 0), b1 = __ballot_sync(0xffffffffu, bin == 1);
+    const unsigned b2 = __ballot_sync(0xffffffffu, bin == 2), b3 = __ballot_sync(0xffffffffu, bin == 3);
+    if (bin >= 0)
     {
-      const unsigned ballot = __ballot_sync(0xffffffffu, bin == k);
-      uint32_t& cnt = (k == 0 ? cnt0 : (k == 1 ? cnt1 : (k == 2 ? cnt2 : cnt3)));
-      if (bin == k)
-      {
-        const int64_t j = (int64_t)k * A.binStride + base + cnt + __popc(ballot & ((1u << lane) - 1u));
-        A.bin0[j] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
-        A.bin1[j] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
-        A.bin2[j] = make_uint4(__float_as_uint(T.z), pid, rng, __float_as_uint(t));
-        A.binCode[j] = (uint32_t)code;
-      }
-      cnt += __popc(ballot);
+      const unsigned mine = bin == 0 ? b0 : (bin == 1 ? b1 : (bin == 2 ? b2 : b3));
+      const uint32_t cnt = bin == 0 ? cnt0 : (bin == 1 ? cnt1 : (bin == 2 ? cnt2 : cnt3));
+      const int64_t j = (int64_t)bin * A.binStride + base + cnt + __popc(mine & lt);
+      A.bin0[j] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
+      A.bin1[j] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
+      A.bin2[j] = make_uint4(__float_as_uint(T.z), pid, rng, __float_as_uint(t));
+      A.binCode[j] = (uint32_t)code;
     }
+    cnt0 += __popc(b0), cnt1 += __popc(b1), cnt2 += __popc(b2), cnt3 += __popc(b3);
   }
   if (lane == 0)
   {
@@ -458,7 +459,7 @@ cudaError_t query_launch_cfg(LaunchCfg* cfg)
 // args.numWarps regions (cfg.persistentBlocks CTAs of kWarps warps).
 cudaError_t launch_bounce(const LaunchCfg& cfg, bool primary, const B2Camera& cam, const B2SmallScene* small,
                           const B2BvhScene* bvh, const B2Lights& lights, const B2RenderArgs& args, int64_t,
-                          cudaStream_t stream)
+                          cudaStream_t stream, cudaEvent_t betweenStages)
 {
   const int grid = (args.numWarps + kWarps - 1) / kWarps;
   (void)cfg;
@@ -468,6 +469,8 @@ cudaError_t launch_bounce(const LaunchCfg& cfg, bool primary, const B2Camera& ca
       k_trace<true, B2BvhScene><<<grid, kBlock, 0, stream>>>(cam, *bvh, args);
     else
       k_trace<false, B2BvhScene><<<grid, kBlock, 0, stream>>>(cam, *bvh, args);
+    if (betweenStages)
+      cudaEventRecord(betweenStages, stream);
     k_shade<B2BvhScene><<<grid, kBlock, 0, stream>>>(*bvh, lights, args);
   }
   else
@@ -476,6 +479,8 @@ cudaError_t launch_bounce(const LaunchCfg& cfg, bool primary, const B2Camera& ca
       k_trace<true, B2SmallScene><<<grid, kBlock, 0, stream>>>(cam, *small, args);
     else
       k_trace<false, B2SmallScene><<<grid, kBlock, 0, stream>>>(cam, *small, args);
+    if (betweenStages)
+      cudaEventRecord(betweenStages, stream);
     k_shade<B2SmallScene><<<grid, kBlock, 0, stream>>>(*small, lights, args);
   }
   return cudaGetLastError();

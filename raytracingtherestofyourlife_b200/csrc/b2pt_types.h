@@ -119,18 +119,46 @@ struct alignas(16) B2Lights
   B2LightSphere ls[B2PT_MAX_LIGHT_SPH];
 };
 
+// Candidate filter of the small-scene trace (closest_small, phase 1).  A planar quad whose plane is normal to one
+// axis of a FRAME (frame 0 = world axes; further frames are rotated boxes such as the Cornell tall box) is
+// described by that plane's coordinate and the bounding rectangle of its vertices on the other two axes
+// (u = axis n+1, v = axis n+2, cyclic).  The filter intersects the ray with the plane in fast arithmetic (FMA,
+// MUFU.RCP) and keeps the quad as a CANDIDATE when the hit point lies inside the rectangle widened by a rigorous
+// error margin; only candidates run the reference's Lagae-Dutre test (quad_hit), so accepted hits and their t
+// stay bit-identical.  Margins: DESIGN.md "candidate filter".
+struct alignas(16) B2FiltQuad // 32 B, two 16-byte chunks
+{
+  float c;      // plane coordinate on the frame axis n
+  float uc, hu; // rectangle centre / half width (static margin included) on axis u
+  float vc;
+  float hv;
+  int32_t slot; // index into quads[] (== position in filt[]: filtered quads come first)
+  int32_t pad[2];
+};
+struct alignas(16) B2Frame // 64 B
+{
+  float R[9];         // rows = frame axes in world coordinates (world -> frame rotation)
+  float org[3];       // frame origin (subtracted before the rotation)
+  int32_t axisEnd[3]; // end index in filt[] of the quads normal to frame axis 0,1,2 (cumulative over frames)
+  int32_t identity;   // 1: world axes, no transform
+};
+#define B2PT_MAX_FRAMES 4
+#define B2PT_MAX_FILT 32
+
 struct alignas(16) B2SmallScene
 {
   int32_t nQuads, nSph;
-  int32_t nGate, nAA;
-  // Trace order: axis-aligned quads aa[0..nAA) grouped by class (aaEnd[c] = end of class c); then the other
+  int32_t nGate, nFilt;
+  // Trace order: filtered quads quads[0..nFilt) through the two-phase candidate filter; then the remaining
   // quads, quads[firstBoxed..nQuads), each behind the slab test of its own leaf box gate[quad.gate-1] --
   // planar ones first (the box is a conservative filter there), non-planar ones last (the box is part of the
   // acceptance rule); then the spheres.  quads[] holds every traced quad (attributes by slot).
-  int32_t aaEnd[6];
-  int32_t firstBoxed, pad1;
+  int32_t firstBoxed, nFrames;
+  float sceneAbs; // max |coordinate| of the traced primitives (scale of the filter margins)
+  int32_t pad1;
+  B2Frame frames[B2PT_MAX_FRAMES];
+  B2FiltQuad filt[B2PT_MAX_FILT];
   B2GateBox gate[B2PT_SMALL_MAX_GATES];
-  B2AAQuad aa[B2PT_SMALL_MAX_QUADS];
   B2Quad quads[B2PT_SMALL_MAX_QUADS];
   B2Sphere sph[B2PT_SMALL_MAX_SPH];
 };
