@@ -298,7 +298,9 @@ def main():
         # (b2pt_get_stage_profile).  Algorithmic bytes = 88 B per live segment of that bounce (SURVEY.md 8d:
         # 44 B ray record read + 44 B written per bounce), charged against BOTH launches' time.
         prof = ctx_profile
-        top = max(range(len(prof)), key=lambda k: prof[k][0] + prof[k][1]) if prof else None
+        # bounce 0 generates its rays in registers (no queue read), so the 88 B figure applies from bounce 1 on
+        cand = range(1, len(prof)) if len(prof) > 1 else range(len(prof))
+        top = max(cand, key=lambda k: prof[k][0] + prof[k][1]) if prof else None
         if top is not None and prof[top][0] + prof[top][1] > 0:
             tr_ms, sh_ms, top_rays = prof[top]
             achieved = top_rays * ALGO_BYTES_PER_SEGMENT / ((tr_ms + sh_ms) * 1e-3) / 1e9

@@ -47,6 +47,7 @@ typedef enum b2pt_status
                                                with B2PT_FLAG_REFERENCE_STREAM */
 #define B2PT_FLAG_NO_DEDUP 0x4u             /* keep bit-identical duplicate quads in the trace list */
 #define B2PT_FLAG_FORCE_BVH 0x8u            /* use the BVH traversal kernels even for small scenes */
+#define B2PT_FLAG_NO_TAIL 0x20u             /* never switch deep bounces to the global-queue tail mode (A/B parity checks) */
 #define B2PT_FLAG_NO_AA 0x10u               /* do not use the axis-aligned quad specialisation (A/B parity checks) */
 
 typedef struct b2pt_stats
@@ -63,6 +64,8 @@ typedef struct b2pt_stats
   int32_t bvhNodes;
   int32_t tracedQuads; /* quads in the trace list after dedup */
   int32_t tracedSpheres;
+  int32_t tailDepth;  /* first bounce run in tail mode (global queue); == maxDepth when never */
+  int32_t loopDepth;  /* first bounce run inside the persistent cluster launch; == maxDepth when never */
 } b2pt_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */

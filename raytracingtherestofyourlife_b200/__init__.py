@@ -14,7 +14,7 @@ import numpy as np
 from . import _build
 
 __all__ = ["lib", "Scene", "Camera", "Context", "B2ptError", "Stats", "FLAG_REFERENCE_STREAM",
-           "FLAG_KILL_ZERO_THROUGHPUT", "FLAG_NO_DEDUP", "FLAG_FORCE_BVH", "FLAG_NO_AA", "LIB_PATH"]
+           "FLAG_KILL_ZERO_THROUGHPUT", "FLAG_NO_DEDUP", "FLAG_FORCE_BVH", "FLAG_NO_AA", "FLAG_NO_TAIL", "LIB_PATH"]
 
 LIB_PATH = _build.LIB
 FLAG_REFERENCE_STREAM = 0x1
@@ -22,6 +22,7 @@ FLAG_KILL_ZERO_THROUGHPUT = 0x2
 FLAG_NO_DEDUP = 0x4
 FLAG_FORCE_BVH = 0x8
 FLAG_NO_AA = 0x10
+FLAG_NO_TAIL = 0x20
 
 ERR_BAD_VALUE, ERR_CUDA, ERR_STATE, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 
@@ -36,7 +37,8 @@ class Stats(C.Structure):
     _fields_ = [("paths", C.c_int64), ("segments", C.c_int64), ("nanSamples", C.c_int64), ("launches", C.c_int64),
                 ("queueBytes", C.c_int64), ("renderMs", C.c_double), ("batches", C.c_int32),
                 ("samplesPerBatch", C.c_int32), ("tracePath", C.c_int32), ("bvhNodes", C.c_int32),
-                ("tracedQuads", C.c_int32), ("tracedSpheres", C.c_int32)]
+                ("tracedQuads", C.c_int32), ("tracedSpheres", C.c_int32), ("tailDepth", C.c_int32),
+                ("loopDepth", C.c_int32)]
 
 
 _lib = None

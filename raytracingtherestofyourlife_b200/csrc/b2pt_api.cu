@@ -135,6 +135,7 @@ struct b2pt_ctx
   DevBuf<uint32_t> regionCounts; // qCount[numWarps] + binCount[4*numWarps]
   DevBuf<float4> rad;
   DevBuf<uint32_t> counters;
+  DevBuf<uint32_t> binTotals; // tail mode: per batch, per depth, per bin record counts
   DevBuf<uint32_t> seeds;
   DevBuf<unsigned long long> nanCounter;
   std::vector<uint32_t> hCounters;
@@ -827,6 +828,30 @@ int b2pt_clear_color(b2pt_ctx* ctx)
   return B2PT_OK;
 }
 
+static int64_t tail_rays_per_warp()
+{
+  const char* e = getenv("B2PT_TAIL_RAYS_PER_WARP");
+  if (e)
+  {
+    long long v = atoll(e);
+    if (v >= 0)
+      return v;
+  }
+  return 512; // below 16 tiles per region the four strategy bins stop filling whole warps (measured flat 256..2048)
+}
+
+static int64_t tail_loop_rays()
+{
+  const char* e = getenv("B2PT_TAIL_LOOP_RAYS");
+  if (e)
+  {
+    long long v = atoll(e);
+    if (v >= 0)
+      return v;
+  }
+  return 24576; // ~break-even between one 8-SM cluster pass and a full-grid launch pair
+}
+
 static int64_t batch_target_paths()
 {
   const char* e = getenv("B2PT_BATCH_PATHS");
@@ -895,9 +920,11 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
   CU(ctx->rad.reserve((size_t)pathsPerBatch));
   const int64_t nCounters = std::max<int64_t>(1, nBatches * maxDepth); // rays entering bounce d+1, per batch
   CU(ctx->counters.reserve((size_t)nCounters));
+  CU(ctx->binTotals.reserve((size_t)nCounters * 4));
   CU(ctx->nanCounter.reserve(1));
   CU(cudaEventRecord(ctx->evStart, ctx->stream));
   CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(uint32_t) * (size_t)nCounters, ctx->stream));
+  CU(cudaMemsetAsync(ctx->binTotals.p, 0, sizeof(uint32_t) * (size_t)nCounters * 4, ctx->stream));
   CU(cudaMemsetAsync(ctx->nanCounter.p, 0, sizeof(unsigned long long), ctx->stream));
   if (refStream)
   {
@@ -906,6 +933,8 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
   }
 
   int64_t launches = refStream ? 1 : 0;
+  int tailDepth = maxDepth; // bounces >= tailDepth run in tail mode; chosen after the first batch
+  int loopDepth = maxDepth; // bounces >= loopDepth (>= tailDepth) run inside one persistent cluster launch
   const int profDepths = std::min(maxDepth - 1, (int)b2pt_ctx::kProfDepths); // events 0..profDepths bracket that many bounces
   ctx->profDepths = nBatches > 0 ? profDepths : 0;
   ctx->profPaths = nBatches > 0 ? N * std::min<int64_t>(B, sampleCount) : 0;
@@ -915,6 +944,7 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
     const int64_t nb = std::min<int64_t>(B, sampleCount - s0);
     B2RenderArgs A{};
     A.depthTotals = ctx->counters.p + batch * maxDepth;
+    A.binTotals = ctx->binTotals.p + batch * maxDepth * 4;
     A.rad = ctx->rad.p;
     A.bin0 = ctx->bins[0].p, A.bin1 = ctx->bins[1].p, A.bin2 = ctx->bins[2].p;
     A.binCode = ctx->binCode.p;
@@ -947,12 +977,42 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
         mid = ctx->evMid[depth];
       }
       A.depth = depth;
-      CU(b2pt::launch_bounce(ctx->cfg, depth == 0, ctx->cam, ctx->useBvh ? nullptr : &ctx->small,
-                             ctx->useBvh ? &ctx->bvh : nullptr, ctx->lights, A, A.nPaths, ctx->stream, mid));
+      if (depth >= loopDepth)
+      { // every remaining bounce in one cluster launch
+        CU(b2pt::launch_tail_loop(ctx->cam, ctx->useBvh ? nullptr : &ctx->small, ctx->useBvh ? &ctx->bvh : nullptr,
+                                  ctx->lights, A, ctx->stream));
+        ++launches;
+        break;
+      }
+      const int mode = depth >= tailDepth ? b2pt::B2PT_BOUNCE_TAIL
+                                          : (depth == tailDepth - 1 ? b2pt::B2PT_BOUNCE_TO_GLOBAL : b2pt::B2PT_BOUNCE_REGIONS);
+      CU(b2pt::launch_bounce(ctx->cfg, depth == 0, mode, ctx->cam, ctx->useBvh ? nullptr : &ctx->small,
+                             ctx->useBvh ? &ctx->bvh : nullptr, ctx->lights, A, ctx->stream, mid));
       launches += 2;
     }
     CU(b2pt::launch_accumulate(ctx->color(), ctx->rad.p, (int)N, (int)nb, ctx->nanCounter.p, ctx->stream));
     ++launches;
+    if (batch == 0 && nBatches > 1 && tailDepth == maxDepth && !(flags & B2PT_FLAG_NO_TAIL) && maxDepth > 2)
+    { // Tail mode for the remaining batches: from the first bounce that less than tailRaysPerWarp rays per region
+      // enter, rays live in one flat global queue (k_trace TAIL).  Decided from the first batch's own counters: one
+      // stream synchronisation per render.
+      CU(cudaStreamSynchronize(ctx->stream));
+      std::vector<uint32_t> first((size_t)maxDepth);
+      CU(cudaMemcpy(first.data(), ctx->counters.p, sizeof(uint32_t) * (size_t)maxDepth, cudaMemcpyDeviceToHost));
+      const int64_t threshold = numWarps * tail_rays_per_warp();
+      for (int d = 1; d < maxDepth; ++d) // first[d-1] = rays entering bounce d
+        if ((int64_t)first[(size_t)d - 1] < threshold)
+        {
+          tailDepth = d;
+          break;
+        }
+      for (int d = tailDepth; d < maxDepth; ++d)
+        if ((int64_t)first[(size_t)d - 1] < tail_loop_rays())
+        {
+          loopDepth = d;
+          break;
+        }
+    }
   }
   CU(cudaEventRecord(ctx->evStop, ctx->stream));
 
@@ -962,6 +1022,8 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
   ctx->stats.batches = (int32_t)nBatches;
   ctx->stats.samplesPerBatch = (int32_t)B;
   ctx->stats.tracePath = ctx->useBvh ? 1 : 0;
+  ctx->stats.tailDepth = tailDepth;
+  ctx->stats.loopDepth = loopDepth;
   ctx->stats.bvhNodes = ctx->bvhNodes;
   ctx->stats.tracedQuads = ctx->tracedQuads;
   ctx->stats.tracedSpheres = ctx->tracedSph;

@@ -307,6 +307,10 @@ __device__ __forceinline__ void aa_permute(int c, f3 a, float& u, float& v, floa
 // ---- phase 1 of the small-scene trace: candidate filter (B2FiltQuad).  All 32 lanes run the same
 // straight-line code per quad (no divergence); the output per lane is the candidate bit mask, the candidate
 // with the smallest LOWER BOUND of its hit distance and the second-smallest lower bound.
+#ifndef B2PT_FILT_UNROLL
+#define B2PT_FILT_UNROLL 2
+#endif
+constexpr int kFiltUnroll = B2PT_FILT_UNROLL;
 struct FiltState
 {
   uint32_t mask; // candidate quads (bit = filt index)
@@ -346,7 +350,7 @@ __device__ __forceinline__ void filt_axis(const B2SmallScene& S, int qBegin, int
   // that passes the threshold); extreme grazing (er >= 0.5) gets -inf, i.e. is never pruned
   const float cLo = er < 0.5f ? 1.0f - er : 0.f;
   const float off = er < 0.5f ? 3.0f * ea : inf;
-#pragma unroll 2
+#pragma unroll kFiltUnroll
   for (int q = qBegin; q < qEnd; ++q)
   {
     const float4 a = *reinterpret_cast<const float4*>(&S.filt[q]); // c uc hu vc

@@ -18,6 +18,9 @@
 #include "b2pt_device.cuh"
 #include "b2pt_kernels.h"
 
+#include <algorithm>
+#include <cooperative_groups.h>
+
 namespace b2pt
 {
 
@@ -102,9 +105,11 @@ __device__ __forceinline__ void load_ray(const B2Camera& cam, const B2RenderArgs
   }
   else
   {
-    const uint4 a = A.q.p0[idx];
-    const uint4 b = A.q.p1[idx];
-    const uint4 c = A.q.p2[idx];
+    // .cg loads: queue data is streamed once, and the persistent tail kernel re-reads addresses that other
+    // SMs rewrote earlier in the same launch (L1 is not coherent)
+    const uint4 a = __ldcg(A.q.p0 + idx);
+    const uint4 b = __ldcg(A.q.p1 + idx);
+    const uint4 c = __ldcg(A.q.p2 + idx);
     o = mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
     d = mk3(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
     T = mk3(__uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(c.x));
@@ -133,39 +138,19 @@ __device__ __forceinline__ void finish_path(const B2RenderArgs& A, uint32_t pid,
 // warp-uniform work with all 32 lanes alive.  The ray AND its hit (t, primitive) are appended to the warp's
 // region of the bin as one dense 52-byte record (coalesced 16-byte stores): ballot + popcount prefix on top of
 // a register counter, no atomics.
-template <bool PRIMARY, class SceneT>
-__global__ void __launch_bounds__(kBlock, kTraceMinBlocksPerSM)
-  k_trace(const __grid_constant__ B2Camera cam, const __grid_constant__ SceneT scene,
-          const __grid_constant__ B2RenderArgs A)
+// TAIL = true (deep bounces, few rays left): the input is ONE flat global queue of A.depthTotals[depth-1] rays
+// and the four bins are global too; warps take 32-ray tiles grid-stride and append with one warp-aggregated
+// atomicAdd per non-empty bin per tile.  Per-warp regions would leave thousands of warps with a handful of rays
+// each (DESIGN.md "tail mode").
+// Work of one warp in k_trace: rays [.., nIn) of its region (TAIL: tiles w, w+tailWarps, ... of the flat queue).
+template <bool PRIMARY, class SceneT, bool TAIL>
+__device__ __forceinline__ void trace_body(const B2Camera& cam, const SceneT& S, const B2RenderArgs& A, int depth,
+                                           int w, int lane, int64_t nIn, int64_t tailWarps)
 {
-  const int w = blockIdx.x * kWarps + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  const int64_t base = (int64_t)w * A.regionCap;
-  // PRIMARY: the batch's 32-path tiles are dealt round-robin to the warps (tile j of warp w is global tile
-  // j*numWarps + w), so every region samples the whole image and the regions shrink at the same rate;
-  // contiguous pixel ranges would leave the regions that cover the image border (rays that miss) empty.
-  const int64_t tilesTotal = (A.nPaths + 31) >> 5;
-  int64_t nIn;
-  if (PRIMARY)
-    nIn = w < A.numWarps && tilesTotal > w ? ((tilesTotal - 1 - w) / A.numWarps + 1) * 32 : 0;
-  else
-    nIn = w < A.numWarps ? (int64_t)A.qCount[w] : 0;
-  // CTAs whose eight regions are all empty (deep bounces) leave before staging the scene.
-  if (!__syncthreads_or(nIn > 0))
-  {
-    if (w < A.numWarps && lane == 0)
-      for (int k = 0; k < 4; ++k)
-        A.binCount[k * A.numWarps + w] = 0;
-    return;
-  }
-  __shared__ StageArea<SceneT> sStage;
-  const SceneT& S = stage_scene(scene, sStage);
-  __syncthreads();
-  if (w >= A.numWarps)
-    return;
+  const int64_t base = TAIL ? 0 : (int64_t)w * A.regionCap;
   const bool refStream = (A.flags & B2PT_FLAG_REFERENCE_STREAM_DEV) != 0;
   uint32_t cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
-  for (int64_t i0 = 0; i0 < nIn; i0 += 32)
+  for (int64_t i0 = TAIL ? (int64_t)w * 32 : 0; i0 < nIn; i0 += TAIL ? tailWarps * 32 : 32)
   {
     const int64_t i = i0 + lane;
     int bin = -1;
@@ -179,7 +164,7 @@ __global__ void __launch_bounds__(kBlock, kTraceMinBlocksPerSM)
       load_ray<PRIMARY>(cam, A, idx, o, d, T, pid, rng);
       code = closest_hit(S, o, d, 0.001f, FLT_MAX, t);
       if (code == B2PT_MISS)
-        finish_path(A, pid, T * 0.f, rng, refStream, A.maxDepth - A.depth); // a[d]=1, e[d]=0
+        finish_path(A, pid, T * 0.f, rng, refStream, A.maxDepth - depth); // a[d]=1, e[d]=0
       else
       {
         const int kind = hit_kind(S, code);
@@ -188,7 +173,7 @@ __global__ void __launch_bounds__(kBlock, kTraceMinBlocksPerSM)
           Hit hit;
           fill_hit(S, code, o, d, t, hit);
           const f3 em = (dot3(hit.n, d) < 0.0f) ? hit.alb : mk3(0.f, 0.f, 0.f);
-          finish_path(A, pid, mul3(T, em), rng, refStream, A.maxDepth - A.depth);
+          finish_path(A, pid, mul3(T, em), rng, refStream, A.maxDepth - depth);
         }
         else
         {
@@ -197,11 +182,24 @@ __global__ void __launch_bounds__(kBlock, kTraceMinBlocksPerSM)
         }
       }
     }
-    // destination of this lane's record: rank among the lanes of its bin on top of the bin's register counter;
-    // the four ballots are warp-uniform work, the stores happen once (no per-bin divergent blocks)
+    // destination of this lane's record: rank among the lanes of its bin on top of the bin's counter (a
+    // register per warp region; tail mode: one atomicAdd per non-empty bin per tile); the four ballots are
+    // warp-uniform work, the stores happen once (no per-bin divergent blocks)
     const unsigned lt = (1u << lane) - 1u;
     const unsigned b0 = __ballot_sync(0xffffffffu, bin == 0), b1 = __ballot_sync(0xffffffffu, bin == 1);
     const unsigned b2 = __ballot_sync(0xffffffffu, bin == 2), b3 = __ballot_sync(0xffffffffu, bin == 3);
+    if (TAIL)
+    {
+      uint32_t got = 0;
+      if (lane < 4)
+      {
+        const unsigned bk = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
+        if (bk)
+          got = atomicAdd(&A.binTotals[depth * 4 + lane], (uint32_t)__popc(bk));
+      }
+      cnt0 = __shfl_sync(0xffffffffu, got, 0), cnt1 = __shfl_sync(0xffffffffu, got, 1);
+      cnt2 = __shfl_sync(0xffffffffu, got, 2), cnt3 = __shfl_sync(0xffffffffu, got, 3);
+    }
     if (bin >= 0)
     {
       const unsigned mine = bin == 0 ? b0 : (bin == 1 ? b1 : (bin == 2 ? b2 : b3));
@@ -212,9 +210,10 @@ __global__ void __launch_bounds__(kBlock, kTraceMinBlocksPerSM)
       A.bin2[j] = make_uint4(__float_as_uint(T.z), pid, rng, __float_as_uint(t));
       A.binCode[j] = (uint32_t)code;
     }
-    cnt0 += __popc(b0), cnt1 += __popc(b1), cnt2 += __popc(b2), cnt3 += __popc(b3);
+    if (!TAIL)
+      cnt0 += __popc(b0), cnt1 += __popc(b1), cnt2 += __popc(b2), cnt3 += __popc(b3);
   }
-  if (lane == 0)
+  if (!TAIL && lane == 0)
   {
     A.binCount[0 * A.numWarps + w] = cnt0;
     A.binCount[1 * A.numWarps + w] = cnt1;
@@ -223,40 +222,72 @@ __global__ void __launch_bounds__(kBlock, kTraceMinBlocksPerSM)
   }
 }
 
-// K3+K5: material response, direction generator, light pdfs, mixture pdf and the next ray for every binned hit
-// of the warp's regions; survivors are compacted into the warp's region of the ray queue.  A warp works on 32
-// consecutive records of ONE bin, so the strategy branch is warp-uniform.
-template <class SceneT>
-__global__ void __launch_bounds__(kBlock, kMinBlocksPerSM)
-  k_shade(const __grid_constant__ SceneT scene, const __grid_constant__ B2Lights lights,
+template <bool PRIMARY, class SceneT, bool TAIL>
+__global__ void __launch_bounds__(kBlock, kTraceMinBlocksPerSM)
+  k_trace(const __grid_constant__ B2Camera cam, const __grid_constant__ SceneT scene,
           const __grid_constant__ B2RenderArgs A)
 {
+  static_assert(!(PRIMARY && TAIL), "primary rays are never traced in tail mode");
   const int w = blockIdx.x * kWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  const int64_t base = (int64_t)w * A.regionCap;
-  uint32_t nAny = 0;
-  if (w < A.numWarps)
-    nAny = A.binCount[w] | A.binCount[A.numWarps + w] | A.binCount[2 * A.numWarps + w] | A.binCount[3 * A.numWarps + w];
-  if (!__syncthreads_or(nAny != 0))
-  { // nothing binned for any warp of this CTA: its queue regions become empty, no staging needed
+  // PRIMARY: the batch's 32-path tiles are dealt round-robin to the warps (tile j of warp w is global tile
+  // j*numWarps + w), so every region samples the whole image and the regions shrink at the same rate;
+  // contiguous pixel ranges would leave the regions that cover the image border (rays that miss) empty.
+  const int64_t tilesTotal = (A.nPaths + 31) >> 5;
+  const int64_t tailWarps = (int64_t)gridDim.x * kWarps;
+  int64_t nIn;
+  if (TAIL)
+  {
+    const int64_t nAll = (int64_t)A.depthTotals[A.depth - 1];
+    // rays of this warp: tiles w, w + tailWarps, ... of the flat queue (the last tile may be partial)
+    nIn = nAll;
+    if ((int64_t)blockIdx.x * kWarps * 32 >= nAll)
+      return; // no tile for any warp of this CTA
+  }
+  else if (PRIMARY)
+    nIn = w < A.numWarps && tilesTotal > w ? ((tilesTotal - 1 - w) / A.numWarps + 1) * 32 : 0;
+  else
+    nIn = w < A.numWarps ? (int64_t)A.qCount[w] : 0;
+  // CTAs whose eight regions are all empty (deep bounces) leave before staging the scene.
+  if (!TAIL && !__syncthreads_or(nIn > 0))
+  {
     if (w < A.numWarps && lane == 0)
-      A.qCount[w] = 0;
+      for (int k = 0; k < 4; ++k)
+        A.binCount[k * A.numWarps + w] = 0;
     return;
   }
   __shared__ StageArea<SceneT> sStage;
   const SceneT& S = stage_scene(scene, sStage);
-  const B2Lights& LT = stage_lights(lights, sStage);
   __syncthreads();
-  if (w >= A.numWarps)
+  if (!TAIL && w >= A.numWarps)
     return;
-  const bool lastDepth = (A.depth == A.maxDepth - 1);
+  trace_body<PRIMARY, SceneT, TAIL>(cam, S, A, A.depth, w, lane, nIn, tailWarps);
+}
+
+// K3+K5: material response, direction generator, light pdfs, mixture pdf and the next ray for every binned hit
+// of the warp's regions; survivors are compacted into the warp's region of the ray queue.  A warp works on 32
+// consecutive records of ONE bin, so the strategy branch is warp-uniform.
+// TAIL_IN: the bins are global (binTotals[depth*4+k] records, tiles taken grid-stride).  GLOBAL_OUT: survivors are
+// appended to ONE flat global queue (warp-aggregated atomicAdd on A.depthTotals[depth]) instead of the warp's region;
+// used by the last regular bounce before the tail and by every tail bounce.
+// Work of one warp in k_shade: the four bins of its region (TAIL_IN: tiles of the global bins, dealt so that the
+// bins of a nearly empty queue land on different warps).
+template <class SceneT, bool TAIL_IN, bool GLOBAL_OUT>
+__device__ __forceinline__ void shade_body(const SceneT& S, const B2Lights& LT, const B2RenderArgs& A, int depth, int w,
+                                           int lane, int64_t tailWarps)
+{
+  const int64_t base = TAIL_IN ? 0 : (int64_t)w * A.regionCap;
+  const bool lastDepth = (depth == A.maxDepth - 1);
   const bool refStream = (A.flags & B2PT_FLAG_REFERENCE_STREAM_DEV) != 0;
   uint32_t qcnt = 0;
   for (int k = 0; k < 4; ++k)
   {
-    const int64_t nk = A.binCount[k * A.numWarps + w];
+    const int64_t nk =
+      TAIL_IN ? (int64_t)__ldcg(&A.binTotals[depth * 4 + k]) : (int64_t)A.binCount[k * A.numWarps + w];
     const int64_t binBase = (int64_t)k * A.binStride + base;
-    for (int64_t i0 = 0; i0 < nk; i0 += 32)
+    // TAIL_IN: tile t of bin k goes to warp (t + k*tailWarps/4) mod tailWarps
+    const int64_t wk = TAIL_IN ? (w + tailWarps - (k * tailWarps) / 4) % tailWarps : 0;
+    for (int64_t i0 = TAIL_IN ? wk * 32 : 0; i0 < nk; i0 += TAIL_IN ? tailWarps * 32 : 32)
     {
       const int64_t i = i0 + lane;
       bool survive = false;
@@ -265,14 +296,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM)
       if (i < nk)
       {
         const int64_t j = binBase + i;
-        const uint4 a = A.bin0[j], b = A.bin1[j], c = A.bin2[j];
+        const uint4 a = __ldcg(A.bin0 + j), b = __ldcg(A.bin1 + j), c = __ldcg(A.bin2 + j);
         o = mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
         d = mk3(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
         T = mk3(__uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(c.x));
         pid = c.y;
         rng = c.z;
         Hit hit;
-        fill_hit(S, (int)A.binCode[j], o, d, __uint_as_float(c.w), hit);
+        fill_hit(S, (int)__ldcg(A.binCode + j), o, d, __uint_as_float(c.w), hit);
         f3 L;
         BounceResult r = (k == 0) ? shade(LT, true, hit, o, d, T, rng, A.flags, L)
                                   : shade_lambert(LT, hit, o, d, T, rng, A.flags, L);
@@ -285,18 +316,97 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM)
         else
           survive = true;
       }
-      // ---- K5: compaction of survivors into the warp's queue region: ballot + popcount prefix
+      // ---- K5: compaction of survivors: ballot + popcount prefix on top of the warp region's register counter
+      // (GLOBAL_OUT: on top of one atomicAdd per tile on the global queue's counter)
       const unsigned ballot = __ballot_sync(0xffffffffu, survive);
+      if (GLOBAL_OUT)
+      {
+        uint32_t got = 0;
+        if (lane == 0 && ballot)
+          got = atomicAdd(&A.depthTotals[depth], (uint32_t)__popc(ballot));
+        qcnt = __shfl_sync(0xffffffffu, got, 0);
+      }
       if (survive)
-        store_ray(A.q, base + qcnt + __popc(ballot & ((1u << lane) - 1u)), o, d, T, pid, rng);
-      qcnt += __popc(ballot);
+        store_ray(A.q, (GLOBAL_OUT ? 0 : base) + qcnt + __popc(ballot & ((1u << lane) - 1u)), o, d, T, pid, rng);
+      if (!GLOBAL_OUT)
+        qcnt += __popc(ballot);
     }
   }
-  if (lane == 0)
+  if (!GLOBAL_OUT && lane == 0)
   {
     A.qCount[w] = qcnt;
     if (qcnt)
-      atomicAdd(&A.depthTotals[A.depth], qcnt); // statistics only: one add per warp per launch
+      atomicAdd(&A.depthTotals[depth], qcnt); // statistics only: one add per warp per launch
+  }
+}
+
+template <class SceneT, bool TAIL_IN, bool GLOBAL_OUT>
+__global__ void __launch_bounds__(kBlock, kMinBlocksPerSM)
+  k_shade(const __grid_constant__ SceneT scene, const __grid_constant__ B2Lights lights,
+          const __grid_constant__ B2RenderArgs A)
+{
+  static_assert(GLOBAL_OUT || !TAIL_IN, "tail bounces always write the global queue");
+  const int w = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int64_t tailWarps = (int64_t)gridDim.x * kWarps;
+  if (TAIL_IN)
+  {
+    // (no early exit: the bins' tiles are dealt to warps all over the grid; the grid is small)
+  }
+  else
+  {
+    uint32_t nAny = 0;
+    if (w < A.numWarps)
+      nAny =
+        A.binCount[w] | A.binCount[A.numWarps + w] | A.binCount[2 * A.numWarps + w] | A.binCount[3 * A.numWarps + w];
+    if (!__syncthreads_or(nAny != 0))
+    { // nothing binned for any warp of this CTA: its queue regions become empty, no staging needed
+      if (!GLOBAL_OUT && w < A.numWarps && lane == 0)
+        A.qCount[w] = 0;
+      return;
+    }
+  }
+  __shared__ StageArea<SceneT> sStage;
+  const SceneT& S = stage_scene(scene, sStage);
+  const B2Lights& LT = stage_lights(lights, sStage);
+  __syncthreads();
+  if (!TAIL_IN && w >= A.numWarps)
+    return;
+  shade_body<SceneT, TAIL_IN, GLOBAL_OUT>(S, LT, A, A.depth, w, lane, tailWarps);
+}
+
+// The deep tail in ONE launch: a single thread-block cluster (kTailCluster CTAs = SMs) runs every remaining bounce
+// of the batch, trace and shade phases separated by the cluster's hardware barrier, and stops as soon as the queue
+// is empty.  Used from the first bounce that fewer than ~24 K rays enter: there a full-grid launch pair costs
+// more in launch latency and per-CTA set-up than the work itself.  Queue/bin data and the counters are read with
+// .cg loads (they were written by other SMs earlier in this launch).
+constexpr int kTailCluster = 8;
+constexpr int kTailBlock = 512;
+template <class SceneT>
+__global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kTailBlock, 1)
+  k_tail_loop(const __grid_constant__ B2Camera cam, const __grid_constant__ SceneT scene,
+              const __grid_constant__ B2Lights lights, const __grid_constant__ B2RenderArgs A)
+{
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int w = blockIdx.x * (kTailBlock / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int64_t tailWarps = (int64_t)gridDim.x * (kTailBlock / 32);
+  __shared__ StageArea<SceneT> sStage;
+  const SceneT& S = stage_scene(scene, sStage);
+  const B2Lights& LT = stage_lights(lights, sStage);
+  __syncthreads();
+  for (int depth = A.depth; depth < A.maxDepth; ++depth)
+  {
+    const int64_t nIn = (int64_t)__ldcg(&A.depthTotals[depth - 1]);
+    if (nIn == 0)
+      break; // uniform over the cluster: nobody writes this counter any more
+    trace_body<false, SceneT, true>(cam, S, A, depth, w, lane, nIn, tailWarps);
+    __threadfence();
+    cluster.sync();
+    shade_body<SceneT, true, true>(S, LT, A, depth, w, lane, tailWarps);
+    __threadfence();
+    cluster.sync();
   }
 }
 
@@ -445,45 +555,66 @@ cudaError_t query_launch_cfg(LaunchCfg* cfg)
     out = n > 0 ? n : 1;
     return err;
   };
-  if ((e = occ((const void*)k_trace<true, B2SmallScene>, cfg->traceBlocksPerSM[1][0])) != cudaSuccess ||
-      (e = occ((const void*)k_trace<false, B2SmallScene>, cfg->traceBlocksPerSM[0][0])) != cudaSuccess ||
-      (e = occ((const void*)k_trace<true, B2BvhScene>, cfg->traceBlocksPerSM[1][1])) != cudaSuccess ||
-      (e = occ((const void*)k_trace<false, B2BvhScene>, cfg->traceBlocksPerSM[0][1])) != cudaSuccess ||
-      (e = occ((const void*)k_shade<B2SmallScene>, cfg->shadeBlocksPerSM[0][0])) != cudaSuccess ||
-      (e = occ((const void*)k_shade<B2BvhScene>, cfg->shadeBlocksPerSM[0][1])) != cudaSuccess)
+  if ((e = occ((const void*)k_trace<true, B2SmallScene, false>, cfg->traceBlocksPerSM[1][0])) != cudaSuccess ||
+      (e = occ((const void*)k_trace<false, B2SmallScene, false>, cfg->traceBlocksPerSM[0][0])) != cudaSuccess ||
+      (e = occ((const void*)k_trace<true, B2BvhScene, false>, cfg->traceBlocksPerSM[1][1])) != cudaSuccess ||
+      (e = occ((const void*)k_trace<false, B2BvhScene, false>, cfg->traceBlocksPerSM[0][1])) != cudaSuccess ||
+      (e = occ((const void*)k_shade<B2SmallScene, false, false>, cfg->shadeBlocksPerSM[0][0])) != cudaSuccess ||
+      (e = occ((const void*)k_shade<B2BvhScene, false, false>, cfg->shadeBlocksPerSM[0][1])) != cudaSuccess)
     return e;
   return cudaSuccess;
 }
 
-// One bounce = k_trace then k_shade on the same stream, both on the fixed persistent grid that owns the
-// args.numWarps regions (cfg.persistentBlocks CTAs of kWarps warps).
-cudaError_t launch_bounce(const LaunchCfg& cfg, bool primary, const B2Camera& cam, const B2SmallScene* small,
-                          const B2BvhScene* bvh, const B2Lights& lights, const B2RenderArgs& args, int64_t,
-                          cudaStream_t stream, cudaEvent_t betweenStages)
+// One bounce = k_trace then k_shade on the same stream.  mode B2PT_BOUNCE_REGIONS: both on the fixed persistent
+// grid that owns the args.numWarps regions; B2PT_BOUNCE_TO_GLOBAL: the same, but k_shade appends the survivors to
+// the flat global queue; B2PT_BOUNCE_TAIL: global queue and bins, a small persistent grid (2 CTAs per SM).
+template <class SceneT>
+static cudaError_t launch_bounce_t(const LaunchCfg& cfg, bool primary, int mode, const B2Camera& cam, const SceneT& S,
+                                   const B2Lights& lights, const B2RenderArgs& args, cudaStream_t stream,
+                                   cudaEvent_t betweenStages)
 {
   const int grid = (args.numWarps + kWarps - 1) / kWarps;
-  (void)cfg;
-  if (bvh)
+  const int tailGrid = std::max(1, std::min(grid, cfg.numSMs * 2));
+  if (mode == B2PT_BOUNCE_TAIL)
   {
     if (primary)
-      k_trace<true, B2BvhScene><<<grid, kBlock, 0, stream>>>(cam, *bvh, args);
-    else
-      k_trace<false, B2BvhScene><<<grid, kBlock, 0, stream>>>(cam, *bvh, args);
-    if (betweenStages)
-      cudaEventRecord(betweenStages, stream);
-    k_shade<B2BvhScene><<<grid, kBlock, 0, stream>>>(*bvh, lights, args);
+      return cudaErrorInvalidValue;
+    k_trace<false, SceneT, true><<<tailGrid, kBlock, 0, stream>>>(cam, S, args);
   }
+  else if (primary)
+    k_trace<true, SceneT, false><<<grid, kBlock, 0, stream>>>(cam, S, args);
   else
-  {
-    if (primary)
-      k_trace<true, B2SmallScene><<<grid, kBlock, 0, stream>>>(cam, *small, args);
-    else
-      k_trace<false, B2SmallScene><<<grid, kBlock, 0, stream>>>(cam, *small, args);
-    if (betweenStages)
-      cudaEventRecord(betweenStages, stream);
-    k_shade<B2SmallScene><<<grid, kBlock, 0, stream>>>(*small, lights, args);
-  }
+    k_trace<false, SceneT, false><<<grid, kBlock, 0, stream>>>(cam, S, args);
+  if (betweenStages)
+    cudaEventRecord(betweenStages, stream);
+  if (mode == B2PT_BOUNCE_TAIL)
+    k_shade<SceneT, true, true><<<tailGrid, kBlock, 0, stream>>>(S, lights, args);
+  else if (mode == B2PT_BOUNCE_TO_GLOBAL)
+    k_shade<SceneT, false, true><<<grid, kBlock, 0, stream>>>(S, lights, args);
+  else
+    k_shade<SceneT, false, false><<<grid, kBlock, 0, stream>>>(S, lights, args);
   return cudaGetLastError();
+}
+
+cudaError_t launch_tail_loop(const B2Camera& cam, const B2SmallScene* small, const B2BvhScene* bvh,
+                             const B2Lights& lights, const B2RenderArgs& args, cudaStream_t stream)
+{
+  if (args.depth < 1)
+    return cudaErrorInvalidValue;
+  if (bvh)
+    k_tail_loop<B2BvhScene><<<kTailCluster, kTailBlock, 0, stream>>>(cam, *bvh, lights, args);
+  else
+    k_tail_loop<B2SmallScene><<<kTailCluster, kTailBlock, 0, stream>>>(cam, *small, lights, args);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bounce(const LaunchCfg& cfg, bool primary, int mode, const B2Camera& cam, const B2SmallScene* small,
+                          const B2BvhScene* bvh, const B2Lights& lights, const B2RenderArgs& args,
+                          cudaStream_t stream, cudaEvent_t betweenStages)
+{
+  if (bvh)
+    return launch_bounce_t(cfg, primary, mode, cam, *bvh, lights, args, stream, betweenStages);
+  return launch_bounce_t(cfg, primary, mode, cam, *small, lights, args, stream, betweenStages);
 }
 
 int warps_per_block() { return kWarps; }

@@ -20,11 +20,23 @@ struct LaunchCfg
 cudaError_t query_launch_cfg(LaunchCfg* cfg);
 
 // One bounce of every ray of the input queue (or, primary=true, of freshly generated camera rays): k_trace
-// (K1+K2: raygen + closest hit -> 8-byte hit records) then k_shade (K3+K5: fused shading, survivors compacted
-// into the output queue).  scene is B2SmallScene or B2BvhScene.  betweenStages (optional) is recorded after k_trace.
-cudaError_t launch_bounce(const LaunchCfg& cfg, bool primary, const B2Camera& cam, const B2SmallScene* small,
+// (K1+K2: raygen + closest hit, hits binned by shading strategy) then k_shade (K3+K5: fused shading, survivors
+// compacted into the output queue).  scene is B2SmallScene or B2BvhScene.  betweenStages (optional) is recorded
+// after k_trace.  mode: per-warp regions in and out / regions in, flat global queue out / global queue and bins
+// (tail of the bounce loop, see k_trace).
+enum
+{
+  B2PT_BOUNCE_REGIONS = 0,
+  B2PT_BOUNCE_TO_GLOBAL = 1,
+  B2PT_BOUNCE_TAIL = 2
+};
+cudaError_t launch_bounce(const LaunchCfg& cfg, bool primary, int mode, const B2Camera& cam, const B2SmallScene* small,
                           const B2BvhScene* bvh, const B2Lights& lights, const B2RenderArgs& args,
-                          int64_t maxRaysIn, cudaStream_t stream, cudaEvent_t betweenStages = nullptr);
+                          cudaStream_t stream, cudaEvent_t betweenStages = nullptr);
+// Every bounce from args.depth (>= 1, global-queue mode) to args.maxDepth-1 in one launch of a single thread-block
+// cluster; stops early when the queue runs empty.
+cudaError_t launch_tail_loop(const B2Camera& cam, const B2SmallScene* small, const B2BvhScene* bvh,
+                             const B2Lights& lights, const B2RenderArgs& args, cudaStream_t stream);
 // K4: color[p] += sum_b rad[b*N + p] in sample order; counts NaN samples into *nanCounter.
 int warps_per_block();
 cudaError_t launch_accumulate(float4* color, const float4* rad, int nPixels, int samplesInBatch,

@@ -205,7 +205,9 @@ struct B2RenderArgs
   uint32_t* binCode;
   uint32_t* qCount;     // [numWarps]
   uint32_t* binCount;   // [4*numWarps]
-  uint32_t* depthTotals; // [maxDepth] of this batch: rays entering bounce d+1 (statistics only)
+  uint32_t* depthTotals; // [maxDepth] of this batch: rays entering bounce d+1 (statistics; in tail mode also the
+                         // append counter of the global ray queue)
+  uint32_t* binTotals;   // [maxDepth*4] of this batch: tail mode, records appended to global bin k at bounce d
   float4* rad;          // per-path radiance, [b*N + pixel]
   uint32_t* seeds;      // per-pixel persistent RNG state (reference-stream mode)
   int64_t binStride;    // numWarps * regionCap

@@ -166,6 +166,42 @@ def test_axis_aligned_specialisation_is_bit_identical(gpu_ctx, b2pt):
     gpu_ctx.render(1, 1, 0)
 
 
+def test_tail_mode_is_bit_identical(gpu_ctx, b2pt, oracle, monkeypatch):
+    """Deep bounces switch to one flat global queue with atomically appended bins (k_trace/k_shade TAIL); the
+    processing order changes, the paths and the sample-order accumulation do not."""
+    W, spp, depth = 256, 16, 50
+    monkeypatch.setenv("B2PT_BATCH_PATHS", str(W * W * 4))  # 4 batches: the tail depth is chosen after the first
+    gpu_ctx.set_camera(b2pt.Camera(W, W))
+    gpu_ctx.render(spp, depth, b2pt.FLAG_NO_TAIL)
+    a, sa = gpu_ctx.read_color(), gpu_ctx.stats()
+    # default thresholds; everything after bounce 0 in tail mode; everything after bounce 0 inside the persistent
+    # cluster launch; no persistent launch at all
+    for per_warp, loop_rays in (("512", "24576"), ("100000", "24576"), ("100000", "100000000"), ("256", "0")):
+        monkeypatch.setenv("B2PT_TAIL_RAYS_PER_WARP", per_warp)
+        monkeypatch.setenv("B2PT_TAIL_LOOP_RAYS", loop_rays)
+        gpu_ctx.render(spp, depth, 0)
+        b, sb = gpu_ctx.read_color(), gpu_ctx.stats()
+        assert sa.batches == sb.batches == 4 and sa.tailDepth == depth and 1 <= sb.tailDepth < depth
+        assert sb.tailDepth <= sb.loopDepth <= depth
+        assert sa.segments == sb.segments and sa.nanSamples == sb.nanSamples
+        assert np.array_equal(a, b, equal_nan=True)
+        if loop_rays == "100000000":
+            assert sb.tailDepth == 1 and sb.loopDepth == 1
+        if loop_rays == "0":
+            assert sb.loopDepth == depth
+    monkeypatch.delenv("B2PT_TAIL_RAYS_PER_WARP")
+    monkeypatch.delenv("B2PT_TAIL_LOOP_RAYS")
+    o, ost = oracle.render(oracle.cornell_scene(), oracle.Camera(W, W), spp, depth, mode=oracle.MODE_FORWARD_FAST)
+    assert sa.segments == ost.segments
+    # reference-stream mode (one sample per batch) through the tail as well
+    gpu_ctx.set_camera(b2pt.Camera(64, 64))
+    gpu_ctx.render(6, 30, b2pt.FLAG_REFERENCE_STREAM | b2pt.FLAG_NO_TAIL)
+    c, sc = gpu_ctx.read_color(), gpu_ctx.stats()
+    gpu_ctx.render(6, 30, b2pt.FLAG_REFERENCE_STREAM)
+    d, sd = gpu_ctx.read_color(), gpu_ctx.stats()
+    assert sd.tailDepth < 30 and sc.segments == sd.segments and np.array_equal(c, d, equal_nan=True)
+
+
 def test_edge_cases(gpu_ctx, b2pt):
     gpu_ctx.set_camera(b2pt.Camera(16, 16))
     gpu_ctx.render(0, 5, 0)  # empty render

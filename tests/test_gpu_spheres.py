@@ -1,0 +1,73 @@
+"""BASELINE.json configs[3]: the synthetic many-sphere scene through the BVH traversal kernels.
+
+There is no reference counterpart for more than one sphere (SphereExtractor.cxx:108-111), so parity is against
+the oracle's brute-force closest hit (orc_closest_hit tests every primitive in index order)."""
+import ctypes as C
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_scene(oracle, s):
+    return oracle.Scene(s.pts, s.quadIds, s.sphPt, s.sphR, s.matIdxQ, s.texIdxQ, s.matIdxS, s.texIdxS, s.matType,
+                        s.texType, s.tex, s.lightQuadIds, s.lightSphPt, s.lightSphR, s.lightables, s.refIdx)
+
+
+@pytest.mark.parametrize("n,W,H,spp,depth", [(300, 64, 36, 4, 6), (5000, 96, 54, 2, 8)])
+def test_sphere_scene_matches_oracle(b2pt, oracle, n, W, H, spp, depth):
+    s = b2pt.Scene.spheres(n)
+    osc, ocam = _oracle_scene(oracle, s), oracle.Camera(W, H)
+    with b2pt.Context(0) as ctx:
+        ctx.set_scene(s)
+        ctx.build_bvh()
+        ctx.set_camera(b2pt.Camera(W, H))
+        prim, t = ctx.primary_hits()
+        ctx.render(spp, depth, 0)
+        g, st = ctx.read_color(), ctx.stats()
+    assert st.tracePath == 1 and st.bvhNodes > 1  # BVH kernels, not the small-scene path
+    oprim, ot = oracle.primary_hits(osc, ocam)
+    assert np.array_equal(prim, oprim)
+    assert np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+    o, ost = oracle.render(osc, ocam, spp, depth, mode=oracle.MODE_FORWARD_FAST)
+    assert st.segments == ost.segments  # identical trajectories
+    ok = ~(np.isnan(o[:, :3]) | np.isnan(g[:, :3]))
+    rel = np.abs(g[:, :3][ok] - o[:, :3][ok]) / np.maximum(np.abs(o[:, :3][ok]), 1e-3 * spp)
+    assert (rel < 1e-4).mean() > 0.9995
+
+
+def test_million_sphere_scene_properties(b2pt, oracle):
+    """Full-size configs[3]: 1,000,000 spheres, 1920x1080.  Size-independent checks: sampled primary hits equal the
+    oracle's brute force over all primitives bit for bit, renders are deterministic and additive over sample ranges."""
+    n, W, H = 1_000_000, 1920, 1080
+    s = b2pt.Scene.spheres(n)
+    with b2pt.Context(0) as ctx:
+        ctx.set_scene(s)
+        t0 = time.time()
+        ctx.build_bvh()
+        build_s = time.time() - t0
+        ctx.set_camera(b2pt.Camera(W, H))
+        prim, t = ctx.primary_hits()
+        ctx.render(4, 50, 0)
+        a, st = ctx.read_color(), ctx.stats()
+        ctx.clear_color()
+        ctx.render_range(0, 1, 50, 0)
+        ctx.render_range(1, 3, 50, 0)
+        b = ctx.read_color()
+    assert st.tracePath == 1 and st.tracedSpheres == n
+    assert np.array_equal(a, b, equal_nan=True)
+    assert st.segments > st.paths
+    assert build_s < 120
+    # brute-force check of a pixel sample (every primitive tested, index order)
+    osc, ocam = _oracle_scene(oracle, s), oracle.Camera(W, H)
+    rng = np.random.default_rng(3)
+    pix = rng.choice(W * H, 192, replace=False)
+    for p in pix:
+        d, _ = oracle.raygen(ocam, int(p), int(p))
+        oprim, rec, _ = oracle.closest_hit(osc, ocam.pos, d)
+        assert oprim == prim[p], (p, oprim, prim[p])
+        if oprim >= 0:
+            assert np.float32(rec[2]).view(np.uint32) == t[p].view(np.uint32)
+    assert (prim >= 2).mean() > 0.2  # spheres are actually visible
