@@ -223,6 +223,17 @@ __device__ __forceinline__ bool slab_hit(const float* bmin, const float* bmax, f
   tnear = mn;
   return mx >= mn;
 }
+// Same slab test with FMA contraction, for the BVH traversal only: there the padded boxes are conservative
+// culling volumes (hit / t come from the exact primitive tests), so the last-ulp difference cannot change a result.
+__device__ __forceinline__ bool slab_hit_fma(float4 lo, float4 hi, f3 inv, f3 od, float tmin, float closest, float& tnear)
+{
+  const float xmin = __fmaf_rn(lo.x, inv.x, -od.x), ymin = __fmaf_rn(lo.y, inv.y, -od.y), zmin = __fmaf_rn(lo.z, inv.z, -od.z);
+  const float xmax = __fmaf_rn(hi.x, inv.x, -od.x), ymax = __fmaf_rn(hi.y, inv.y, -od.y), zmax = __fmaf_rn(hi.z, inv.z, -od.z);
+  const float mn = fmaxf(fmaxf(fmaxf(fminf(ymin, ymax), fminf(xmin, xmax)), fminf(zmin, zmax)), tmin);
+  const float mx = fminf(fminf(fminf(fmaxf(ymin, ymax), fmaxf(xmin, xmax)), fmaxf(zmin, zmax)), closest);
+  tnear = mn;
+  return mx >= mn;
+}
 __device__ __forceinline__ float rcp_safe(float f) { return 1.0f / ((fabsf(f) < 1e-8f) ? 1e-8f : f); }
 
 struct Hit

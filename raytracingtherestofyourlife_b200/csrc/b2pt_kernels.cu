@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cooperative_groups.h>
+#include <type_traits>
 
 namespace b2pt
 {
@@ -142,11 +143,232 @@ __device__ __forceinline__ void finish_path(const B2RenderArgs& A, uint32_t pid,
 // and the four bins are global too; warps take 32-ray tiles grid-stride and append with one warp-aggregated
 // atomicAdd per non-empty bin per tile.  Per-warp regions would leave thousands of warps with a handful of rays
 // each (DESIGN.md "tail mode").
+// ---- BVH scenes: persistent-lane traversal.  A per-ray traversal loop leaves most lanes idle (measured 7.8 of 32
+// active on the 1M-sphere scene: trip counts differ by an order of magnitude between the rays of a warp).  Here a
+// lane that finishes its ray hands the hit over and takes the NEXT ray of the warp's own region (a warp-uniform
+// cursor, no atomics: the region is private to the warp), and the warp leaves the traversal loop to refill as soon
+// as fewer than kRefillLanes lanes are still traversing (Aila & Laine's persistent while-while with replacement).
+// The node visits, their order and the leaf tests are those of closest_bvh, so hits are bit-identical.
+#ifndef B2PT_BVH_REFILL
+#define B2PT_BVH_REFILL 24
+#endif
+constexpr int kRefillLanes = B2PT_BVH_REFILL;
+#ifndef B2PT_BVH_INNER_STEPS
+#define B2PT_BVH_INNER_STEPS 8
+#endif
+constexpr int kInnerSteps = B2PT_BVH_INNER_STEPS;
+
+template <bool PRIMARY, bool TAIL>
+__device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhScene& S, const B2RenderArgs& A,
+                                               int depth, int w, int lane, int64_t nIn, int64_t tailWarps)
+{
+  const int64_t base = TAIL ? 0 : (int64_t)w * A.regionCap;
+  const bool refStream = (A.flags & B2PT_FLAG_REFERENCE_STREAM_DEV) != 0;
+  const unsigned lt = (1u << lane) - 1u;
+  // local ray numbers 0..nLocal-1 of this warp and their queue index (tile-interleaved for PRIMARY and TAIL)
+  int64_t nLocal = nIn;
+  if (TAIL)
+  {
+    const int64_t tiles = (nIn + 31) >> 5;
+    nLocal = tiles > w ? ((tiles - 1 - w) / tailWarps + 1) * 32 : 0;
+  }
+  const int64_t stride = TAIL ? tailWarps : (int64_t)A.numWarps;
+  uint32_t cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
+  int64_t next = 0;
+  bool has = false, done = false;
+  f3 o = mk3(0.f, 0.f, 0.f), d = o, T = o, inv = o, od = o;
+  uint32_t pid = 0, rng = 0, cur = 0;
+  float closest = FLT_MAX;
+  int best = 0, sp = 0;
+  bool found = false;
+  uint32_t stack[64];
+  const float4* nodes4 = reinterpret_cast<const float4*>(S.nodes);
+  for (;;)
+  {
+    // ---- refill: lanes without a ray take the next local ray numbers
+    const unsigned need = __ballot_sync(0xffffffffu, !has);
+    if (need)
+    {
+      const int64_t r = next + __popc(need & lt);
+      if (!has && r < nLocal)
+      {
+        const int64_t idx = (PRIMARY || TAIL) ? ((((r >> 5) * stride + w) << 5) + (r & 31)) : base + r;
+        if (PRIMARY ? idx < A.nPaths : (TAIL ? idx < nIn : true))
+        {
+          load_ray<PRIMARY>(cam, A, idx, o, d, T, pid, rng);
+          inv = mk3(rcp_safe(d.x), rcp_safe(d.y), rcp_safe(d.z));
+          od = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+          closest = FLT_MAX;
+          found = false;
+          best = 0;
+          sp = 0;
+          done = S.nNodes <= 0;
+          cur = done ? 0u : bvh_pack(__ldg(nodes4).w, __ldg(nodes4 + 1).w);
+          has = true;
+        }
+      }
+      next += __popc(need);
+    }
+    if (!__any_sync(0xffffffffu, has))
+      break;
+    // ---- traverse until too few lanes are still busy (or, with nothing left to refill, until all are done)
+    for (;;)
+    {
+      // inner nodes: at most kInnerSteps rounds before the lanes waiting at a leaf get their turn
+#pragma unroll 1
+      for (int it = 0; it < kInnerSteps; ++it)
+      {
+        const bool inner = has && !done && !(cur >> 24);
+        if (!__any_sync(0xffffffffu, inner))
+          break;
+        if (!inner)
+          continue;
+        // one 64-byte fetch of the child pair, nearer child first (BVHTraverser.h:189-201)
+        const float4* lp = nodes4 + 2 * (size_t)(cur & 0xffffffu);
+        const float4 l0 = __ldg(lp), l1 = __ldg(lp + 1), r0 = __ldg(lp + 2), r1 = __ldg(lp + 3);
+        float tl, tr;
+        const bool hl = slab_hit_fma(l0, l1, inv, od, 0.001f, closest, tl);
+        const bool hr = slab_hit_fma(r0, r1, inv, od, 0.001f, closest, tr);
+        const uint32_t cl = bvh_pack(l0.w, l1.w), crr = bvh_pack(r0.w, r1.w);
+        if (hl && hr)
+        {
+          const bool rightCloser = tl > tr;
+          cur = rightCloser ? crr : cl;
+          if (sp < 64)
+            stack[sp++] = rightCloser ? cl : crr;
+        }
+        else if (hl)
+          cur = cl;
+        else if (hr)
+          cur = crr;
+        else if (sp == 0)
+          done = true;
+        else
+          cur = stack[--sp];
+      }
+      if (has && !done && (cur >> 24))
+      { // leaf: primitives in ascending original index
+        const uint32_t count = cur >> 24, left = cur & 0xffffffu;
+        for (uint32_t k = 0; k < count; ++k)
+        {
+          const int enc = __ldg(S.primSlots + left + k);
+          float t;
+          if (enc >= 0)
+          {
+            if (quad_accept(S.quads[enc], o, d, 0.001f, closest, t))
+            {
+              closest = t;
+              best = enc;
+              found = true;
+            }
+          }
+          else
+          {
+            const float4 cr = __ldg(reinterpret_cast<const float4*>(S.sph + (~enc)));
+            if (sphere_accept(mk3(cr.x, cr.y, cr.z), cr.w, o, d, 0.001f, closest, t))
+            {
+              closest = t;
+              best = enc;
+              found = true;
+            }
+          }
+        }
+        if (sp == 0)
+          done = true;
+        else
+          cur = stack[--sp];
+      }
+      const unsigned act = __ballot_sync(0xffffffffu, has && !done);
+      if (act == 0u || (next < nLocal && __popc(act) < kRefillLanes))
+        break;
+    }
+    // ---- resolve the finished rays: gated quads, then miss / emitter / bin (as in the generic body)
+    const bool resolve = has && done;
+    int bin = -1;
+    int code = B2PT_MISS;
+    if (resolve)
+    {
+      for (int g = 0; g < S.nGate; ++g)
+      {
+        float tn, t;
+        if (!slab_hit(S.gate[g].bmin, S.gate[g].bmax, inv, od, 0.001f, closest, tn))
+          continue;
+        const int q = S.gate[g].quad;
+        if (quad_accept(S.quads[q], o, d, 0.001f, closest, t))
+        {
+          closest = t;
+          best = q;
+          found = true;
+        }
+      }
+      code = found ? best : B2PT_MISS;
+      if (code == B2PT_MISS)
+        finish_path(A, pid, T * 0.f, rng, refStream, A.maxDepth - depth);
+      else
+      {
+        const int kind = hit_kind(S, code);
+        if (kind == 1)
+        {
+          Hit hit;
+          fill_hit(S, code, o, d, closest, hit);
+          const f3 em = (dot3(hit.n, d) < 0.0f) ? hit.alb : mk3(0.f, 0.f, 0.f);
+          finish_path(A, pid, mul3(T, em), rng, refStream, A.maxDepth - depth);
+        }
+        else
+        {
+          uint32_t peek = rng;
+          bin = (kind == 2) ? 0 : draw_which(peek);
+        }
+      }
+      has = false;
+      done = false;
+    }
+    const unsigned b0 = __ballot_sync(0xffffffffu, bin == 0), b1 = __ballot_sync(0xffffffffu, bin == 1);
+    const unsigned b2 = __ballot_sync(0xffffffffu, bin == 2), b3 = __ballot_sync(0xffffffffu, bin == 3);
+    if (TAIL)
+    {
+      uint32_t got = 0;
+      if (lane < 4)
+      {
+        const unsigned bk = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
+        if (bk)
+          got = atomicAdd(&A.binTotals[depth * 4 + lane], (uint32_t)__popc(bk));
+      }
+      cnt0 = __shfl_sync(0xffffffffu, got, 0), cnt1 = __shfl_sync(0xffffffffu, got, 1);
+      cnt2 = __shfl_sync(0xffffffffu, got, 2), cnt3 = __shfl_sync(0xffffffffu, got, 3);
+    }
+    if (bin >= 0)
+    {
+      const unsigned mine = bin == 0 ? b0 : (bin == 1 ? b1 : (bin == 2 ? b2 : b3));
+      const uint32_t cnt = bin == 0 ? cnt0 : (bin == 1 ? cnt1 : (bin == 2 ? cnt2 : cnt3));
+      const int64_t j = (int64_t)bin * A.binStride + base + cnt + __popc(mine & lt);
+      A.bin0[j] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
+      A.bin1[j] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
+      A.bin2[j] = make_uint4(__float_as_uint(T.z), pid, rng, __float_as_uint(closest));
+      A.binCode[j] = (uint32_t)code;
+    }
+    if (!TAIL)
+      cnt0 += __popc(b0), cnt1 += __popc(b1), cnt2 += __popc(b2), cnt3 += __popc(b3);
+  }
+  if (!TAIL && lane == 0)
+  {
+    A.binCount[0 * A.numWarps + w] = cnt0;
+    A.binCount[1 * A.numWarps + w] = cnt1;
+    A.binCount[2 * A.numWarps + w] = cnt2;
+    A.binCount[3 * A.numWarps + w] = cnt3;
+  }
+}
+
 // Work of one warp in k_trace: rays [.., nIn) of its region (TAIL: tiles w, w+tailWarps, ... of the flat queue).
 template <bool PRIMARY, class SceneT, bool TAIL>
 __device__ __forceinline__ void trace_body(const B2Camera& cam, const SceneT& S, const B2RenderArgs& A, int depth,
                                            int w, int lane, int64_t nIn, int64_t tailWarps)
 {
+  if constexpr (std::is_same<SceneT, B2BvhScene>::value)
+  {
+    trace_body_bvh<PRIMARY, TAIL>(cam, S, A, depth, w, lane, nIn, tailWarps);
+    return;
+  }
   const int64_t base = TAIL ? 0 : (int64_t)w * A.regionCap;
   const bool refStream = (A.flags & B2PT_FLAG_REFERENCE_STREAM_DEV) != 0;
   uint32_t cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
