@@ -211,7 +211,12 @@ def main():
 
     scene, cam = B.Scene.cornell(), B.Camera(W, H)
     ctx = B.Context(local)
-    stream = torch.cuda.current_stream()
+    # A dedicated (non-default) torch stream carries everything: the library's kernels (b2pt_set_stream), the NCCL
+    # all-reduce and the timing events.  torch's default stream has handle 0, which b2pt_set_stream treats as "use
+    # the context's own non-blocking stream" -- events recorded on stream 0 would then not see the kernels.
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     color = torch.zeros((N, 4), dtype=torch.float32, device="cuda")
     ctx.set_scene(scene)
@@ -324,6 +329,7 @@ def main():
                        "flags": args.flags, "segments_per_path": segments_per_step / paths_per_step,
                        "batches_per_step": st.batches, "samples_per_batch": st.samplesPerBatch},
             "segments_per_s": segments_per_step * args.steps / (ms * 1e-3),
+            "render_ms_library_events_last_step": st.renderMs,  # cross-check of ms_per_step (same stream, own events)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
                          "kernel": top_desc, "algorithmic_bytes_per_segment": ALGO_BYTES_PER_SEGMENT,

@@ -41,6 +41,15 @@ struct PeerPtrs
   const float4* p[8];
 };
 
+// L2 prefetch of the 16-byte element a lane will load in its NEXT iteration (hides part of the HBM latency at the
+// head of every tile; the kernels keep only 8 warps per scheduler)
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+#ifndef B2PT_NO_PREFETCH
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
 __device__ __forceinline__ void store_ray(const B2Queue& q, int64_t pos, f3 o, f3 d, f3 T, uint32_t pid, uint32_t rng)
 {
   q.p0[pos] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
@@ -381,6 +390,12 @@ __device__ __forceinline__ void trace_body(const B2Camera& cam, const SceneT& S,
     float t = 0.f;
     int code = B2PT_MISS;
     const int64_t idx = PRIMARY ? (((i0 >> 5) * A.numWarps + w) << 5) + lane : base + i;
+    if (!PRIMARY && !TAIL && i + 32 < nIn)
+    {
+      prefetch_l2(A.q.p0 + idx + 32);
+      prefetch_l2(A.q.p1 + idx + 32);
+      prefetch_l2(A.q.p2 + idx + 32);
+    }
     if (PRIMARY ? idx < A.nPaths : i < nIn)
     {
       load_ray<PRIMARY>(cam, A, idx, o, d, T, pid, rng);
@@ -515,6 +530,13 @@ __device__ __forceinline__ void shade_body(const SceneT& S, const B2Lights& LT, 
       bool survive = false;
       f3 o, d, T;
       uint32_t pid = 0, rng = 0;
+      if (!TAIL_IN && i + 32 < nk)
+      {
+        prefetch_l2(A.bin0 + binBase + i + 32);
+        prefetch_l2(A.bin1 + binBase + i + 32);
+        prefetch_l2(A.bin2 + binBase + i + 32);
+        prefetch_l2(A.binCode + binBase + i + 32);
+      }
       if (i < nk)
       {
         const int64_t j = binBase + i;
