@@ -140,6 +140,12 @@ struct b2pt_ctx
   DevBuf<unsigned long long> nanCounter;
   std::vector<uint32_t> hCounters;
 
+  // tail-mode depths chosen by the last render with the same scene / canvas / depth / batch shape (reused without
+  // a new synchronisation; they are heuristics, any value is correct)
+  int64_t tailKey[7] = { -1, -1, -1, -1, -1, -1, -1 };
+  int64_t sceneVersion = 0;
+  int tailDepthCached = 0, loopDepthCached = 0;
+
   b2pt_stats stats{};
   bool statsPending = false;
   int64_t pendingCounters = 0;
@@ -489,6 +495,7 @@ int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t*
   ctx->nSph = nSpheres;
   ctx->haveScene = true;
   ctx->haveBvh = false;
+  ++ctx->sceneVersion;
   return B2PT_OK;
 }
 
@@ -935,6 +942,14 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
   int64_t launches = refStream ? 1 : 0;
   int tailDepth = maxDepth; // bounces >= tailDepth run in tail mode; chosen after the first batch
   int loopDepth = maxDepth; // bounces >= loopDepth (>= tailDepth) run inside one persistent cluster launch
+  const int64_t tailKey[7] = { ctx->sceneVersion,  N, maxDepth, pathsPerBatch, (int64_t)flags, tail_rays_per_warp(),
+                               tail_loop_rays() };
+  const bool tailAllowed = nBatches > 1 && !(flags & B2PT_FLAG_NO_TAIL) && maxDepth > 2;
+  if (tailAllowed && std::equal(tailKey, tailKey + 7, ctx->tailKey))
+  {
+    tailDepth = ctx->tailDepthCached;
+    loopDepth = ctx->loopDepthCached;
+  }
   const int profDepths = std::min(maxDepth - 1, (int)b2pt_ctx::kProfDepths); // events 0..profDepths bracket that many bounces
   ctx->profDepths = nBatches > 0 ? profDepths : 0;
   ctx->profPaths = nBatches > 0 ? N * std::min<int64_t>(B, sampleCount) : 0;
@@ -992,7 +1007,7 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
     }
     CU(b2pt::launch_accumulate(ctx->color(), ctx->rad.p, (int)N, (int)nb, ctx->nanCounter.p, ctx->stream));
     ++launches;
-    if (batch == 0 && nBatches > 1 && tailDepth == maxDepth && !(flags & B2PT_FLAG_NO_TAIL) && maxDepth > 2)
+    if (batch == 0 && tailAllowed && tailDepth == maxDepth && !std::equal(tailKey, tailKey + 7, ctx->tailKey))
     { // Tail mode for the remaining batches: from the first bounce that less than tailRaysPerWarp rays per region
       // enter, rays live in one flat global queue (k_trace TAIL).  Decided from the first batch's own counters: one
       // stream synchronisation per render.
@@ -1012,6 +1027,9 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
           loopDepth = d;
           break;
         }
+      std::copy(tailKey, tailKey + 7, ctx->tailKey);
+      ctx->tailDepthCached = tailDepth;
+      ctx->loopDepthCached = loopDepth;
     }
   }
   CU(cudaEventRecord(ctx->evStop, ctx->stream));
