@@ -115,6 +115,7 @@ struct b2pt_ctx
   B2BvhScene bvh{};
   DevBuf<B2BvhNode> dNodes;
   DevBuf<int32_t> dSlots;
+  DevBuf<float4> dLeafSph;
   DevBuf<B2Quad> dQuads;
   DevBuf<B2Sphere> dSph;
   DevBuf<B2GateBox> dGates;
@@ -339,7 +340,7 @@ void b2pt_destroy(b2pt_ctx* ctx)
     return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  ctx->dNodes.release(), ctx->dSlots.release(), ctx->dQuads.release(), ctx->dSph.release(), ctx->dGates.release();
+  ctx->dNodes.release(), ctx->dSlots.release(), ctx->dLeafSph.release(), ctx->dQuads.release(), ctx->dSph.release(), ctx->dGates.release();
   ctx->colorOwn.release();
   for (auto& p : ctx->queue)
     p.release();
@@ -711,6 +712,14 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
     return fail(B2PT_ERR_UNSUPPORTED, "scene too large for the 24-bit BVH index packing");
   CU(ctx->dNodes.reserve(std::max<size_t>(nodes.size(), 1)));
   CU(ctx->dSlots.reserve(std::max<size_t>(slots.size(), 1)));
+  CU(ctx->dLeafSph.reserve(std::max<size_t>(slots.size(), 1)));
+  std::vector<float4> leafSph(slots.size(), make_float4(0.f, 0.f, 0.f, 0.f));
+  for (size_t i = 0; i < slots.size(); ++i)
+    if (slots[i] < 0)
+    {
+      const B2Sphere& sp = ctx->sph[(size_t)(~slots[i])];
+      leafSph[i] = make_float4(sp.c[0], sp.c[1], sp.c[2], sp.r);
+    }
   CU(ctx->dQuads.reserve(std::max<size_t>(ctx->quads.size(), 1)));
   CU(ctx->dSph.reserve(std::max<size_t>(ctx->sph.size(), 1)));
   CU(ctx->dGates.reserve(std::max<size_t>(ctx->gates.size(), 1)));
@@ -719,6 +728,9 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
                        cudaMemcpyHostToDevice, ctx->stream));
   if (!nodes.empty())
     CU(cudaMemcpyAsync(ctx->dNodes.p, nodes.data(), nodes.size() * sizeof(B2BvhNode), cudaMemcpyHostToDevice,
+                       ctx->stream));
+  if (!slots.empty())
+    CU(cudaMemcpyAsync(ctx->dLeafSph.p, leafSph.data(), leafSph.size() * sizeof(float4), cudaMemcpyHostToDevice,
                        ctx->stream));
   if (!slots.empty())
     CU(cudaMemcpyAsync(ctx->dSlots.p, slots.data(), slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
@@ -732,6 +744,7 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
   CU(cudaStreamSynchronize(ctx->stream)); // host vectors go out of scope
   ctx->bvh.nodes = ctx->dNodes.p;
   ctx->bvh.primSlots = ctx->dSlots.p;
+  ctx->bvh.leafSph = ctx->dLeafSph.p;
   ctx->bvh.quads = ctx->dQuads.p;
   ctx->bvh.sph = ctx->dSph.p;
   ctx->bvh.gate = ctx->dGates.p;

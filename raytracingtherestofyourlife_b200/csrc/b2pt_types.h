@@ -176,6 +176,8 @@ struct B2BvhScene
 {
   const B2BvhNode* nodes;
   const int32_t* primSlots; // slot -> encoded primitive: >=0 quad index into quads[], <0 sphere ~index
+  const float4* leafSph;    // slot -> (cx,cy,cz,r) of the sphere in that slot (zeros for quads): a leaf's spheres are
+                            // contiguous, fetched without going through primSlots -> sph[] (one latency, not two)
   const B2Quad* quads;
   const B2Sphere* sph;
   const B2GateBox* gate;
