@@ -253,7 +253,6 @@ def main():
     sampler.join()
     ms = ev0.elapsed_time(ev1)
     st = ctx.stats()
-    ctx_profile = ctx.stage_profile(16)  # first batch of the last timed step: (trace ms, shade ms, rays in)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     seg = torch.tensor([float(st.segments)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -264,6 +263,12 @@ def main():
     paths_per_step = float(N) * total_spp
     value = paths_per_step * args.steps / (ms * 1e-3)
     img_sum = color.cpu().numpy()
+    # Per-launch durations for the roofline: the timed steps keep 4 sample batches in flight on 4 streams, so their
+    # launches overlap and a launch's own duration cannot be read off them.  One extra render of a single batch with
+    # B2PT_FLAG_NO_OVERLAP (outside the timed region, same stream, CUDA events around every launch) times the
+    # dominant launches alone.
+    ctx.render_range(begin, min(count, st.samplesPerBatch), args.depth, args.flags | B.FLAG_NO_OVERLAP)
+    ctx_profile = ctx.stage_profile(16)  # (trace ms, shade ms, rays in) per bounce of that batch
 
     # ---- e2e through the C-ABI with host buffers (scene upload + render + D2H inside the timed region)
     host = torch.empty((N, 4), dtype=torch.float32).pin_memory()
@@ -310,7 +315,7 @@ def main():
             tr_ms, sh_ms, top_rays = prof[top]
             achieved = top_rays * ALGO_BYTES_PER_SEGMENT / ((tr_ms + sh_ms) * 1e-3) / 1e9
             top_desc = ("bounce %d of a %d-sample batch = k_trace<%s> launch (%.3f ms) + k_shade launch (%.3f ms), "
-                        "%d rays in (CUDA events on the launching stream)" % (
+                        "%d rays in (CUDA events on the launching stream, launches timed alone)" % (
                             top, st.samplesPerBatch, "primary" if top == 0 else "queue", tr_ms, sh_ms, top_rays))
         else:
             achieved = segments_per_step * args.steps * ALGO_BYTES_PER_SEGMENT / (ms * 1e-3) / 1e9 / world

@@ -48,6 +48,7 @@ typedef enum b2pt_status
 #define B2PT_FLAG_NO_DEDUP 0x4u             /* keep bit-identical duplicate quads in the trace list */
 #define B2PT_FLAG_FORCE_BVH 0x8u            /* use the BVH traversal kernels even for small scenes */
 #define B2PT_FLAG_NO_TAIL 0x20u             /* never switch deep bounces to the global-queue tail mode (A/B parity checks) */
+#define B2PT_FLAG_NO_OVERLAP 0x40u          /* run the sample batches one after the other on the context's stream */
 #define B2PT_FLAG_NO_AA 0x10u               /* do not use the axis-aligned quad specialisation (A/B parity checks) */
 
 typedef struct b2pt_stats

@@ -14,7 +14,7 @@ import numpy as np
 from . import _build
 
 __all__ = ["lib", "Scene", "Camera", "Context", "B2ptError", "Stats", "FLAG_REFERENCE_STREAM",
-           "FLAG_KILL_ZERO_THROUGHPUT", "FLAG_NO_DEDUP", "FLAG_FORCE_BVH", "FLAG_NO_AA", "FLAG_NO_TAIL", "LIB_PATH"]
+           "FLAG_KILL_ZERO_THROUGHPUT", "FLAG_NO_DEDUP", "FLAG_FORCE_BVH", "FLAG_NO_AA", "FLAG_NO_TAIL", "FLAG_NO_OVERLAP", "LIB_PATH"]
 
 LIB_PATH = _build.LIB
 FLAG_REFERENCE_STREAM = 0x1
@@ -23,6 +23,7 @@ FLAG_NO_DEDUP = 0x4
 FLAG_FORCE_BVH = 0x8
 FLAG_NO_AA = 0x10
 FLAG_NO_TAIL = 0x20
+FLAG_NO_OVERLAP = 0x40
 
 ERR_BAD_VALUE, ERR_CUDA, ERR_STATE, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 

@@ -130,11 +130,19 @@ struct b2pt_ctx
   DevBuf<float4> colorOwn;
   float4* colorExt = nullptr;
   int64_t colorPixels = 0;
-  DevBuf<uint4> queue[3];  // the compact ray queue (three 16-byte planes)
-  DevBuf<uint4> bins[3];   // sorted hit queues: 4 bins x pathsPerBatch records per plane
-  DevBuf<uint32_t> binCode;
-  DevBuf<uint32_t> regionCounts; // qCount[numWarps] + binCount[4*numWarps]
-  DevBuf<float4> rad;
+  // Two sets of per-batch buffers: consecutive sample batches run on up to kMaxSets streams, so the poorly occupied tail of
+  // batch b overlaps the full-grid head of batch b+1 (set = batch % nSets; sets are allocated on first use)
+  static constexpr int kMaxSets = 4;
+  struct BatchBufs
+  {
+    DevBuf<uint4> queue[3];  // the compact ray queue (three 16-byte planes)
+    DevBuf<uint4> bins[3];   // sorted hit queues: 4 bins x pathsPerBatch records per plane
+    DevBuf<uint32_t> binCode;
+    DevBuf<uint32_t> regionCounts; // qCount[numWarps] + binCount[4*numWarps]
+    DevBuf<float4> rad;
+  } bufs[kMaxSets];
+  cudaStream_t extra[kMaxSets] = {}; // own non-blocking streams of sets 1.. (set 0 runs on `stream`)
+  cudaEvent_t evFork = nullptr, evJoin[kMaxSets] = {}, evAcc[kMaxSets] = {};
   DevBuf<uint32_t> counters;
   DevBuf<uint32_t> binTotals; // tail mode: per batch, per depth, per bin record counts
   DevBuf<uint32_t> seeds;
@@ -282,6 +290,20 @@ int b2pt_version(void) { return 100; }
 
 const char* b2pt_last_error(void) { return g_lastError.c_str(); }
 
+static cudaError_t create_sets(b2pt_ctx* ctx)
+{
+  for (int k = 0; k < b2pt_ctx::kMaxSets; ++k)
+  {
+    cudaError_t e;
+    if (k > 0 && (e = cudaStreamCreateWithFlags(&ctx->extra[k], cudaStreamNonBlocking)) != cudaSuccess)
+      return e;
+    if ((e = cudaEventCreateWithFlags(&ctx->evJoin[k], cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->evAcc[k], cudaEventDisableTiming)) != cudaSuccess)
+      return e;
+  }
+  return cudaSuccess;
+}
+
 b2pt_ctx* b2pt_create(int device, int* err)
 {
   auto bail = [&](int code) -> b2pt_ctx* {
@@ -322,6 +344,8 @@ b2pt_ctx* b2pt_create(int device, int* err)
   ctx->device = device;
   if ((e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->evStart)) != cudaSuccess || (e = cudaEventCreate(&ctx->evStop)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = create_sets(ctx)) != cudaSuccess ||
       (e = b2pt::query_launch_cfg(&ctx->cfg)) != cudaSuccess)
   {
     fail(B2PT_ERR_CUDA, "context set-up failed: %s", cudaGetErrorString(e));
@@ -340,15 +364,33 @@ void b2pt_destroy(b2pt_ctx* ctx)
     return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (cudaStream_t st : ctx->extra)
+    if (st)
+      cudaStreamSynchronize(st);
   ctx->dNodes.release(), ctx->dSlots.release(), ctx->dLeafSph.release(), ctx->dQuads.release(), ctx->dSph.release(), ctx->dGates.release();
   ctx->colorOwn.release();
-  for (auto& p : ctx->queue)
-    p.release();
-  for (auto& p : ctx->bins)
-    p.release();
-  ctx->binCode.release();
-  ctx->regionCounts.release();
-  ctx->rad.release(), ctx->counters.release(), ctx->seeds.release(), ctx->nanCounter.release();
+  for (auto& b : ctx->bufs)
+  {
+    for (auto& p : b.queue)
+      p.release();
+    for (auto& p : b.bins)
+      p.release();
+    b.binCode.release();
+    b.regionCounts.release();
+    b.rad.release();
+  }
+  ctx->counters.release(), ctx->binTotals.release(), ctx->seeds.release(), ctx->nanCounter.release();
+  if (ctx->evFork)
+    cudaEventDestroy(ctx->evFork);
+  for (int k = 0; k < b2pt_ctx::kMaxSets; ++k)
+  {
+    if (ctx->evJoin[k])
+      cudaEventDestroy(ctx->evJoin[k]);
+    if (ctx->evAcc[k])
+      cudaEventDestroy(ctx->evAcc[k]);
+    if (ctx->extra[k])
+      cudaStreamDestroy(ctx->extra[k]);
+  }
   if (ctx->evStart)
     cudaEventDestroy(ctx->evStart);
   if (ctx->evStop)
@@ -860,6 +902,15 @@ static int64_t tail_rays_per_warp()
   return 512; // below 16 tiles per region the four strategy bins stop filling whole warps (measured flat 256..2048)
 }
 
+static int64_t overlap_sets()
+{ // B2PT_OVERLAP = number of sample batches in flight (1 = serial), default 4
+  const char* e = getenv("B2PT_OVERLAP");
+  int64_t v = e ? atoll(e) : 4;
+  if (v <= 0)
+    v = 1;
+  return std::min<int64_t>(v, b2pt_ctx::kMaxSets);
+}
+
 static int64_t tail_loop_rays()
 {
   const char* e = getenv("B2PT_TAIL_LOOP_RAYS");
@@ -930,14 +981,25 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
   int64_t regionCap = (pathsPerBatch + numWarps - 1) / numWarps;
   regionCap = std::max<int64_t>(32, (regionCap + 31) / 32 * 32);
   const int64_t queueCap = numWarps * regionCap;
-  for (int p = 0; p < 3; ++p)
+  // Consecutive batches alternate between the context's stream and stream2 (own buffers each): the tail of one
+  // batch (small grids, one cluster) overlaps the head of the next.  Not in reference-stream mode, where sample s+1
+  // continues the per-pixel RNG states sample s leaves behind.
+  const int nSets = (nBatches > 1 && !refStream && !(flags & B2PT_FLAG_NO_OVERLAP))
+    ? (int)std::min<int64_t>(overlap_sets(), nBatches)
+    : 1;
+  const bool overlap = nSets > 1;
+  for (int set = 0; set < nSets; ++set)
   {
-    CU(ctx->queue[p].reserve((size_t)queueCap));
-    CU(ctx->bins[p].reserve((size_t)queueCap * 4));
+    b2pt_ctx::BatchBufs& bb = ctx->bufs[set];
+    for (int p = 0; p < 3; ++p)
+    {
+      CU(bb.queue[p].reserve((size_t)queueCap));
+      CU(bb.bins[p].reserve((size_t)queueCap * 4));
+    }
+    CU(bb.binCode.reserve((size_t)queueCap * 4));
+    CU(bb.regionCounts.reserve((size_t)numWarps * 5));
+    CU(bb.rad.reserve((size_t)pathsPerBatch));
   }
-  CU(ctx->binCode.reserve((size_t)queueCap * 4));
-  CU(ctx->regionCounts.reserve((size_t)numWarps * 5));
-  CU(ctx->rad.reserve((size_t)pathsPerBatch));
   const int64_t nCounters = std::max<int64_t>(1, nBatches * maxDepth); // rays entering bounce d+1, per batch
   CU(ctx->counters.reserve((size_t)nCounters));
   CU(ctx->binTotals.reserve((size_t)nCounters * 4));
@@ -952,6 +1014,12 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
     CU(b2pt::launch_fill_seeds(ctx->seeds.p, (int)N, ctx->seedOffset, ctx->stream));
   }
 
+  if (overlap)
+  { // stream2 starts after everything queued so far on the context's stream (clears, seeds, earlier renders)
+    CU(cudaEventRecord(ctx->evFork, ctx->stream));
+    for (int k = 1; k < nSets; ++k)
+      CU(cudaStreamWaitEvent(ctx->extra[k], ctx->evFork, 0));
+  }
   int64_t launches = refStream ? 1 : 0;
   int tailDepth = maxDepth; // bounces >= tailDepth run in tail mode; chosen after the first batch
   int loopDepth = maxDepth; // bounces >= loopDepth (>= tailDepth) run inside one persistent cluster launch
@@ -970,16 +1038,19 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
   {
     const int64_t s0 = batch * B;
     const int64_t nb = std::min<int64_t>(B, sampleCount - s0);
+    const int set = (int)(batch % nSets);
+    b2pt_ctx::BatchBufs& bb = ctx->bufs[set];
+    cudaStream_t bs = set ? ctx->extra[set] : ctx->stream;
     B2RenderArgs A{};
     A.depthTotals = ctx->counters.p + batch * maxDepth;
     A.binTotals = ctx->binTotals.p + batch * maxDepth * 4;
-    A.rad = ctx->rad.p;
-    A.bin0 = ctx->bins[0].p, A.bin1 = ctx->bins[1].p, A.bin2 = ctx->bins[2].p;
-    A.binCode = ctx->binCode.p;
+    A.rad = bb.rad.p;
+    A.bin0 = bb.bins[0].p, A.bin1 = bb.bins[1].p, A.bin2 = bb.bins[2].p;
+    A.binCode = bb.binCode.p;
     A.binStride = queueCap;
-    A.q = { ctx->queue[0].p, ctx->queue[1].p, ctx->queue[2].p };
-    A.qCount = ctx->regionCounts.p;
-    A.binCount = ctx->regionCounts.p + numWarps;
+    A.q = { bb.queue[0].p, bb.queue[1].p, bb.queue[2].p };
+    A.qCount = bb.regionCounts.p;
+    A.binCount = bb.regionCounts.p + numWarps;
     A.numWarps = (int32_t)numWarps;
     A.regionCap = (int32_t)regionCap;
     A.seeds = ctx->seeds.p;
@@ -995,7 +1066,7 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
       { // per-launch CUDA events of the first bounces of batch 0 (b2pt_get_bounce_profile)
         if (!ctx->evBounce[depth])
           CU(cudaEventCreate(&ctx->evBounce[depth]));
-        CU(cudaEventRecord(ctx->evBounce[depth], ctx->stream));
+        CU(cudaEventRecord(ctx->evBounce[depth], bs));
       }
       cudaEvent_t mid = nullptr;
       if (batch == 0 && depth < profDepths)
@@ -1008,18 +1079,23 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
       if (depth >= loopDepth)
       { // every remaining bounce in one cluster launch
         CU(b2pt::launch_tail_loop(ctx->cam, ctx->useBvh ? nullptr : &ctx->small, ctx->useBvh ? &ctx->bvh : nullptr,
-                                  ctx->lights, A, ctx->stream));
+                                  ctx->lights, A, bs));
         ++launches;
         break;
       }
       const int mode = depth >= tailDepth ? b2pt::B2PT_BOUNCE_TAIL
                                           : (depth == tailDepth - 1 ? b2pt::B2PT_BOUNCE_TO_GLOBAL : b2pt::B2PT_BOUNCE_REGIONS);
       CU(b2pt::launch_bounce(ctx->cfg, depth == 0, mode, ctx->cam, ctx->useBvh ? nullptr : &ctx->small,
-                             ctx->useBvh ? &ctx->bvh : nullptr, ctx->lights, A, ctx->stream, mid));
+                             ctx->useBvh ? &ctx->bvh : nullptr, ctx->lights, A, bs, mid));
       launches += 2;
     }
-    CU(b2pt::launch_accumulate(ctx->color(), ctx->rad.p, (int)N, (int)nb, ctx->nanCounter.p, ctx->stream));
+    // the canvas is accumulated in batch order (sample-order sums): wait for the previous batch's accumulate
+    if (overlap && batch > 0)
+      CU(cudaStreamWaitEvent(bs, ctx->evAcc[(set + nSets - 1) % nSets], 0));
+    CU(b2pt::launch_accumulate(ctx->color(), bb.rad.p, (int)N, (int)nb, ctx->nanCounter.p, bs));
     ++launches;
+    if (overlap)
+      CU(cudaEventRecord(ctx->evAcc[set], bs));
     if (batch == 0 && tailAllowed && tailDepth == maxDepth && !std::equal(tailKey, tailKey + 7, ctx->tailKey))
     { // Tail mode for the remaining batches: from the first bounce that less than tailRaysPerWarp rays per region
       // enter, rays live in one flat global queue (k_trace TAIL).  Decided from the first batch's own counters: one
@@ -1043,6 +1119,14 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
       std::copy(tailKey, tailKey + 7, ctx->tailKey);
       ctx->tailDepthCached = tailDepth;
       ctx->loopDepthCached = loopDepth;
+    }
+  }
+  if (overlap)
+  { // join: the context's stream continues after everything stream2 did
+    for (int k = 1; k < nSets; ++k)
+    {
+      CU(cudaEventRecord(ctx->evJoin[k], ctx->extra[k]));
+      CU(cudaStreamWaitEvent(ctx->stream, ctx->evJoin[k], 0));
     }
   }
   CU(cudaEventRecord(ctx->evStop, ctx->stream));
