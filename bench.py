@@ -329,8 +329,8 @@ def main():
             "config": {"workload": "Cornell box %dx%d, %d spp per GPU (%d total), max depth %d "
                                    "(BASELINE.json configs[1])" % (W, H, args.spp, total_spp, args.depth),
                        "parallelism": "samples sharded across %d GPU(s), one NCCL all-reduce of %d B" % (world, N * 16),
-                       "l2": "per-step working set (ray queues + radiance, %.1f GB) exceeds the 126 MB L2" % (
-                           st.samplesPerBatch * N * 112 / 1e9),
+                       "l2": "working set of the batches in flight (ray queue + hit bins + radiance, 272 B per path, "
+                             "%.1f GB per batch) exceeds the 126 MB L2" % (st.samplesPerBatch * N * 272 / 1e9),
                        "flags": args.flags, "segments_per_path": segments_per_step / paths_per_step,
                        "batches_per_step": st.batches, "samples_per_batch": st.samplesPerBatch},
             "segments_per_s": segments_per_step * args.steps / (ms * 1e-3),

@@ -20,7 +20,7 @@ HOST_CXX = "/usr/bin/g++"  # $CXX in this image points at a g++ without OpenMP/s
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
-    "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
+    "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall,-fopenmp",
 ]
 
 
@@ -50,7 +50,8 @@ def build_lib(force=False, verbose=False):
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s" % src)
         objs.append(obj)
-    cmd = [NVCC, "-shared", "-ccbin", HOST_CXX, "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    cmd = [NVCC, "-shared", "-ccbin", HOST_CXX, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fopenmp",
+           "-o", LIB] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -11,6 +11,7 @@
 #define B2PT_BVH_H
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -70,56 +71,46 @@ inline float half_area(const float* bmin, const float* bmax)
 }
 
 // Returns false if the tree does not fit the traversal's 24-bit index packing.
-inline bool build_bvh(const std::vector<B2Quad>& quads, const std::vector<int32_t>& keptQuads,
-                      const std::vector<B2Sphere>& sph, std::vector<B2BvhNode>& nodes, std::vector<int32_t>& slots)
+// The recursion is task-parallel (OpenMP, when compiled with -fopenmp): a node's two subtrees work on disjoint
+// ranges of `items`; node pairs and leaf slot ranges are taken from atomic counters, so the numbering of nodes and
+// slots depends on scheduling but the tree (boxes, splits, leaf contents and their order) does not.
+struct BvhBuilder
 {
-  constexpr int kBins = 16;
-  constexpr int kLeafTarget = 4;
-  constexpr int kLeafMax = 8;
+  static constexpr int kBins = 16;
+  static constexpr int kLeafTarget = 4;
+  static constexpr int kLeafMax = 8;
+  static constexpr size_t kTaskMin = 8192; // subtrees below this size are built by the thread that reached them
+
   std::vector<BvhItem> items;
-  items.reserve(keptQuads.size() + sph.size());
-  for (int32_t q : keptQuads)
-  {
-    BvhItem it;
-    quad_aabb(quads[(size_t)q], it.bmin, it.bmax);
-    it.enc = q;
-    items.push_back(it);
-  }
-  for (size_t s = 0; s < sph.size(); ++s)
-  {
-    BvhItem it;
-    sphere_aabb(sph[s], it.bmin, it.bmax);
-    it.enc = ~(int32_t)s;
-    items.push_back(it);
-  }
-  for (auto& it : items)
-    for (int c = 0; c < 3; ++c)
-      it.cen[c] = 0.5f * (it.bmin[c] + it.bmax[c]);
+  std::vector<B2BvhNode>& nodes;
+  std::vector<int32_t>& slots;
+  std::atomic<int32_t> nodeCount{ 0 }, slotCount{ 0 };
 
-  nodes.clear();
-  slots.clear();
-  if (items.empty())
-    return true; // nothing for the tree (all primitives gated): traversal is skipped when nNodes == 0
-  nodes.reserve(items.size());
-  slots.reserve(items.size());
-  struct Work
+  BvhBuilder(std::vector<B2BvhNode>& n, std::vector<int32_t>& s)
+    : nodes(n)
+    , slots(s)
   {
-    size_t lo, hi;
-    int32_t node;
-  };
-  std::vector<Work> stack;
-  nodes.push_back(B2BvhNode{});
-  stack.push_back({ 0, items.size(), 0 });
-  auto order_key = [](int32_t enc) -> int64_t { return enc >= 0 ? (int64_t)enc : ((int64_t)1 << 32) + (int64_t)(~enc); };
+  }
+  static int64_t order_key(int32_t enc) { return enc >= 0 ? (int64_t)enc : ((int64_t)1 << 32) + (int64_t)(~enc); }
 
-  while (!stack.empty())
+  void make_leaf(size_t lo, size_t hi, int32_t node)
   {
-    const Work w = stack.back();
-    stack.pop_back();
-    const size_t n = w.hi - w.lo;
+    std::sort(items.begin() + (std::ptrdiff_t)lo, items.begin() + (std::ptrdiff_t)hi,
+              [](const BvhItem& a, const BvhItem& b) { return order_key(a.enc) < order_key(b.enc); });
+    const int32_t n = (int32_t)(hi - lo);
+    const int32_t first = slotCount.fetch_add(n);
+    nodes[(size_t)node].left = first;
+    nodes[(size_t)node].count = n;
+    for (size_t i = lo; i < hi; ++i)
+      slots[(size_t)first + (i - lo)] = items[i].enc;
+  }
+
+  void build(size_t wlo, size_t whi, int32_t wnode)
+  {
+    const size_t n = whi - wlo;
     float bmin[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, bmax[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
     float cmin[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, cmax[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
-    for (size_t i = w.lo; i < w.hi; ++i)
+    for (size_t i = wlo; i < whi; ++i)
       for (int c = 0; c < 3; ++c)
       {
         bmin[c] = std::fmin(bmin[c], items[i].bmin[c]);
@@ -127,26 +118,13 @@ inline bool build_bvh(const std::vector<B2Quad>& quads, const std::vector<int32_
         cmin[c] = std::fmin(cmin[c], items[i].cen[c]);
         cmax[c] = std::fmax(cmax[c], items[i].cen[c]);
       }
-    B2BvhNode& node = nodes[(size_t)w.node];
     for (int c = 0; c < 3; ++c)
     {
-      node.bmin[c] = bmin[c];
-      node.bmax[c] = bmax[c];
+      nodes[(size_t)wnode].bmin[c] = bmin[c];
+      nodes[(size_t)wnode].bmax[c] = bmax[c];
     }
-    auto make_leaf = [&]() {
-      std::sort(items.begin() + (std::ptrdiff_t)w.lo, items.begin() + (std::ptrdiff_t)w.hi,
-                [&](const BvhItem& a, const BvhItem& b) { return order_key(a.enc) < order_key(b.enc); });
-      B2BvhNode& nd = nodes[(size_t)w.node];
-      nd.left = (int32_t)slots.size();
-      nd.count = (int32_t)n;
-      for (size_t i = w.lo; i < w.hi; ++i)
-        slots.push_back(items[i].enc);
-    };
     if (n <= 1)
-    {
-      make_leaf();
-      continue;
-    }
+      return make_leaf(wlo, whi, wnode);
     // binned SAH over the three axes
     int bestAxis = -1, bestSplit = -1;
     float bestCost = FLT_MAX;
@@ -164,7 +142,7 @@ inline bool build_bvh(const std::vector<B2Quad>& quads, const std::vector<int32_
           bbmax[b][c] = -FLT_MAX;
         }
       const float scale = (float)kBins / ext;
-      for (size_t i = w.lo; i < w.hi; ++i)
+      for (size_t i = wlo; i < whi; ++i)
       {
         int b = (int)((items[i].cen[axis] - cmin[axis]) * scale);
         b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
@@ -216,25 +194,19 @@ inline bool build_bvh(const std::vector<B2Quad>& quads, const std::vector<int32_
       }
     }
     const float parentArea = half_area(bmin, bmax);
-    const float leafCost = (float)n;                                         // intersection cost 1 per primitive
+    const float leafCost = (float)n;                                                 // intersection cost 1 per primitive
     const float splitCost = bestAxis >= 0 ? 1.5f + bestCost / parentArea : FLT_MAX; // traversal step ~1.5
     if (n <= (size_t)kLeafTarget && (splitCost >= leafCost || bestAxis < 0))
-    {
-      make_leaf();
-      continue;
-    }
+      return make_leaf(wlo, whi, wnode);
     if (bestAxis < 0 && n <= (size_t)kLeafMax)
-    {
-      make_leaf();
-      continue;
-    }
+      return make_leaf(wlo, whi, wnode);
     size_t mid;
     if (bestAxis >= 0 && (splitCost < leafCost || n > (size_t)kLeafMax))
     {
       const float ext = cmax[bestAxis] - cmin[bestAxis];
       const float scale = (float)kBins / ext;
       const float lo = cmin[bestAxis];
-      auto it = std::partition(items.begin() + (std::ptrdiff_t)w.lo, items.begin() + (std::ptrdiff_t)w.hi,
+      auto it = std::partition(items.begin() + (std::ptrdiff_t)wlo, items.begin() + (std::ptrdiff_t)whi,
                                [&](const BvhItem& a) {
                                  int b = (int)((a.cen[bestAxis] - lo) * scale);
                                  b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
@@ -243,27 +215,69 @@ inline bool build_bvh(const std::vector<B2Quad>& quads, const std::vector<int32_
       mid = (size_t)(it - items.begin());
     }
     else if (n <= (size_t)kLeafMax)
+      return make_leaf(wlo, whi, wnode);
+    else
+      mid = wlo; // force the median fallback below
+    if (mid == wlo || mid == whi)
+    { // coincident centroids: median split on primitive order
+      mid = wlo + n / 2;
+      std::nth_element(items.begin() + (std::ptrdiff_t)wlo, items.begin() + (std::ptrdiff_t)mid,
+                       items.begin() + (std::ptrdiff_t)whi,
+                       [](const BvhItem& a, const BvhItem& b) { return order_key(a.enc) < order_key(b.enc); });
+    }
+    const int32_t left = nodeCount.fetch_add(2); // sibling pair, adjacent in memory
+    nodes[(size_t)wnode].left = left;
+    nodes[(size_t)wnode].count = 0;
+    if (n >= kTaskMin)
     {
-      make_leaf();
-      continue;
+#pragma omp task default(shared) firstprivate(wlo, mid, left)
+      build(wlo, mid, left);
+      build(mid, whi, left + 1);
+#pragma omp taskwait
     }
     else
-      mid = w.lo; // force the median fallback below
-    if (mid == w.lo || mid == w.hi)
-    { // coincident centroids: median split on primitive order
-      mid = w.lo + n / 2;
-      std::nth_element(items.begin() + (std::ptrdiff_t)w.lo, items.begin() + (std::ptrdiff_t)mid,
-                       items.begin() + (std::ptrdiff_t)w.hi,
-                       [&](const BvhItem& a, const BvhItem& b) { return order_key(a.enc) < order_key(b.enc); });
+    {
+      build(wlo, mid, left);
+      build(mid, whi, left + 1);
     }
-    const int32_t left = (int32_t)nodes.size();
-    nodes.push_back(B2BvhNode{});
-    nodes.push_back(B2BvhNode{});
-    nodes[(size_t)w.node].left = left;
-    nodes[(size_t)w.node].count = 0;
-    stack.push_back({ mid, w.hi, left + 1 });
-    stack.push_back({ w.lo, mid, left });
   }
+};
+
+inline bool build_bvh(const std::vector<B2Quad>& quads, const std::vector<int32_t>& keptQuads,
+                      const std::vector<B2Sphere>& sph, std::vector<B2BvhNode>& nodes, std::vector<int32_t>& slots)
+{
+  BvhBuilder B(nodes, slots);
+  std::vector<BvhItem>& items = B.items;
+  items.reserve(keptQuads.size() + sph.size());
+  for (int32_t q : keptQuads)
+  {
+    BvhItem it;
+    quad_aabb(quads[(size_t)q], it.bmin, it.bmax);
+    it.enc = q;
+    items.push_back(it);
+  }
+  for (size_t s = 0; s < sph.size(); ++s)
+  {
+    BvhItem it;
+    sphere_aabb(sph[s], it.bmin, it.bmax);
+    it.enc = ~(int32_t)s;
+    items.push_back(it);
+  }
+  for (auto& it : items)
+    for (int c = 0; c < 3; ++c)
+      it.cen[c] = 0.5f * (it.bmin[c] + it.bmax[c]);
+
+  nodes.clear();
+  slots.clear();
+  if (items.empty())
+    return true; // nothing for the tree (all primitives gated): traversal is skipped when nNodes == 0
+  nodes.assign(2 * items.size() + 2, B2BvhNode{}); // a binary tree over n >= 1 leaves has at most 2n-1 nodes
+  slots.assign(items.size(), 0);
+  B.nodeCount = 2; // node 0 = root, node 1 unused: sibling pairs start at even indices = 64-byte aligned fetches
+#pragma omp parallel
+#pragma omp single nowait
+  B.build(0, items.size(), 0);
+  nodes.resize((size_t)B.nodeCount.load());
   return nodes.size() < ((size_t)1 << 24) && slots.size() < ((size_t)1 << 24);
 }
 
