@@ -2,19 +2,25 @@
 //
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo (see _build.py).
 //
-//   k_bounce<PRIMARY,Scene>  one launch per bounce.  PRIMARY=true fuses per-pixel camera-ray generation
-//                            (wang-seeded RNG) into bounce 0, so primary rays never touch HBM.  Every
-//                            launch: load ray (3x16 B, coalesced) -> closest hit -> fused material /
-//                            direction sampling / mixture pdf / emission -> survivors compacted with
-//                            warp ballot + block prefix + ONE atomicAdd per 256-ray tile into the next
-//                            SoA queue.  Terminated paths write their radiance once (16 B).
-//   k_accumulate             per pixel: sum the batch's samples in registers (sample order) and do a
-//                            single read-modify-write of the canvas float4.
-//   k_primary_hits           parity hook: production raygen + trace, writes hit primitive id / t.
+//   k_trace<PRIMARY,Scene,TAIL>   K1+K2: load ray (3x16 B, coalesced; PRIMARY: generate it from (pixel, sample) with
+//                                 the wang-hash RNG, primary rays never touch HBM) -> closest hit -> paths that miss
+//                                 or land on an emitter finish (radiance written once, 16 B) -> every other hit is
+//                                 appended with its ray to one of four bins by shading strategy.
+//                                 Small scenes: two-phase candidate filter (b2pt_device.cuh closest_small);
+//                                 BVH scenes: persistent lanes with ray replacement (trace_body_bvh).
+//   k_shade<Scene,TAIL_IN,GLOBAL_OUT>  K3+K5: fused material / direction sampling / light pdfs / mixture pdf on 32
+//                                 records of ONE bin (warp-uniform), survivors compacted into the ray queue.
+//   k_tail_loop<Scene>            every remaining bounce of a batch in one launch of one 8-CTA cluster.
+//   k_accumulate                  per pixel: sum the batch's samples in registers (sample order) and do a
+//                                 single read-modify-write of the canvas float4.
+//   k_primary_hits                parity hook: production raygen + trace, writes hit primitive id / t.
 //   k_create_rays, k_intersect, k_normalize, k_fill_seeds, k_sum_peers: stage-level API kernels.
 //
-// Grid sizing: persistent CTAs, numSMs x occupancy blocks, each striding over 256-ray tiles; the input
-// count of bounce d>0 lives in device memory (counters[d-1]) so no host round trip sits between bounces.
+// Work distribution: queue and bins are statically partitioned into one region per persistent warp
+// (numSMs x occupancy x 8 regions); a warp consumes and refills only its own region with register counters
+// (ballot + popcount prefix), no atomics.  TAIL instantiations (deep bounces) use one flat global queue and
+// global bins with one warp-aggregated atomicAdd per 32-ray tile.  All counts live in device memory: no host
+// round trip sits between bounces.
 #include "b2pt_device.cuh"
 #include "b2pt_kernels.h"
 
