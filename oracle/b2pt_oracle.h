@@ -13,10 +13,11 @@
  * oracle/ref_harness.cxx compiles those from /root/reference against a minimal VTK-m stand-in
  * (oracle/vtkm_min/) and runs them in the reference's launch order.  This oracle's PASSES mode is bit-identical
  * to that harness (images, segment counts, primary distances; tests/test_ref_harness.py and the committed
- * "refworklets" vectors in tests/golden/).  Still unpinned, because they live in .cxx files that need all of
- * VTK-m: camera ray generation (Camera.cxx:438-524), VTK-m's own math (Cross/Normalize/Min/Max, restated in
- * vtkm_min from its documented semantics) and VTK-m's LinearBVH tree shape (affects 1 of 65536 primary rays
- * through the non-planar quad's leaf box).
+ * "refworklets" vectors in tests/golden/).  Camera ray generation is pinned the same way: the class
+ * Camera::RayGen is lifted out of the reference's Camera.cxx at build time and compiled into the harness.
+ * Still unpinned, because they live inside VTK-m: its math (Cross/Normalize/Min/Max, restated in vtkm_min from its
+ * documented semantics) and its LinearBVH tree shape (affects 1 of 65536 primary rays through the non-planar
+ * quad's leaf box).
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference).

@@ -11,8 +11,13 @@
 // assumed).  What this file adds is only what VTK-m's dispatcher would do: call each worklet's operator() once
 // per pixel with the arguments its ExecutionSignature lists, in the launch order of the reference.
 //
-// Not taken from the reference (restated, because they live in .cxx files that need all of VTK-m):
-//   * camera ray generation (Camera.cxx:483-524): primary directions come from the C oracle's orc_raygen;
+// Camera ray generation: the class Camera::RayGen (Camera.cxx:425-524) lives in a .cxx file that needs all of VTK-m;
+// the Makefile lifts exactly that class definition out of the reference file into _ref/camera_raygen_extract.inc
+// (generated, git-ignored) and it is included below, so primary rays also come from the reference's own code.  The
+// two statements that feed it (Look = normalize(LookAt - Position), Camera.cxx:911-912, and the constructor call,
+// :935-940) are restated in b2ref_render.
+//
+// Not taken from the reference (restated, because it lives inside VTK-m):
 //   * the LinearBVH build (VTK-m): a median-split tree over the reference's own leaf AABBs (AABBSurface.h), laid
 //     out as BVHTraverser.h:45-69,182-221 consumes it.  The reference's traversal code itself runs on it.
 //
@@ -45,8 +50,38 @@
 
 #include "b2pt_oracle.h"
 
+// ---- Camera::RayGen, lifted from the reference's Camera.cxx by the Makefile
+namespace vtkm
+{
+namespace rendering
+{
+namespace pathtracing
+{
+class Camera
+{
+public:
+  class RayGen;
+};
+#include "camera_raygen_extract.inc"
+}
+}
+}
+
 namespace
 {
+// Camera::SetUp (Camera.cxx:773-781) applied to the constructor's default Up = (0,1,0) (Camera.cxx:595-597): the
+// vector is stored normalised unless it equals the default
+inline vtkm::Vec<vtkm::Float32, 3> camera_up(const orc_camera* cam)
+{
+  vtkm::Vec<vtkm::Float32, 3> up(0.f, 1.f, 0.f);
+  const vtkm::Vec<vtkm::Float32, 3> want(cam->up[0], cam->up[1], cam->up[2]);
+  if (up[0] != want[0] || up[1] != want[1] || up[2] != want[2])
+  {
+    up = want;
+    vtkm::Normalize(up);
+  }
+  return up;
+}
 using vtkm::Id;
 using Vec4f = vtkm::Vec<vtkm::Float32, 4>;
 using Id5 = vtkm::Vec<vtkm::Id, 5>;
@@ -173,6 +208,21 @@ void b2ref_set_tree_variant(int v) { g_treeVariant = v; }
 uint32_t b2ref_wang32(uint32_t* state) { return xorshiftWang::getWang32(*state); }
 float b2ref_randf(uint32_t* state) { return xorshiftWang::getRandF(*state); }
 
+// Camera::RayGen (Camera.cxx:425-524) for one pixel: seed is advanced by the two jitter draws
+void b2ref_raygen(const orc_camera* cam, int64_t idx, uint32_t* seed, float* dir3)
+{
+  vec3 look = vec3(cam->lookAt[0], cam->lookAt[1], cam->lookAt[2]) - vec3(cam->pos[0], cam->pos[1], cam->pos[2]);
+  vtkm::Normalize(look);
+  const vtkm::rendering::pathtracing::Camera::RayGen raygen(cam->W, cam->H, cam->fovDeg, cam->fovDeg, look,
+                                                            camera_up(cam), 0, cam->W, 0, 0);
+  float dx = 0.f, dy = 0.f, dz = 0.f;
+  vtkm::Id pixelIndex = 0;
+  unsigned int s = *seed;
+  raygen(idx, dx, dy, dz, s, pixelIndex);
+  *seed = s;
+  dir3[0] = dx, dir3[1] = dy, dir3[2] = dz;
+}
+
 // Surface.h:30-161 (QuadLeafIntersector::hit) on explicit vertices
 int b2ref_quad_hit(const float* o, const float* d, const float* v00, const float* v10, const float* v11,
                    const float* v01, float* u, float* v, float* t)
@@ -296,17 +346,21 @@ int b2ref_render(const orc_scene* sc, const orc_camera* cam, int spp, int maxDep
   (void)HRT;
   vtkm::rendering::pathtracing::BVHTraverser::Intersector traverse;
 
+  // Camera.cxx:911-912 and :935-940: Look = normalize(LookAt - Position); RayGen(W, H, fov, fov, Look, Up, 0, W, 0, 0)
+  vec3 look = vec3(cam->lookAt[0], cam->lookAt[1], cam->lookAt[2]) - vec3(cam->pos[0], cam->pos[1], cam->pos[2]);
+  vtkm::Normalize(look);
+  const vtkm::rendering::pathtracing::Camera::RayGen raygen(cam->W, cam->H, cam->fovDeg, cam->fovDeg, look,
+                                                            camera_up(cam), 0, cam->W, 0, 0);
   for (int s = 0; s < spp; ++s)
   {
-    // rayCam.CreateRays (Camera.cxx:880-960; restated by the C oracle) + Status = 1<<3 (MapperPathTracer.cxx:283)
+    // rayCam.CreateRays (Camera.cxx:880-960) + Status = 1<<3 (MapperPathTracer.cxx:283)
     _Pragma("omp parallel for schedule(static)")
     for (Id i = 0; i < N; ++i)
     {
-      float d3[3];
-      uint32_t st = seeds[i];
-      orc_raygen(cam, i, &st, d3);
-      seeds[i] = st;
-      dir[i] = vec3(d3[0], d3[1], d3[2]);
+      float dx = 0.f, dy = 0.f, dz = 0.f;
+      vtkm::Id pixelIndex = 0;
+      raygen(i, dx, dy, dz, seeds[i], pixelIndex);
+      dir[i] = vec3(dx, dy, dz);
       origin[i] = vec3(cam->pos[0], cam->pos[1], cam->pos[2]);
       hrec[i][static_cast<Id>(HR::T)] = 0.f; // Distance <- 0 (Camera.cxx:899)
       status[i] = static_cast<vtkm::UInt8>(1UL << 3);

@@ -54,6 +54,8 @@ def lib():
         L.b2ref_quad_hit.argtypes = [C.c_void_p] * 9
         L.b2ref_sphere_hit.restype = C.c_int
         L.b2ref_sphere_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p]
+        L.b2ref_raygen.restype = None
+        L.b2ref_raygen.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_uint32), C.c_void_p]
         L.b2ref_render.restype = C.c_int
         L.b2ref_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64),
                                    C.c_void_p, C.c_void_p]
@@ -73,6 +75,15 @@ def wang_chain(seed, n):
 def randf_chain(seed, n):
     s = C.c_uint32(seed)
     return [float(lib().b2ref_randf(C.byref(s))) for _ in range(n)]
+
+
+def raygen(cam, idx, seed):
+    """Camera::RayGen of the reference for pixel idx; returns (dir[3], advanced seed)."""
+    s = C.c_uint32(seed)
+    d = np.zeros(3, np.float32)
+    cs = cam.c_struct()
+    lib().b2ref_raygen(C.byref(cs), idx, C.byref(s), _p(d))
+    return d, int(s.value)
 
 
 def quad_hit(o, d, v00, v10, v11, v01):

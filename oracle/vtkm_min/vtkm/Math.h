@@ -5,6 +5,7 @@
 namespace vtkm
 {
 inline Float64 Pi() { return 3.14159265358979323846264338327950288; }
+inline Float32 Pi_180f() { return 0.01745329251994329547f; }
 template <typename T>
 inline T Epsilon();
 template <>
