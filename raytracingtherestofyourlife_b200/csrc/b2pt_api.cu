@@ -565,10 +565,14 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
   ctx->tracedSph = (int32_t)ctx->nSph;
   // classify: planar quads normal to an axis of one of up to B2PT_MAX_FRAMES frames go through the candidate
   // filter (b2pt_types.h B2FiltQuad); every other quad is traced behind its leaf box
+  struct FiltRec
+  {
+    float c, uc, hu, vc, hv;
+  };
   struct FiltEntry
   {
     int frame, axis;
-    B2FiltQuad fq;
+    FiltRec fq;
     int32_t quad;
   };
   std::vector<FiltEntry> filt;
@@ -628,7 +632,7 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
       // plane-offset spread, doubled
       const double mu = 2e-5 * (hi[u] - lo[u]) + 2e-6 * scale, mv = 2e-5 * (hi[vv] - lo[vv]) + 2e-6 * scale;
       E.axis = n;
-      E.fq = B2FiltQuad{};
+      E.fq = FiltRec{};
       E.fq.c = (float)(0.5 * (lo[n] + hi[n]));
       E.fq.uc = (float)(0.5 * (lo[u] + hi[u]));
       E.fq.hu = (float)(0.5 * (hi[u] - lo[u]) + mu);
@@ -694,6 +698,30 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
     if (!placed)
       (Q.pad[0] ? boxedNonPlanar : boxedPlanar).push_back(k);
   }
+  std::stable_sort(filt.begin(), filt.end(), [](const FiltEntry& x, const FiltEntry& y) {
+    return x.frame != y.frame ? x.frame < y.frame : x.axis < y.axis;
+  });
+  { // the filter holds B2PT_MAX_PAIRS pairs; quads that do not fit go behind their leaf box like any other
+    int pairs = 0;
+    size_t keep = 0, k = 0;
+    while (k < filt.size())
+    {
+      size_t e = k;
+      while (e < filt.size() && filt[e].frame == filt[k].frame && filt[e].axis == filt[k].axis)
+        ++e;
+      const int room = 2 * (B2PT_MAX_PAIRS - pairs);
+      const size_t take = std::min<size_t>(e - k, (size_t)std::max(room, 0));
+      pairs += (int)((take + 1) / 2);
+      keep = k + take;
+      if (take < e - k)
+        break;
+      k = e;
+    }
+    for (size_t i = keep; i < filt.size(); ++i)
+      boxedPlanar.push_back(filt[i].quad);
+    filt.resize(keep);
+    std::sort(boxedPlanar.begin(), boxedPlanar.end());
+  }
   const size_t nBoxed = boxedPlanar.size() + boxedNonPlanar.size();
   const bool fitsSmall = keptQuads.size() <= B2PT_SMALL_MAX_QUADS && ctx->nSph <= B2PT_SMALL_MAX_SPH &&
     nBoxed <= B2PT_SMALL_MAX_GATES;
@@ -708,28 +736,44 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
     S.nFilt = (int32_t)filt.size();
     S.firstBoxed = (int32_t)filt.size();
     S.sceneAbs = sceneAbs;
-    std::stable_sort(filt.begin(), filt.end(), [](const FiltEntry& x, const FiltEntry& y) {
-      return x.frame != y.frame ? x.frame < y.frame : x.axis < y.axis;
-    });
-    // frames without quads are dropped (frame 0 may be empty)
+    // frames without quads are dropped (frame 0 may be empty); within a frame quads are grouped by axis and
+    // stored two per B2FiltPair, odd groups padded with a never-matching half
     std::vector<int> frameMap(frames.size(), -1);
     S.nFrames = 0;
-    for (size_t k = 0; k < filt.size(); ++k)
+    int nPairs = 0;
+    size_t k = 0;
+    while (k < filt.size())
     {
+      size_t e = k;
+      while (e < filt.size() && filt[e].frame == filt[k].frame && filt[e].axis == filt[k].axis)
+        ++e;
       int& fm = frameMap[(size_t)filt[k].frame];
       if (fm < 0)
       {
         fm = S.nFrames++;
         S.frames[fm] = frames[(size_t)filt[k].frame];
         for (int a = 0; a < 3; ++a)
-          S.frames[fm].axisEnd[a] = (int32_t)k;
+          S.frames[fm].axisEnd[a] = nPairs;
       }
-      S.quads[k] = ctx->quads[(size_t)filt[k].quad];
-      S.filt[k] = filt[k].fq;
-      S.filt[k].slot = (int32_t)k;
+      for (size_t i = k; i < e; i += 2)
+      {
+        B2FiltPair& P = S.pairs[nPairs];
+        for (int h = 0; h < 2; ++h)
+        {
+          const bool real = i + h < e;
+          const FiltRec r = real ? filt[i + h].fq : FiltRec{ std::nanf(""), 0.f, -1.f, 0.f, -1.f };
+          P.c[h] = r.c, P.uc[h] = r.uc, P.hu[h] = r.hu, P.vc[h] = r.vc, P.hv[h] = r.hv;
+          S.visitSlot[2 * nPairs + h] = real ? (int32_t)(i + h) : -1;
+        }
+        ++nPairs;
+      }
       for (int a = filt[k].axis; a < 3; ++a)
-        S.frames[fm].axisEnd[a] = (int32_t)k + 1;
+        S.frames[fm].axisEnd[a] = nPairs;
+      k = e;
     }
+    S.nVisit = 2 * nPairs;
+    for (size_t i = 0; i < filt.size(); ++i)
+      S.quads[i] = ctx->quads[(size_t)filt[i].quad]; // slot = position in the (frame, axis)-sorted list
     size_t slot = filt.size();
     for (int pass = 0; pass < 2; ++pass) // planar boxed quads first, non-planar last (DESIGN.md "leaf-box gate")
       for (int32_t k : (pass == 0 ? boxedPlanar : boxedNonPlanar))

@@ -315,8 +315,9 @@ __device__ __forceinline__ void aa_permute(int c, f3 a, float& u, float& v, floa
   }
 }
 
-// ---- phase 1 of the small-scene trace: candidate filter (B2FiltQuad).  All 32 lanes run the same
-// straight-line code per quad (no divergence); the output per lane is the candidate bit mask, the candidate
+// ---- phase 1 of the small-scene trace: candidate filter (B2FiltPair).  All 32 lanes run the same
+// straight-line code per pair of quads (no divergence), on packed FP32 pairs (FFMA2 / FADD2: two quads per
+// instruction); the output per lane is the candidate bit mask (bit nVisit-1-v for visit index v), the candidate
 // with the smallest LOWER BOUND of its hit distance and the second-smallest lower bound.
 #ifndef B2PT_FILT_UNROLL
 #define B2PT_FILT_UNROLL 2
@@ -324,10 +325,10 @@ __device__ __forceinline__ void aa_permute(int c, f3 a, float& u, float& v, floa
 constexpr int kFiltUnroll = B2PT_FILT_UNROLL;
 struct FiltState
 {
-  uint32_t mask; // candidate quads (bit = filt index)
+  uint32_t mask; // candidates in visit order, shifted in from the right
   float tbl;     // smallest lower bound of t over the candidates
   float t2;      // second smallest
-  int qb;        // candidate holding tbl
+  int vb;        // visit index of the candidate holding tbl
 };
 __device__ __forceinline__ float rcp_fast(float x)
 {
@@ -335,16 +336,44 @@ __device__ __forceinline__ float rcp_fast(float x)
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// One axis group: quads [qb,qe) are normal to the frame axis whose ray components are (on,dn); (ou,du),(ov,dv)
-// are the components on the two other axes.  Error model (u = 2^-24, S = coordinate scale, D = |d|_1/|dn| >= 1):
-// the filter's t' = c*rcp(dn) - on*rcp(dn) and the exact test's t both lie within  t*(4e-6*D) + 4e-6*S/|dn|  of the
-// true plane distance (>= 20x the forward error of either evaluation, incl. the rotation into the frame), and
-// the hit point within  S*(2e-5 + 2e-5*D)  of the true one plus the exact test's own edge tolerance (static
-// part folded into hu/hv on the host).  A quad the exact test could accept therefore always passes.
-__device__ __forceinline__ void filt_axis(const B2SmallScene& S, int qBegin, int qEnd, float on, float dn, float ou,
+// packed pairs of floats in one 64-bit register (sm_100 FFMA2 / FADD2)
+typedef unsigned long long f2x;
+__device__ __forceinline__ f2x pk2(float lo, float hi)
+{
+  f2x r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f2x v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2x fma2(f2x a, f2x b, f2x c)
+{
+  f2x r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f2x add2(f2x a, f2x b)
+{
+  f2x r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2x sub2(f2x a, f2x b)
+{
+  f2x r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// One axis group: pairs [pBegin,pEnd) hold quads normal to the frame axis whose ray components are (on,dn);
+// (ou,du),(ov,dv) are the components on the two other axes.  Error model (u = 2^-24, S = coordinate scale,
+// D = |d|_1/|dn| >= 1): the filter's t' = c*rcp(dn) - on*rcp(dn) and the exact test's t both lie within
+// t*(4e-6*D) + 4e-6*S/|dn|  of the true plane distance (>= 20x the forward error of either evaluation, incl. the
+// rotation into the frame), and the hit point within  S*(2e-5 + 2e-5*D)  of the true one plus the exact test's
+// own edge tolerance (static part folded into hu/hv on the host).  A quad the exact test could accept therefore
+// always passes.
+__device__ __forceinline__ void filt_axis(const B2SmallScene& S, int pBegin, int pEnd, float on, float dn, float ou,
                                           float du, float ov, float dv, float dabs, float Sr, float tmin, FiltState& F)
 {
-  if (qEnd <= qBegin)
+  if (pEnd <= pBegin)
     return;
   const float inf = __int_as_float(0x7f800000);
   const bool axisOk = fabsf(dn) > 1e-30f; // below that the exact test rejects on |det| < 1e-5
@@ -352,8 +381,8 @@ __device__ __forceinline__ void filt_axis(const B2SmallScene& S, int qBegin, int
   const float odn = on * rdn;
   const float D = dabs * fabsf(rdn);
   const float marg = Sr * __fmaf_rn(2e-5f, D, 2e-5f);
-  const float er = 4e-6f * D;                // relative error bound of t' (and of the exact t)
-  const float ea = 4e-6f * Sr * fabsf(rdn);  // absolute part
+  const float er = 4e-6f * D;               // relative error bound of t' (and of the exact t)
+  const float ea = 4e-6f * Sr * fabsf(rdn); // absolute part
   // candidate iff  t' + |t'|*er + ea > tmin  (upper bound of the true distance beyond tmin); as a threshold on t':
   const float bt = tmin - ea;
   const float tlo = !axisOk ? inf : (bt > 0.f ? bt * (1.0f - er) : (er < 0.5f ? bt * __fmaf_rn(2.0f, er, 1.0f) : -inf));
@@ -361,25 +390,36 @@ __device__ __forceinline__ void filt_axis(const B2SmallScene& S, int qBegin, int
   // that passes the threshold); extreme grazing (er >= 0.5) gets -inf, i.e. is never pruned
   const float cLo = er < 0.5f ? 1.0f - er : 0.f;
   const float off = er < 0.5f ? 3.0f * ea : inf;
+  const f2x rdn2 = pk2(rdn, rdn), modn2 = pk2(-odn, -odn), du2 = pk2(du, du), ou2 = pk2(ou, ou), dv2 = pk2(dv, dv),
+            ov2 = pk2(ov, ov), marg2 = pk2(marg, marg), cLo2 = pk2(cLo, cLo), moff2 = pk2(-off, -off);
 #pragma unroll kFiltUnroll
-  for (int q = qBegin; q < qEnd; ++q)
+  for (int p = pBegin; p < pEnd; ++p)
   {
-    const float4 a = *reinterpret_cast<const float4*>(&S.filt[q]); // c uc hu vc
-    const float hv = S.filt[q].hv;
-    const float tp = __fmaf_rn(a.x, rdn, -odn);
-    const float up = __fmaf_rn(tp, du, ou), vp = __fmaf_rn(tp, dv, ov);
-    const bool pass = (tp > tlo) & (fabsf(up - a.y) <= a.z + marg) & (fabsf(vp - a.w) <= hv + marg); // no short circuit
-    const float tl = pass ? __fmaf_rn(tp, cLo, -off) : inf;
-    F.t2 = fminf(F.t2, fmaxf(F.tbl, tl));
-    if (tl < F.tbl)
-      F.qb = q;
-    F.tbl = fminf(F.tbl, tl);
-    const uint32_t bit = 1u << q;
-    if (pass)
-      F.mask |= bit;
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&S.pairs[p]);       // (c0,c1) (uc0,uc1)
+    const ulonglong2 b = *(reinterpret_cast<const ulonglong2*>(&S.pairs[p]) + 1); // (hu0,hu1) (vc0,vc1)
+    const f2x hv2 = *(reinterpret_cast<const f2x*>(&S.pairs[p]) + 4);             // (hv0,hv1)
+    const f2x tp2 = fma2(a.x, rdn2, modn2);
+    const f2x eu2 = sub2(fma2(tp2, du2, ou2), a.y), ev2 = sub2(fma2(tp2, dv2, ov2), b.y);
+    const f2x hu2 = add2(b.x, marg2), hw2 = add2(hv2, marg2);
+    const f2x tl2 = fma2(tp2, cLo2, moff2);
+    float tp0, tp1, eu0, eu1, ev0, ev1, hu0, hu1, hw0, hw1, tl0, tl1;
+    upk2(tp2, tp0, tp1), upk2(eu2, eu0, eu1), upk2(ev2, ev0, ev1), upk2(hu2, hu0, hu1), upk2(hw2, hw0, hw1);
+    upk2(tl2, tl0, tl1);
+    const bool pass0 = (tp0 > tlo) & (fabsf(eu0) <= hu0) & (fabsf(ev0) <= hw0); // no short circuit
+    const bool pass1 = (tp1 > tlo) & (fabsf(eu1) <= hu1) & (fabsf(ev1) <= hw1);
+    const float l0 = pass0 ? tl0 : inf, l1 = pass1 ? tl1 : inf;
+    F.t2 = fminf(F.t2, fmaxf(F.tbl, l0));
+    if (l0 < F.tbl)
+      F.vb = 2 * p;
+    F.tbl = fminf(F.tbl, l0);
+    F.t2 = fminf(F.t2, fmaxf(F.tbl, l1));
+    if (l1 < F.tbl)
+      F.vb = 2 * p + 1;
+    F.tbl = fminf(F.tbl, l1);
+    F.mask = (F.mask << 2) | (pass0 ? 2u : 0u) | (pass1 ? 1u : 0u);
   }
 }
-__device__ __forceinline__ void filt_frame(const B2SmallScene& S, int f, int& qBegin, f3 o, f3 d, float Sr, float tmin,
+__device__ __forceinline__ void filt_frame(const B2SmallScene& S, int f, int& pBegin, f3 o, f3 d, float Sr, float tmin,
                                            FiltState& F)
 {
   const B2Frame& Fr = S.frames[f];
@@ -397,10 +437,10 @@ __device__ __forceinline__ void filt_frame(const B2SmallScene& S, int f, int& qB
     Sf = 4.0f * Sr; // frame coordinates are relative to org: |.| <= 2*sqrt(3)*Sr
   }
   const float dabs = fabsf(dl.x) + fabsf(dl.y) + fabsf(dl.z);
-  filt_axis(S, qBegin, Fr.axisEnd[0], ol.x, dl.x, ol.y, dl.y, ol.z, dl.z, dabs, Sf, tmin, F);
-  filt_axis(S, max(qBegin, Fr.axisEnd[0]), Fr.axisEnd[1], ol.y, dl.y, ol.z, dl.z, ol.x, dl.x, dabs, Sf, tmin, F);
-  filt_axis(S, max(qBegin, Fr.axisEnd[1]), Fr.axisEnd[2], ol.z, dl.z, ol.x, dl.x, ol.y, dl.y, dabs, Sf, tmin, F);
-  qBegin = max(qBegin, Fr.axisEnd[2]);
+  filt_axis(S, pBegin, Fr.axisEnd[0], ol.x, dl.x, ol.y, dl.y, ol.z, dl.z, dabs, Sf, tmin, F);
+  filt_axis(S, max(pBegin, Fr.axisEnd[0]), Fr.axisEnd[1], ol.y, dl.y, ol.z, dl.z, ol.x, dl.x, dabs, Sf, tmin, F);
+  filt_axis(S, max(pBegin, Fr.axisEnd[1]), Fr.axisEnd[2], ol.z, dl.z, ol.x, dl.x, ol.y, dl.y, dabs, Sf, tmin, F);
+  pBegin = max(pBegin, Fr.axisEnd[2]);
 }
 
 // Closest hit over a kernel-parameter-resident scene.  MapperPathTracer.cxx:410-435: quads first
@@ -430,23 +470,24 @@ __device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, 
     FiltState F;
     F.mask = 0u;
     F.tbl = F.t2 = __int_as_float(0x7f800000);
-    F.qb = 0;
+    F.vb = 0;
     const float Sr = fmaxf(S.sceneAbs, fmaxf(fabsf(o.x), fmaxf(fabsf(o.y), fabsf(o.z))));
-    int qBegin = 0;
+    int pBegin = 0;
     for (int f = 0; f < S.nFrames; ++f)
-      filt_frame(S, f, qBegin, o, d, Sr, tmin, F);
+      filt_frame(S, f, pBegin, o, d, Sr, tmin, F);
     // ---- phase 2: the reference's exact test on the candidates, nearest lower bound first.  Every other
     // candidate's exact t is >= its lower bound >= t2, so once the nearest one is accepted with closest < t2
-    // none of them can win or tie.
+    // none of them can win or tie.  Visit index v sits at mask bit nVisit-1-v.
     uint32_t rest = F.mask;
-    int q = F.qb;
+    const int top = S.nVisit - 1;
+    int v = F.vb;
     while (rest)
     {
-      rest &= ~(1u << q);
-      test_quad(q);
-      if (slot >= 0 && F.t2 > closest) // valid from the first iteration on: F.qb is tested first
+      rest &= ~(1u << (top - v));
+      test_quad(S.visitSlot[v]);
+      if (slot >= 0 && F.t2 > closest) // valid from the first iteration on: F.vb is tested first
         break;
-      q = __ffs((int)rest) - 1;
+      v = top - (__ffs((int)rest) - 1);
     }
   }
   // ---- remaining quads behind the slab test of their own leaf box (BVHTraverser.h:35-79, 143-157)

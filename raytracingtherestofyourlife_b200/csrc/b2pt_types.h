@@ -119,31 +119,35 @@ struct alignas(16) B2Lights
   B2LightSphere ls[B2PT_MAX_LIGHT_SPH];
 };
 
-// Candidate filter of the small-scene trace (closest_small, phase 1).  A planar quad whose plane is normal to one
+// Candidate filter of the small-scene trace (closest_small, phase 1; records: B2FiltPair).  A planar quad whose plane is normal to one
 // axis of a FRAME (frame 0 = world axes; further frames are rotated boxes such as the Cornell tall box) is
 // described by that plane's coordinate and the bounding rectangle of its vertices on the other two axes
 // (u = axis n+1, v = axis n+2, cyclic).  The filter intersects the ray with the plane in fast arithmetic (FMA,
 // MUFU.RCP) and keeps the quad as a CANDIDATE when the hit point lies inside the rectangle widened by a rigorous
 // error margin; only candidates run the reference's Lagae-Dutre test (quad_hit), so accepted hits and their t
 // stay bit-identical.  Margins: DESIGN.md "candidate filter".
-struct alignas(16) B2FiltQuad // 32 B, two 16-byte chunks
+// Filter records are stored two quads at a time so that phase 1 runs on packed FP32 pairs (FFMA2 / FADD2 on
+// sm_100): a pair holds two quads of the same frame axis; an odd group is padded with a dummy half (c = NaN, never
+// a candidate).  The visit index of a half is 2*pair + half; visitSlot[] maps it to the quad's slot.
+struct alignas(16) B2FiltPair // 48 B: two 16-byte chunks + one 8-byte chunk
 {
-  float c;      // plane coordinate on the frame axis n
-  float uc, hu; // rectangle centre / half width (static margin included) on axis u
-  float vc;
-  float hv;
-  int32_t slot; // index into quads[] (== position in filt[]: filtered quads come first)
-  int32_t pad[2];
+  float c[2];  // plane coordinate on the frame axis n
+  float uc[2]; // rectangle centre on axis u
+  float hu[2]; // half width (static margin included) on axis u
+  float vc[2];
+  float hv[2];
+  float pad[2];
 };
 struct alignas(16) B2Frame // 64 B
 {
   float R[9];         // rows = frame axes in world coordinates (world -> frame rotation)
   float org[3];       // frame origin (subtracted before the rotation)
-  int32_t axisEnd[3]; // end index in filt[] of the quads normal to frame axis 0,1,2 (cumulative over frames)
+  int32_t axisEnd[3]; // end index in pairs[] of the quads normal to frame axis 0,1,2 (cumulative over frames)
   int32_t identity;   // 1: world axes, no transform
 };
 #define B2PT_MAX_FRAMES 4
-#define B2PT_MAX_FILT 32
+#define B2PT_MAX_PAIRS 16
+#define B2PT_MAX_FILT (2 * B2PT_MAX_PAIRS) // visit indices fit one 32-bit candidate mask
 
 struct alignas(16) B2SmallScene
 {
@@ -157,7 +161,9 @@ struct alignas(16) B2SmallScene
   float sceneAbs; // max |coordinate| of the traced primitives (scale of the filter margins)
   int32_t pad1;
   B2Frame frames[B2PT_MAX_FRAMES];
-  B2FiltQuad filt[B2PT_MAX_FILT];
+  B2FiltPair pairs[B2PT_MAX_PAIRS];
+  int32_t visitSlot[B2PT_MAX_FILT]; // visit index -> slot in quads[], -1 for a padding half
+  int32_t nVisit, padv[3];          // 2 * number of pairs
   B2GateBox gate[B2PT_SMALL_MAX_GATES];
   B2Quad quads[B2PT_SMALL_MAX_QUADS];
   B2Sphere sph[B2PT_SMALL_MAX_SPH];

@@ -223,6 +223,21 @@ def test_two_stream_batch_overlap_is_bit_identical(gpu_ctx, b2pt, monkeypatch):
     assert np.array_equal(a, gpu_ctx.read_color(), equal_nan=True)
 
 
+def test_stage_profile_reports_both_launches(gpu_ctx, b2pt):
+    """b2pt_get_stage_profile: CUDA-event durations of the k_trace and k_shade launch of the first bounces and the
+    rays entering them; consistent with b2pt_get_bounce_profile and with the segment count."""
+    gpu_ctx.set_camera(b2pt.Camera(256, 256))
+    gpu_ctx.render(8, 12, b2pt.FLAG_NO_OVERLAP)
+    st = gpu_ctx.stats()
+    prof = gpu_ctx.stage_profile(16)
+    both = gpu_ctx.bounce_profile(16)
+    assert len(prof) == len(both) == 11  # depth - 1 bracketed bounces
+    assert prof[0][2] == 256 * 256 * 8 and all(prof[k][2] >= prof[k + 1][2] for k in range(len(prof) - 1))
+    assert sum(p[2] for p in prof) <= st.segments
+    for (tr, sh, rays), (ms, rays2) in zip(prof, both):
+        assert rays == rays2 and tr > 0 and sh > 0 and abs((tr + sh) - ms) < 0.02
+
+
 def test_edge_cases(gpu_ctx, b2pt):
     gpu_ctx.set_camera(b2pt.Camera(16, 16))
     gpu_ctx.render(0, 5, 0)  # empty render
