@@ -77,8 +77,14 @@ inline float half_area(const float* bmin, const float* bmax)
 struct BvhBuilder
 {
   static constexpr int kBins = 16;
-  static constexpr int kLeafTarget = 4;
-  static constexpr int kLeafMax = 8;
+#ifndef B2PT_LEAF_TARGET
+#define B2PT_LEAF_TARGET 4
+#endif
+#ifndef B2PT_LEAF_MAX
+#define B2PT_LEAF_MAX 8
+#endif
+  static constexpr int kLeafTarget = B2PT_LEAF_TARGET;
+  static constexpr int kLeafMax = B2PT_LEAF_MAX;
   static constexpr size_t kTaskMin = 8192; // subtrees below this size are built by the thread that reached them
 
   std::vector<BvhItem> items;

@@ -320,7 +320,7 @@ __device__ __forceinline__ void aa_permute(int c, f3 a, float& u, float& v, floa
 // instruction); the output per lane is the candidate bit mask (bit nVisit-1-v for visit index v), the candidate
 // with the smallest LOWER BOUND of its hit distance and the second-smallest lower bound.
 #ifndef B2PT_FILT_UNROLL
-#define B2PT_FILT_UNROLL 2
+#define B2PT_FILT_UNROLL 1
 #endif
 constexpr int kFiltUnroll = B2PT_FILT_UNROLL;
 struct FiltState
