@@ -2,13 +2,19 @@
 //   ./CornellBox_b2pt -x 128 -y 128 -samplecount 10 -raydepth 5
 // Builds the Cornell box, renders it through MapperPathTracer (GPU), normalises with the reference's
 // NormalizeFunctor semantics and writes output.pnm (ASCII P3, bottom row first) like main.cc:361-384.
-// The -direct G-buffer modes and the -hemisphere camera sweep are outside the hot path.
+// -hemisphere [-phicount P -thetacount T] sweeps the camera over the reference's hemisphere of view points
+// (generateHemisphere, main.cc:504-561): one path-traced image per view, named output-<phi>-<theta>.pnm as the
+// reference's generate() names them (main.cc:386-429).  Every view is an independent render through the same mapper;
+// scene tables and trace structures stay resident on the GPU between views.
+// The -direct G-buffer modes (MapperQuad*, RayTracerNormals/Albedo) are outside the hot path.
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iomanip>
 #include <iostream>
+#include <sstream>
 #include <memory>
 #include <string>
 
@@ -24,6 +30,8 @@ struct Options
   int x = 128, y = 128, samples = 10, depth = 5; // reference defaults, main.cc:56-62
   std::string out = "output";
   bool stats = false;
+  bool hemi = false;
+  int phiCount = 15, thetaCount = 15; // main.cc:59-60
 };
 
 Options parse(int argc, char** argv)
@@ -47,8 +55,14 @@ Options parse(int argc, char** argv)
       o.out = argv[++i];
     else if (!std::strcmp(argv[i], "-stats"))
       o.stats = true;
-    else if (!std::strcmp(argv[i], "-hemisphere") || !std::strcmp(argv[i], "-direct"))
-      std::cerr << "note: " << argv[i] << " is outside the path-tracing hot path and is ignored\n";
+    else if (!std::strcmp(argv[i], "-hemisphere"))
+      o.hemi = true;
+    else if (!std::strcmp(argv[i], "-phicount"))
+      next(o.phiCount);
+    else if (!std::strcmp(argv[i], "-thetacount"))
+      next(o.thetaCount);
+    else if (!std::strcmp(argv[i], "-direct"))
+      std::cerr << "note: -direct is outside the path-tracing hot path and is ignored\n";
   }
   return o;
 }
@@ -103,6 +117,40 @@ void savePnm(const std::string& stem, int nx, int ny, vtkm::rendering::Canvas& c
   }
 }
 
+// the reference's generateHemisphere (main.cc:504-561) for the path-traced output: view points on a sphere of
+// radius 1078/555 around the box centre, phi in [0,1) in phiCount steps, theta in [0,2pi) in thetaCount steps
+int generateHemisphere(CornellBox& cb, const Options& o)
+{
+  vtkm::rendering::CanvasRayTracer canvas(o.x, o.y);
+  vtkm::rendering::Camera cam;
+  cam.SetClippingRange(01.f, 5.f);
+  cam.SetPosition(vec3(278 / 555.0, 278 / 555.0, -800 / 555.0));
+  cam.SetFieldOfView(40.f);
+  cam.SetViewUp(vec3(0, 1, 0));
+  cam.SetLookAt(vec3(278 / 555.0, 278 / 555.0, 278 / 555.0));
+  const float phiBegin = 0.0f, phiEnd = 1.0f, thetaBegin = 0.f;
+  const float thetaEnd = static_cast<float>(2 * 3.14159265358979323846);
+  const float rTheta = thetaEnd / static_cast<float>(o.thetaCount);
+  const float rPhi = (phiEnd - phiBegin) / float(o.phiCount);
+  const float r = static_cast<float>(-1078 / 555.0);
+  int views = 0;
+  for (float phi = phiBegin; phi < (phiEnd - 0.5 * rPhi); phi += rPhi)
+    for (float theta = thetaBegin; theta < thetaEnd; theta += rTheta)
+    {
+      const auto x = r * std::cos(theta) * std::sin(phi);
+      const auto y = r * std::sin(theta) * std::sin(phi);
+      const auto z = r * std::cos(phi);
+      cam.SetPosition(vec3(x + 278 / 555.0, y + 278 / 555.0, z + 278 / 555.0));
+      std::stringstream name; // generate(): "output-" << fixed << setw(4) << setprecision(4) << phi << "-" << theta
+      name << o.out << "-" << std::fixed << std::setw(4) << std::setprecision(4) << phi << "-";
+      name << std::fixed << std::setw(4) << std::setprecision(4) << theta;
+      runPath(cb, o.samples, o.depth, canvas, cam, o.stats);
+      savePnm(name.str(), o.x, o.y, canvas);
+      ++views;
+    }
+  return views;
+}
+
 } // namespace
 
 int main(int argc, char* argv[])
@@ -113,6 +161,15 @@ int main(int argc, char* argv[])
   {
     auto cb = std::make_unique<CornellBox>();
     cb->buildDataSet();
+    if (o.hemi)
+    {
+      const int views = generateHemisphere(*cb, o);
+      std::cout << " views rendered       = " << views << std::endl;
+      b2pt_facade::ReleaseContext();
+      const double dth = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      std::cout << " Elapsed time         = " << dth << std::endl;
+      return 0;
+    }
     vtkm::rendering::CanvasRayTracer canvas(o.x, o.y);
     vtkm::rendering::Camera cam; // main.cc:616-622
     cam.SetClippingRange(0.1f, 5.f);

@@ -92,3 +92,36 @@ def test_cli_driver_writes_the_reference_pnm(host_build, tmp_path, oracle):
     o, _ = oracle.render(oracle.cornell_scene(), oracle.Camera(128, 128), 10, 5, mode=oracle.MODE_FORWARD_FAST)
     want = (255.99 * oracle.normalize(o, 10)[:, :3].astype(np.float64)).astype(np.int64)
     assert (np.abs(got - want) <= 1).mean() > 0.9995 and (got == want).mean() > 0.99
+
+
+@pytest.mark.gpu
+def test_cli_hemisphere_sweep_matches_oracle_views(host_build, tmp_path, oracle):
+    """-hemisphere (generateHemisphere, main.cc:504-561): one image per (phi, theta) view point, named like the
+    reference's generate(); two of the views are checked against the oracle rendered from the same camera."""
+    out = str(tmp_path / "view")
+    r = subprocess.run([os.path.join(host_build, "CornellBox_b2pt"), "-x", "48", "-y", "48", "-samplecount", "6",
+                        "-raydepth", "5", "-hemisphere", "-phicount", "3", "-thetacount", "4", "-o", out],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "views rendered       = 12" in r.stdout
+    files = sorted(f for f in os.listdir(tmp_path) if f.startswith("view-") and f.endswith(".pnm"))
+    assert len(files) == 12 and "view-0.0000-0.0000.pnm" in files
+    rr = np.float32(-1078 / 555.0)
+    c = 278 / 555.0
+    rphi, rtheta = np.float32(1.0 / 3), np.float32(np.float32(2 * np.pi) / np.float32(4))
+    for (iphi, itheta) in [(0, 0), (2, 1)]:
+        phi, theta = np.float32(0), np.float32(0)
+        for _ in range(iphi):
+            phi = np.float32(phi + rphi)
+        for _ in range(itheta):
+            theta = np.float32(theta + rtheta)
+        x = rr * np.cos(theta) * np.sin(phi)
+        y = rr * np.sin(theta) * np.sin(phi)
+        z = rr * np.cos(phi)
+        pos = [np.float32(x + c), np.float32(y + c), np.float32(z + c)]
+        name = "view-%.4f-%.4f.pnm" % (phi, theta)
+        tok = open(os.path.join(tmp_path, name)).read().split()
+        got = np.array(tok[4:], np.int64).reshape(-1, 3)
+        o, _ = oracle.render(oracle.cornell_scene(), oracle.Camera(48, 48, pos=pos), 6, 5, mode=oracle.MODE_FORWARD_FAST)
+        want = (255.99 * oracle.normalize(o, 6)[:, :3].astype(np.float64)).astype(np.int64)
+        assert (np.abs(got - want) <= 1).mean() > 0.999, (name, (np.abs(got - want) <= 1).mean())
