@@ -920,42 +920,22 @@ __device__ __forceinline__ BounceResult shade_lambert(const B2Lights& lights, co
   return BOUNCE_CONTINUE;
 }
 
-// One bounce of one live path in forward (throughput) form: the reference's per-depth worklet chain
-//   intersect + CollectIntersect (MapperPathTracer.cxx:410-435, SurfaceWorklets.h:98-111)
-//   Lambertian / DiffuseLight / Dielectric (EmitWorklet.h:46-73, 112-135, 244-272)
-//   Which / Cosine / Quad / Sphere generators (PdfWorklet.h:19-21, 63-79, 112-137, 193-213)
-//   QuadPDF / SpherePDF / PDFCosine (PdfWorklet.h:274-316, 374-399; ScatterWorklet.h:67-117)
-// fused, with the depth-layer compositing of MapperPathTracer.cxx:328-348 carried as throughput T.
-// Draw order while alive is the reference's.  On BOUNCE_DONE, L holds the path's radiance.
-__device__ __forceinline__ BounceResult shade(const B2Lights& lights, bool found, const Hit& hit, f3& o, f3& d, f3& T,
-                                              uint32_t& rng, uint32_t flags, f3& L)
+// Specular (dielectric) bounce: DielectricWorklet (EmitWorklet.h:244-272): one draw, specular ray, attenuation 1.
+// The direction generators and the sphere-pdf worklet still run for such a pixel and consume their draws (which 1,
+// generator 2 / 3 per light quad / 2 per light sphere, pdf index 1); their outputs are unused.  Draw order while
+// alive is the reference's.  k_trace finishes misses and emitter hits itself, so k_shade only ever
+// sees this case (bin 0) and the lambertian one (bins 1..3, shade_lambert).
+__device__ __forceinline__ BounceResult shade_specular(const B2Lights& lights, const Hit& hit, f3& o, f3& d, uint32_t& rng)
 {
-  if (!found)
-  {
-    L = T * 0.f; // a[d]=1, e[d]=0: radiance 0, NaN/Inf throughput still poisons the pixel like the reference
-    return BOUNCE_DONE;
-  }
-  if (hit.kind == 1)
-  { // DiffuseLightWorklet::emit: front face only, but the normal was already flipped -> two-sided
-    f3 em = (dot3(hit.n, d) < 0.0f) ? hit.alb : mk3(0.f, 0.f, 0.f);
-    L = mul3(T, em);
-    return BOUNCE_DONE;
-  }
-  if (hit.kind == 2)
-  { // DielectricWorklet (EmitWorklet.h:244-272): one draw, specular ray, attenuation 1.  The direction
-    // generators and the sphere-pdf worklet still run for such a pixel and consume their draws
-    // (which 1, generator 2 / 3 per light quad / 2 per light sphere, pdf index 1); their outputs are unused.
-    const float r = randf(rng);
-    const f3 sdir = dielectric_scatter(d, hit.n, lights.refIdx, r);
-    const int which = draw_which(rng);
-    const int burn = (which <= 1) ? 2 : (which == 2 ? 3 * lights.nLightQuads : 2 * lights.nLightSph);
-    for (int k = 0; k < burn + 1; ++k)
-      wang32(rng);
-    o = hit.p;
-    d = sdir;
-    return BOUNCE_CONTINUE;
-  }
-  return shade_lambert(lights, hit, o, d, T, rng, flags, L);
+  const float r = randf(rng);
+  const f3 sdir = dielectric_scatter(d, hit.n, lights.refIdx, r);
+  const int which = draw_which(rng);
+  const int burn = (which <= 1) ? 2 : (which == 2 ? 3 * lights.nLightQuads : 2 * lights.nLightSph);
+  for (int k = 0; k < burn + 1; ++k)
+    wang32(rng);
+  o = hit.p;
+  d = sdir;
+  return BOUNCE_CONTINUE;
 }
 
 } // namespace b2pt

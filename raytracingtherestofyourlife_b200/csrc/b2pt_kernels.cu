@@ -570,8 +570,7 @@ __device__ __forceinline__ void shade_body(const SceneT& S, const B2Lights& LT, 
         Hit hit;
         fill_hit(S, (int)__ldcg(A.binCode + j), o, d, __uint_as_float(c.w), hit);
         f3 L;
-        BounceResult r = (k == 0) ? shade(LT, true, hit, o, d, T, rng, A.flags, L)
-                                  : shade_lambert(LT, hit, o, d, T, rng, A.flags, L);
+        BounceResult r = (k == 0) ? shade_specular(LT, hit, o, d, rng) : shade_lambert(LT, hit, o, d, T, rng, A.flags, L);
         if (r == BOUNCE_CONTINUE && lastDepth)
         { // still alive after maxDepth bounces: e[D-1] = 0 (MapperPathTracer.cxx:328-331); no draws left to burn
           finish_path(A, pid, T * 0.f, rng, refStream, 0);
