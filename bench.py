@@ -140,7 +140,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun presets 1; must be set before libgomp is loaded
     kind, desc, step = cpu_reference_arm()
     for _ in range(args.warmup):
         step(args.size, args.ref_spp, args.depth, cores)
