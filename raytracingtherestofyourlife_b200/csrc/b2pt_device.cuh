@@ -847,23 +847,19 @@ __device__ __forceinline__ BounceResult shade_lambert(const B2Lights& lights, co
                                                       uint32_t& rng, uint32_t flags, f3& L)
 {
   const int which = draw_which(rng);
-  f3 g;
-  if (which <= 1)
+  // The generators overwrite `generated` once per light (PdfWorklet.h:112-137, 193-213), so only the LAST light's
+  // direction survives; the earlier lights only consume their draws.  The cosine and the sphere generator share one
+  // copy of the frame construction and the sincos: local = (cos(phi)*m*s, sin(phi)*m*s, z) around w, with
+  // (m, s, z, w) = (2, sqrt(r2), sqrt(1-r2), n) resp. (1, sqrt(1-z*z), 1+r2*(sqrt(1-R*R/d2)-1), c-p); m = 1 multiplies
+  // exactly, so both evaluate the reference's operation sequence (PdfWorklet.h:47-53, 157-165).
+  f3 g = mk3(0.f, 0.f, 0.f);
+  if (which == 2)
   {
-    float r1 = randf(rng);
-    float r2 = randf(rng);
-    Onb uvw = onb_from_w(hit.n);
-    g = denan3(onb_local(uvw, random_cosine_direction(r1, r2)));
-  }
-  else if (which == 2)
-  {
-    g = mk3(0.f, 0.f, 0.f);
-#pragma unroll
-    for (int l = 0; l < B2PT_MAX_LIGHT_QUADS; ++l)
+    if (lights.nLightQuads > 0)
     {
-      if (l >= lights.nLightQuads)
-        break;
-      const B2LightQuad& LQ = lights.lq[l];
+      for (int k = 0; k < 3 * (lights.nLightQuads - 1); ++k)
+        wang32(rng);
+      const B2LightQuad& LQ = lights.lq[lights.nLightQuads - 1];
       float r1 = randf(rng);
       float r2 = randf(rng);
       float r3 = randf(rng);
@@ -872,23 +868,38 @@ __device__ __forceinline__ BounceResult shade_lambert(const B2Lights& lights, co
       g = rp - hit.p;
     }
   }
-  else
+  else if (which <= 1 || lights.nLightSph > 0)
   {
-    g = mk3(0.f, 0.f, 0.f);
-#pragma unroll
-    for (int l = 0; l < B2PT_MAX_LIGHT_SPH; ++l)
+    float r1, r2, z, s, m;
+    f3 w;
+    if (which <= 1)
     {
-      if (l >= lights.nLightSph)
-        break;
-      // PdfWorklet.h:210: argument evaluation order of GCC x86-64 (right to left): r2 is drawn first
-      float r2 = randf(rng);
-      float r1 = randf(rng);
-      f3 c = ld3(lights.ls[l].c);
-      f3 dirc = c - hit.p;
-      float d2 = dot3(dirc, dirc);
-      Onb uvw = onb_from_w(dirc);
-      g = denan3(onb_local(uvw, random_to_sphere(lights.ls[l].r, d2, r1, r2)));
+      r1 = randf(rng);
+      r2 = randf(rng);
+      w = hit.n;
+      z = sqrtf(1.f - r2);
+      s = sqrtf(r2);
+      m = 2.f;
     }
+    else
+    {
+      for (int k = 0; k < 2 * (lights.nLightSph - 1); ++k)
+        wang32(rng);
+      // PdfWorklet.h:210: argument evaluation order of GCC x86-64 (right to left): r2 is drawn first
+      r2 = randf(rng);
+      r1 = randf(rng);
+      const B2LightSphere& LS = lights.ls[lights.nLightSph - 1];
+      w = ld3(LS.c) - hit.p;
+      const float d2 = dot3(w, w);
+      z = 1.f + r2 * (sqrtf(1.f - LS.r * LS.r / d2) - 1.f);
+      s = sqrtf(1.f - z * z);
+      m = 1.f;
+    }
+    const float phi = (float)(B2PT_TWO_PI_D * (double)r1);
+    float sp, cp;
+    sincosf(phi, &sp, &cp);
+    const Onb uvw = onb_from_w(w);
+    g = denan3(onb_local(uvw, mk3(cp * m * s, sp * m * s, z)));
   }
   wang32(rng); // SpherePDFWorklet's unused index draw (PdfWorklet.h:393)
   // light pdfs: sum = weight*quad + weight*sphere (no occlusion test in either)
