@@ -49,6 +49,7 @@ typedef enum b2pt_status
 #define B2PT_FLAG_FORCE_BVH 0x8u            /* use the BVH traversal kernels even for small scenes */
 #define B2PT_FLAG_NO_TAIL 0x20u             /* never switch deep bounces to the global-queue tail mode (A/B parity checks) */
 #define B2PT_FLAG_NO_OVERLAP 0x40u          /* run the sample batches one after the other on the context's stream */
+#define B2PT_FLAG_GPU_LBVH 0x80u            /* build the BVH on the device (Morton LBVH) instead of the host binned-SAH builder */
 #define B2PT_FLAG_NO_AA 0x10u               /* do not use the axis-aligned quad specialisation (A/B parity checks) */
 
 typedef struct b2pt_stats
@@ -94,6 +95,9 @@ int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t*
  * (pathtracing/SphereIntersector.cxx:46-76), FindQuadAABBs / FindSphereAABBs (pathtracing/AABBSurface.h) and
  * VTK-m's LinearBVH::Construct.  One tree over quads and spheres; small scenes skip the tree. */
 int b2pt_build_bvh(b2pt_ctx* ctx);
+/* Same with build-affecting flags (B2PT_FLAG_FORCE_BVH, _NO_DEDUP, _NO_AA, _GPU_LBVH); a later render with other
+ * build flags rebuilds. */
+int b2pt_build_bvh_ex(b2pt_ctx* ctx, uint32_t flags);
 
 /* ---- camera -------------------------------------------------------------------------------- */
 /* Replaces pathtracing::Camera::SetParameters / CreateRaysImpl set-up (pathtracing/Camera.cxx:625-637,

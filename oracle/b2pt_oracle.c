@@ -599,9 +599,15 @@ static int64_t closest_hit(const orc_scene* sc, v3 ro, v3 rd, float tmin, float 
     float r = sc->sphR[s];
     if (!(flags & ORC_FLAG_NO_AABB_GATE))
     {
+      /* The sphere's leaf box is tested against tmax, not against the running closest distance: for small
+       * spheres far from the ray origin the analytic test below cancels badly and reports "hits" slightly outside
+       * the surface, whose t may lie before the box entry; with the running distance the winner among two such
+       * near-coincident spheres would depend on the order of the primitives (for the reference: on VTK-m's tree
+       * shape).  Against tmax the result is order independent.  The reference itself cannot hold more than one
+       * sphere (SphereExtractor.cxx:108-111); for its single Cornell sphere both forms agree. */
       float bb[6];
       sphere_aabb(c, r, bb);
-      if (!aabb_gate(bb, ro, rd, tmin, closest))
+      if (!aabb_gate(bb, ro, rd, tmin, tmax))
         continue;
     }
     if (sphere_hit(ro, rd, tmp, tmin, closest, c, r))

@@ -14,7 +14,7 @@ import numpy as np
 from . import _build
 
 __all__ = ["lib", "Scene", "Camera", "Context", "B2ptError", "Stats", "FLAG_REFERENCE_STREAM",
-           "FLAG_KILL_ZERO_THROUGHPUT", "FLAG_NO_DEDUP", "FLAG_FORCE_BVH", "FLAG_NO_AA", "FLAG_NO_TAIL", "FLAG_NO_OVERLAP", "LIB_PATH"]
+           "FLAG_KILL_ZERO_THROUGHPUT", "FLAG_NO_DEDUP", "FLAG_FORCE_BVH", "FLAG_NO_AA", "FLAG_NO_TAIL", "FLAG_NO_OVERLAP", "FLAG_GPU_LBVH", "LIB_PATH"]
 
 LIB_PATH = _build.LIB
 FLAG_REFERENCE_STREAM = 0x1
@@ -24,6 +24,7 @@ FLAG_FORCE_BVH = 0x8
 FLAG_NO_AA = 0x10
 FLAG_NO_TAIL = 0x20
 FLAG_NO_OVERLAP = 0x40
+FLAG_GPU_LBVH = 0x80
 
 ERR_BAD_VALUE, ERR_CUDA, ERR_STATE, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 
@@ -67,6 +68,7 @@ SIGNATURES = {
     "b2pt_normalize": (_i32, [_vp, _i32]),
     "b2pt_synchronize": (_i32, [_vp]),
     "b2pt_get_stats": (_i32, [_vp, C.POINTER(Stats)]),
+    "b2pt_build_bvh_ex": (_i32, [_vp, C.c_uint32]),
     "b2pt_get_bounce_profile": (_i32, [_vp, _i32, _vp, _vp]),
     "b2pt_get_stage_profile": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "b2pt_primary_hits": (_i32, [_vp, _vp, _vp]),
@@ -209,8 +211,8 @@ class Context:
             len(s.texType), _p(s.tex), len(s.tex), _p(s.lightQuadIds), len(s.lightQuadIds), _p(s.lightSphPt),
             _p(s.lightSphR), len(s.lightSphPt), s.lightables, s.refIdx))
 
-    def build_bvh(self):
-        _check(lib().b2pt_build_bvh(self._h))
+    def build_bvh(self, flags=0):
+        _check(lib().b2pt_build_bvh_ex(self._h, flags))
 
     def set_camera(self, cam):
         _check(lib().b2pt_set_camera(self._h, _p(cam.pos), _p(cam.lookAt), _p(cam.up), cam.fov, cam.W, cam.H))

@@ -16,6 +16,7 @@
 #include "../../include/b2pt.h"
 #include "b2pt_bvh.h"
 #include "b2pt_kernels.h"
+#include "b2pt_lbvh.h"
 #include "b2pt_types.h"
 
 namespace
@@ -545,7 +546,7 @@ int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t*
 
 static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
 {
-  ctx->builtFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA);
+  ctx->builtFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH);
   // Drop bit-identical duplicate quads: a later copy computes the same t and loses the strict t<tmax
   // comparison (Surface.h:178-179), so removing it cannot change any result.
   std::vector<int32_t> keptQuads;
@@ -786,7 +787,18 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
         ++slot;
       }
     for (int64_t s = 0; s < ctx->nSph; ++s)
-      ctx->small.sph[s] = ctx->sph[(size_t)s];
+    {
+      const B2Sphere& sp = ctx->sph[(size_t)s];
+      ctx->small.sph[s] = sp;
+      B2GateBox& G = ctx->small.sphGate[s]; // FindSphereAABBs (AABBSurface.h:82-174): centre +- radius, unpadded
+      for (int c = 0; c < 3; ++c)
+      {
+        G.bmin[c] = std::fmin(sp.c[c] + sp.r, sp.c[c] - sp.r);
+        G.bmax[c] = std::fmax(sp.c[c] + sp.r, sp.c[c] - sp.r);
+      }
+      G.quad = -1;
+      G.pad = 0;
+    }
     return B2PT_OK;
   }
   std::vector<B2BvhNode> nodes;
@@ -795,40 +807,140 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
   for (int32_t k : keptQuads)
     if (ctx->quads[(size_t)k].gate == 0)
       treeQuads.push_back(k);
-  if (!b2pt::build_bvh(ctx->quads, treeQuads, ctx->sph, nodes, slots))
-    return fail(B2PT_ERR_UNSUPPORTED, "scene too large for the 24-bit BVH index packing");
-  CU(ctx->dNodes.reserve(std::max<size_t>(nodes.size(), 1)));
-  CU(ctx->dSlots.reserve(std::max<size_t>(slots.size(), 1)));
-  CU(ctx->dLeafSph.reserve(std::max<size_t>(slots.size(), 1)));
-  std::vector<float4> leafSph(slots.size(), make_float4(0.f, 0.f, 0.f, 0.f));
-  for (size_t i = 0; i < slots.size(); ++i)
-    if (slots[i] < 0)
-    {
-      const B2Sphere& sp = ctx->sph[(size_t)(~slots[i])];
-      leafSph[i] = make_float4(sp.c[0], sp.c[1], sp.c[2], sp.r);
-    }
   CU(ctx->dQuads.reserve(std::max<size_t>(ctx->quads.size(), 1)));
   CU(ctx->dSph.reserve(std::max<size_t>(ctx->sph.size(), 1)));
   CU(ctx->dGates.reserve(std::max<size_t>(ctx->gates.size(), 1)));
   if (!ctx->gates.empty())
     CU(cudaMemcpyAsync(ctx->dGates.p, ctx->gates.data(), ctx->gates.size() * sizeof(B2GateBox),
                        cudaMemcpyHostToDevice, ctx->stream));
-  if (!nodes.empty())
-    CU(cudaMemcpyAsync(ctx->dNodes.p, nodes.data(), nodes.size() * sizeof(B2BvhNode), cudaMemcpyHostToDevice,
-                       ctx->stream));
-  if (!slots.empty())
-    CU(cudaMemcpyAsync(ctx->dLeafSph.p, leafSph.data(), leafSph.size() * sizeof(float4), cudaMemcpyHostToDevice,
-                       ctx->stream));
-  if (!slots.empty())
-    CU(cudaMemcpyAsync(ctx->dSlots.p, slots.data(), slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
-                       ctx->stream));
   if (!ctx->quads.empty())
     CU(cudaMemcpyAsync(ctx->dQuads.p, ctx->quads.data(), ctx->quads.size() * sizeof(B2Quad), cudaMemcpyHostToDevice,
                        ctx->stream));
   if (!ctx->sph.empty())
     CU(cudaMemcpyAsync(ctx->dSph.p, ctx->sph.data(), ctx->sph.size() * sizeof(B2Sphere), cudaMemcpyHostToDevice,
                        ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream)); // host vectors go out of scope
+  size_t nNodes = 0;
+  if (flags & B2PT_FLAG_GPU_LBVH)
+  { // device builder (b2pt_lbvh.cu): Morton order, radix tree, leaves of <= 4 primitives
+    const size_t n = treeQuads.size() + ctx->sph.size();
+    if (2 * n >= ((size_t)1 << 24))
+      return fail(B2PT_ERR_UNSUPPORTED, "scene too large for the 24-bit BVH index packing");
+    float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    for (int32_t k : treeQuads)
+    {
+      float a[3], b[3];
+      b2pt::quad_aabb(ctx->quads[(size_t)k], a, b);
+      for (int c = 0; c < 3; ++c)
+        lo[c] = std::fmin(lo[c], a[c]), hi[c] = std::fmax(hi[c], b[c]);
+    }
+    for (const B2Sphere& sp : ctx->sph)
+      for (int c = 0; c < 3; ++c)
+        lo[c] = std::fmin(lo[c], sp.c[c] - sp.r), hi[c] = std::fmax(hi[c], sp.c[c] + sp.r);
+    DevBuf<int32_t> dTreeQuads;
+    CU(dTreeQuads.reserve(std::max<size_t>(treeQuads.size(), 1)));
+    if (!treeQuads.empty())
+      CU(cudaMemcpyAsync(dTreeQuads.p, treeQuads.data(), treeQuads.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                         ctx->stream));
+    nNodes = n ? 2 * n : 0;
+    CU(ctx->dNodes.reserve(std::max<size_t>(nNodes, 1)));
+    CU(ctx->dSlots.reserve(std::max<size_t>(n, 1)));
+    CU(ctx->dLeafSph.reserve(std::max<size_t>(n, 1)));
+    const cudaError_t le = b2pt::build_lbvh_device(ctx->dQuads.p, ctx->dSph.p, dTreeQuads.p, (int)treeQuads.size(),
+                                                   (int)ctx->sph.size(), lo, hi, ctx->dNodes.p, ctx->dSlots.p,
+                                                   ctx->dLeafSph.p, ctx->stream);
+    dTreeQuads.release();
+    CU(le);
+  }
+  else
+  {
+    if (!b2pt::build_bvh(ctx->quads, treeQuads, ctx->sph, nodes, slots))
+      return fail(B2PT_ERR_UNSUPPORTED, "scene too large for the 24-bit BVH index packing");
+    nNodes = nodes.size();
+    CU(ctx->dNodes.reserve(std::max<size_t>(nodes.size(), 1)));
+    CU(ctx->dSlots.reserve(std::max<size_t>(slots.size(), 1)));
+    CU(ctx->dLeafSph.reserve(std::max<size_t>(slots.size(), 1)));
+    std::vector<float4> leafSph(slots.size(), make_float4(0.f, 0.f, 0.f, 0.f));
+    for (size_t i = 0; i < slots.size(); ++i)
+      if (slots[i] < 0)
+      {
+        const B2Sphere& sp = ctx->sph[(size_t)(~slots[i])];
+        leafSph[i] = make_float4(sp.c[0], sp.c[1], sp.c[2], sp.r);
+      }
+    if (!nodes.empty())
+      CU(cudaMemcpyAsync(ctx->dNodes.p, nodes.data(), nodes.size() * sizeof(B2BvhNode), cudaMemcpyHostToDevice,
+                         ctx->stream));
+    if (!slots.empty())
+    {
+      CU(cudaMemcpyAsync(ctx->dLeafSph.p, leafSph.data(), leafSph.size() * sizeof(float4), cudaMemcpyHostToDevice,
+                         ctx->stream));
+      CU(cudaMemcpyAsync(ctx->dSlots.p, slots.data(), slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                         ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream)); // host vectors go out of scope
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (getenv("B2PT_VALIDATE_BVH") && nNodes > 0)
+  { // debug self-check: every primitive reachable exactly once, its padded box inside the boxes of all its ancestors
+    const size_t nSlots = treeQuads.size() + ctx->sph.size();
+    std::vector<B2BvhNode> hn(nNodes);
+    std::vector<int32_t> hs(nSlots);
+    CU(cudaMemcpy(hn.data(), ctx->dNodes.p, nNodes * sizeof(B2BvhNode), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hs.data(), ctx->dSlots.p, nSlots * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<int> seen(nSlots, 0);
+    struct W
+    {
+      int32_t node;
+      float lo[3], hi[3];
+    };
+    std::vector<W> st;
+    W r{};
+    r.node = 0;
+    for (int c = 0; c < 3; ++c)
+      r.lo[c] = hn[0].bmin[c], r.hi[c] = hn[0].bmax[c];
+    st.push_back(r);
+    size_t bad = 0, visited = 0;
+    while (!st.empty())
+    {
+      const W w = st.back();
+      st.pop_back();
+      const B2BvhNode& nd = hn[(size_t)w.node];
+      for (int c = 0; c < 3; ++c)
+        if (nd.bmin[c] < w.lo[c] || nd.bmax[c] > w.hi[c])
+          ++bad;
+      if (nd.count > 0)
+      {
+        for (int k = 0; k < nd.count; ++k)
+        {
+          const int32_t enc = hs[(size_t)nd.left + k];
+          ++seen[(size_t)nd.left + k];
+          ++visited;
+          float a[3], b[3];
+          if (enc >= 0)
+            b2pt::quad_aabb(ctx->quads[(size_t)enc], a, b);
+          else
+            b2pt::sphere_aabb(ctx->sph[(size_t)(~enc)], a, b);
+          for (int c = 0; c < 3; ++c)
+            if (a[c] < nd.bmin[c] || b[c] > nd.bmax[c])
+              ++bad;
+        }
+      }
+      else
+        for (int k = 0; k < 2; ++k)
+        {
+          W ch{};
+          ch.node = nd.left + k;
+          for (int c = 0; c < 3; ++c)
+            ch.lo[c] = nd.bmin[c], ch.hi[c] = nd.bmax[c];
+          st.push_back(ch);
+        }
+    }
+    size_t once = 0;
+    for (int v : seen)
+      once += v == 1;
+    if (bad || once != nSlots || visited != nSlots)
+      return fail(B2PT_ERR_STATE, "BVH validation failed: %zu box violations, %zu of %zu slots reached once", bad, once,
+                  nSlots);
+  }
   ctx->bvh.nodes = ctx->dNodes.p;
   ctx->bvh.primSlots = ctx->dSlots.p;
   ctx->bvh.leafSph = ctx->dLeafSph.p;
@@ -836,24 +948,27 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
   ctx->bvh.sph = ctx->dSph.p;
   ctx->bvh.gate = ctx->dGates.p;
   ctx->bvh.nGate = (int32_t)ctx->gates.size();
-  ctx->bvh.nNodes = (int32_t)nodes.size();
+  ctx->bvh.nNodes = (int32_t)nNodes;
   ctx->bvh.nQuads = (int32_t)ctx->quads.size();
   ctx->bvh.nSph = (int32_t)ctx->sph.size();
-  ctx->bvhNodes = (int32_t)nodes.size();
+  ctx->bvhNodes = (int32_t)nNodes;
   return B2PT_OK;
 }
 
-int b2pt_build_bvh(b2pt_ctx* ctx)
+int b2pt_build_bvh_ex(b2pt_ctx* ctx, uint32_t flags)
 {
   if (int rc = bind(ctx))
     return rc;
   if (!ctx->haveScene)
     return fail(B2PT_ERR_STATE, "b2pt_build_bvh before b2pt_set_scene");
-  if (int rc = build_trace_structures(ctx, 0))
+  if (int rc = build_trace_structures(
+        ctx, flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH)))
     return rc;
   ctx->haveBvh = true;
   return B2PT_OK;
 }
+
+int b2pt_build_bvh(b2pt_ctx* ctx) { return b2pt_build_bvh_ex(ctx, 0); }
 
 int b2pt_set_camera(b2pt_ctx* ctx, const float pos[3], const float lookAt[3], const float up[3], float fovDeg, int W,
                     int H)
@@ -1011,7 +1126,7 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
     return fail(B2PT_ERR_BAD_VALUE, "REFERENCE_STREAM renders samples from 0 (one persistent stream per pixel)");
   // MapperPathTracer::RenderCellsImpl builds its acceleration structures on every call (:275-276); here
   // they are rebuilt only when the scene or the build-affecting flags changed.
-  const uint32_t buildFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA);
+  const uint32_t buildFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH);
   if (!ctx->haveBvh || ctx->builtFlags != buildFlags)
   {
     if (int rc = build_trace_structures(ctx, buildFlags))

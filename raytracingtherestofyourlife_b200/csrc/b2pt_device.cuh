@@ -235,6 +235,19 @@ __device__ __forceinline__ bool slab_hit_fma(float4 lo, float4 hi, f3 inv, f3 od
   return mx >= mn;
 }
 __device__ __forceinline__ float rcp_safe(float f) { return 1.0f / ((fabsf(f) < 1e-8f) ? 1e-8f : f); }
+// The reference reaches a sphere only through its own leaf box (FindSphereAABBs, AABBSurface.h:82-174: centre +- radius
+// per axis, unpadded) with the traverser's slab test (BVHTraverser.h:35-79).  The analytic sphere test cancels badly
+// for small spheres far from the ray origin (it reports hits up to ~|oc|^2*2^-24/(2r) outside the surface), so this
+// gate decides grazing hits.  It is evaluated with the reference's arithmetic before every sphere test, against tmax
+// rather than the running closest distance so that the winner among near-coincident grazing hits does not depend
+// on the order in which a tree (or a list) presents the spheres (same rule in the oracle).
+__device__ __forceinline__ bool sphere_gate(f3 c, float r, f3 inv, f3 od, float tmin, float tmax)
+{
+  const float lo[3] = { fminf(c.x + r, c.x - r), fminf(c.y + r, c.y - r), fminf(c.z + r, c.z - r) };
+  const float hi[3] = { fmaxf(c.x + r, c.x - r), fmaxf(c.y + r, c.y - r), fmaxf(c.z + r, c.z - r) };
+  float tn;
+  return slab_hit(lo, hi, inv, od, tmin, tmax, tn);
+}
 
 struct Hit
 {
@@ -490,8 +503,9 @@ __device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, 
       v = top - (__ffs((int)rest) - 1);
     }
   }
-  // ---- remaining quads behind the slab test of their own leaf box (BVHTraverser.h:35-79, 143-157)
-  if (S.firstBoxed < S.nQuads)
+  // ---- remaining quads behind the slab test of their own leaf box (BVHTraverser.h:35-79, 143-157), then the
+  // spheres behind theirs (sphere_gate)
+  if (S.firstBoxed < S.nQuads || S.nSph > 0)
   {
     const f3 inv = mk3(rcp_safe(d.x), rcp_safe(d.y), rcp_safe(d.z));
     const f3 od = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
@@ -510,14 +524,15 @@ __device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, 
         bestPrim = Q.prim;
       }
     }
-  }
-  for (int s = 0; s < S.nSph; ++s)
-  {
-    float t;
-    if (sphere_accept(ld3(S.sph[s].c), S.sph[s].r, o, d, tmin, closest, t))
+    for (int s = 0; s < S.nSph; ++s)
     {
-      closest = t;
-      slot = S.nQuads + s;
+      float tn, t;
+      if (slab_hit(S.sphGate[s].bmin, S.sphGate[s].bmax, inv, od, tmin, tmax, tn) &&
+          sphere_accept(ld3(S.sph[s].c), S.sph[s].r, o, d, tmin, closest, t))
+      {
+        closest = t;
+        slot = S.nQuads + s;
+      }
     }
   }
   tHit = closest;
@@ -593,7 +608,8 @@ __device__ __forceinline__ int closest_bvh(const B2BvhScene& S, f3 o, f3 d, floa
         else
         {
           const float4 cr = __ldg(reinterpret_cast<const float4*>(S.sph + (~enc)));
-          if (sphere_accept(mk3(cr.x, cr.y, cr.z), cr.w, o, d, tmin, closest, t))
+          if (sphere_gate(mk3(cr.x, cr.y, cr.z), cr.w, inv, od, tmin, tmax) &&
+              sphere_accept(mk3(cr.x, cr.y, cr.z), cr.w, o, d, tmin, closest, t))
           {
             closest = t;
             best = enc;

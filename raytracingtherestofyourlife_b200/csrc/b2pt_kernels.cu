@@ -295,7 +295,8 @@ __device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhS
                   found = true;
                 }
               }
-              else if (sphere_accept(mk3(geo[j].x, geo[j].y, geo[j].z), geo[j].w, o, d, 0.001f, closest, t))
+              else if (sphere_gate(mk3(geo[j].x, geo[j].y, geo[j].z), geo[j].w, inv, od, 0.001f, FLT_MAX) &&
+                       sphere_accept(mk3(geo[j].x, geo[j].y, geo[j].z), geo[j].w, o, d, 0.001f, closest, t))
               {
                 closest = t;
                 best = enc[j];

@@ -167,6 +167,7 @@ struct alignas(16) B2SmallScene
   B2GateBox gate[B2PT_SMALL_MAX_GATES];
   B2Quad quads[B2PT_SMALL_MAX_QUADS];
   B2Sphere sph[B2PT_SMALL_MAX_SPH];
+  B2GateBox sphGate[B2PT_SMALL_MAX_SPH]; // the spheres' own leaf boxes (centre +- radius, unpadded; sphere_gate)
 };
 
 // BVH scene: global-memory primitive arrays + 32-byte nodes (see b2pt_bvh.h)

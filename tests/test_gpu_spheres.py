@@ -71,3 +71,73 @@ def test_million_sphere_scene_properties(b2pt, oracle):
         if oprim >= 0:
             assert np.float32(rec[2]).view(np.uint32) == t[p].view(np.uint32)
     assert (prim >= 2).mean() > 0.2  # spheres are actually visible
+
+
+@pytest.mark.parametrize("n,W,H,spp,depth", [(1, 32, 18, 2, 4), (3, 32, 18, 2, 4), (700, 64, 36, 4, 6), (20000, 96, 54, 2, 8)])
+def test_gpu_lbvh_builder_matches_oracle(b2pt, oracle, n, W, H, spp, depth):
+    """B2PT_FLAG_GPU_LBVH: Morton order + Karras radix tree + atomic bottom-up fit on the device.  A different tree,
+    the same closest hits: primary ids / t bit-identical to brute force, trajectories identical."""
+    s = b2pt.Scene.spheres(n)
+    osc, ocam = _oracle_scene(oracle, s), oracle.Camera(W, H)
+    with b2pt.Context(0) as ctx:
+        ctx.set_scene(s)
+        ctx.build_bvh(b2pt.FLAG_GPU_LBVH | b2pt.FLAG_FORCE_BVH)
+        ctx.set_camera(b2pt.Camera(W, H))
+        prim, t = ctx.primary_hits()
+        ctx.render(spp, depth, b2pt.FLAG_GPU_LBVH | b2pt.FLAG_FORCE_BVH)
+        g, st = ctx.read_color(), ctx.stats()
+    assert st.tracePath == 1 and st.bvhNodes == 2 * (n + 2)
+    oprim, ot = oracle.primary_hits(osc, ocam)
+    assert np.array_equal(prim, oprim)
+    assert np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+    o, ost = oracle.render(osc, ocam, spp, depth, mode=oracle.MODE_FORWARD_FAST)
+    # Among tens of thousands of tiny spheres a 1-ulp difference between CUDA's sincosf and glibc's sinf/cosf in a
+    # sampled direction occasionally grazes a different sphere: the paths agree except for a handful (the same
+    # handful for the host-SAH tree, see below), so the segment count is compared with a tolerance at this size.
+    assert abs(st.segments - ost.segments) <= (0 if n <= 700 else 2e-3 * ost.segments)
+    ok = ~(np.isnan(o[:, :3]) | np.isnan(g[:, :3]))
+    rel = np.abs(g[:, :3][ok] - o[:, :3][ok]) / np.maximum(np.abs(o[:, :3][ok]), 1e-3 * spp)
+    assert (rel < 1e-4).mean() > (0.9995 if n <= 700 else 0.99)
+    # the host-SAH tree traces exactly the same paths
+    with b2pt.Context(0) as ctx:
+        ctx.set_scene(s)
+        ctx.build_bvh(b2pt.FLAG_FORCE_BVH)
+        ctx.set_camera(b2pt.Camera(W, H))
+        ctx.render(spp, depth, b2pt.FLAG_FORCE_BVH)
+        g2, st2 = ctx.read_color(), ctx.stats()
+    assert st2.segments == st.segments and np.array_equal(g, g2, equal_nan=True)
+
+
+def test_gpu_lbvh_equals_host_sah_on_the_million_sphere_scene(b2pt):
+    """Both builders, 1M spheres: identical primary hits and identical images; the device build is much faster."""
+    n, W, H = 1_000_000, 960, 540
+    s = b2pt.Scene.spheres(n)
+    with b2pt.Context(0) as ctx:
+        ctx.set_scene(s)
+        ctx.set_camera(b2pt.Camera(W, H))
+        t0 = time.time()
+        ctx.build_bvh(0)
+        ctx.synchronize()
+        host_s = time.time() - t0
+        p0, t0_ = ctx.primary_hits()
+        ctx.render(2, 50, 0)
+        a, sa = ctx.read_color(), ctx.stats()
+        t1 = time.time()
+        ctx.build_bvh(b2pt.FLAG_GPU_LBVH)
+        ctx.synchronize()
+        gpu_s = time.time() - t1
+        p1, t1_ = ctx.primary_hits()
+        ctx.render(2, 50, b2pt.FLAG_GPU_LBVH)
+        b, sb = ctx.read_color(), ctx.stats()
+    # Tree independence holds except for near-coincident grazing hits: the reference's sphere formula cancels badly
+    # for small, far spheres and can report a hit whose t lies BEFORE the ray enters the sphere's own box; whether a
+    # traversal that prunes by the closest distance still reaches that box depends on the order of the visits
+    # (measured: 2 of 518 400 primary rays differ between the two trees; DESIGN.md 5).
+    same = (p0 == p1) & (t0_.view(np.uint32) == t1_.view(np.uint32))
+    assert (~same).sum() <= 1e-5 * same.size, int((~same).sum())
+    assert abs(sa.segments - sb.segments) <= 1e-5 * sa.segments
+    eq = ((a == b) | (np.isnan(a) & np.isnan(b))).all(1)
+    assert eq.mean() > 0.9999
+    assert sb.bvhNodes == 2 * (n + 2)
+    assert gpu_s < host_s
+    print("host SAH build %.3f s, device LBVH build %.3f s" % (host_s, gpu_s))
