@@ -38,18 +38,23 @@ def build_lib(force=False, verbose=False):
         return LIB
     if not force and not _stale():
         return LIB
-    objs = []
-    for src in SOURCES:
+    def compile_one(src):
         obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
         cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         if src.endswith(".cpp"):
             cmd = [NVCC] + NVCC_FLAGS + ["-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        if verbose or r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-        if r.returncode != 0:
-            raise RuntimeError("nvcc failed for %s" % src)
-        objs.append(obj)
+        return src, obj, r
+
+    from concurrent.futures import ThreadPoolExecutor
+    objs = []
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:  # the translation units compile side by side
+        for src, obj, r in pool.map(compile_one, SOURCES):
+            if verbose or r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed for %s" % src)
+            objs.append(obj)
     cmd = [NVCC, "-shared", "-ccbin", HOST_CXX, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fopenmp",
            "-o", LIB] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
