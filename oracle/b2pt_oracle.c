@@ -6,8 +6,10 @@
  * (the reference's CMakeLists.txt:1-93 sets no -march/-mfma, i.e. an x86-64 baseline
  * build with no FMA contraction; -ffp-contract=off reproduces that on any host).
  *
- * PARITY STATUS: parity unpinned (no reference tests/goldens exist; VTK-m is absent so the
- * reference cannot be compiled here).  VTK-m math semantics assumed:
+ * PARITY STATUS: see b2pt_oracle.h -- pinned bit for bit to the reference's own worklets, Camera::RayGen and scene
+ * builder through oracle/ref_harness.cxx + ref_scene.cxx; what stays "parity unpinned" is VTK-m's own math and
+ * LinearBVH shape (VTK-m is absent, so the reference cannot be compiled as a whole here).
+ * VTK-m math semantics assumed:
  *   Dot(a,b)      = (a0*b0 + a1*b1) + a2*b2
  *   Cross(a,b)    = (a1*b2 - a2*b1, a2*b0 - a0*b2, a0*b1 - a1*b0)   (plain, no FMA compensation)
  *   RSqrt(x)      = 1.0f / sqrtf(x)  (host form);  Normalize(v) = v * RSqrt(Dot(v,v))

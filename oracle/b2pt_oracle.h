@@ -15,6 +15,8 @@
  * to that harness (images, segment counts, primary distances; tests/test_ref_harness.py and the committed
  * "refworklets" vectors in tests/golden/).  Camera ray generation is pinned the same way: the class
  * Camera::RayGen is lifted out of the reference's Camera.cxx at build time and compiled into the harness.
+ * The scene too: the reference's CornellBox.cpp is compiled where it lies (oracle/ref_scene.cxx) and its points,
+ * quad/sphere ids and material indices equal orc_cornell_scene's bit for bit.
  * Still unpinned, because they live inside VTK-m: its math (Cross/Normalize/Min/Max, restated in vtkm_min from its
  * documented semantics) and its LinearBVH tree shape (affects 1 of 65536 primary rays through the non-planar
  * quad's leaf box).

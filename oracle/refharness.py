@@ -56,6 +56,8 @@ def lib():
         L.b2ref_sphere_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p]
         L.b2ref_raygen.restype = None
         L.b2ref_raygen.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_uint32), C.c_void_p]
+        L.b2ref_cornell_scene.restype = C.c_int
+        L.b2ref_cornell_scene.argtypes = [C.c_void_p] * 12 + [C.c_int64]
         L.b2ref_render.restype = C.c_int
         L.b2ref_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64),
                                    C.c_void_p, C.c_void_p]
@@ -98,6 +100,25 @@ def sphere_hit(o, d, tmin, tmax, c, r):
     rec = np.zeros(9, np.float32)
     h = lib().b2ref_sphere_hit(_p(a[0]), _p(a[1]), tmin, tmax, _p(a[2]), r, _p(rec))
     return bool(h), rec
+
+
+def cornell_scene():
+    """The reference's own CornellBox::buildDataSet + extract (CornellBox.cpp:141-437), compiled from where it lies.
+    Returns a dict of arrays in orc_cornell_scene's layout, trimmed to the counts the reference produced."""
+    cap = 4096
+    f32, i64, i32 = np.float32, np.int64, np.int32
+    pts, quadIds = np.zeros((cap, 3), f32), np.zeros((cap, 5), i64)
+    sphPt, sphR = np.zeros(cap, i64), np.zeros(cap, f32)
+    matQ, texQ, matS, texS = (np.zeros(cap, i64) for _ in range(4))
+    matType, texType, tex = np.zeros(5, i32), np.zeros(5, i32), np.zeros((4, 3), f32)
+    n = np.zeros(3, i64)
+    rc = lib().b2ref_cornell_scene(_p(pts), _p(quadIds), _p(sphPt), _p(sphR), _p(matQ), _p(texQ), _p(matS),
+                                   _p(texS), _p(matType), _p(texType), _p(tex), _p(n), cap)
+    if rc != 0:
+        raise RuntimeError("b2ref_cornell_scene failed: %d" % rc)
+    npt, nq, ns = (int(v) for v in n)
+    return dict(pts=pts[:npt], quadIds=quadIds[:nq], sphPt=sphPt[:ns], sphR=sphR[:ns], matIdxQ=matQ[:nq],
+                texIdxQ=texQ[:nq], matIdxS=matS[:ns], texIdxS=texS[:ns], matType=matType, texType=texType, tex=tex)
 
 
 def render(scene, cam, spp, max_depth, tree_variant=0):

@@ -33,6 +33,22 @@ using Int64 = std::int64_t;
 using Float32 = float;
 using Float64 = double;
 
+enum class CopyFlag
+{
+  Off = 0,
+  On = 1
+};
+enum CellShapeIdEnum
+{
+  CELL_SHAPE_EMPTY = 0,
+  CELL_SHAPE_VERTEX = 1,
+  CELL_SHAPE_LINE = 3,
+  CELL_SHAPE_TRIANGLE = 5,
+  CELL_SHAPE_QUAD = 9
+};
+struct TopologyElementTagPoint {};
+struct TopologyElementTagCell {};
+
 template <typename T, IdComponent N>
 class Vec
 {

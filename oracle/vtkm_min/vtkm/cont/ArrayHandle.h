@@ -45,10 +45,20 @@ public:
   ArrayPortal<T> PrepareForInput(Device, Token&) const { return Portal(); }
   template <typename Device>
   ArrayPortal<T> PrepareForInPlace(Device, Token&) const { return Portal(); }
+  ArrayPortal<T> WritePortal() const { return Portal(); }
+  ArrayPortal<T> ReadPortal() const { return Portal(); }
   std::vector<T>& Vector() { return *data; }
+  const std::vector<T>& Vector() const { return *data; }
 private:
   std::shared_ptr<std::vector<T>> data;
 };
+template <typename T>
+inline ArrayHandle<T> make_ArrayHandle(const std::vector<T>& v, vtkm::CopyFlag)
+{
+  ArrayHandle<T> h;
+  h.Vector() = v;
+  return h;
+}
 } // namespace cont
 } // namespace vtkm
 #endif

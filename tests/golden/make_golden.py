@@ -2,7 +2,7 @@
 
 Provenance of each group:
   "survey"      derived independently by the surveyor's throwaway numpy probe.
-  "refworklets" outputs of the REFERENCE'S OWN header-only worklets, compiled from /root/reference against the
+  "refworklets" outputs of the REFERENCE'S OWN header-only worklets and scene builder (CornellBox.cpp), compiled from /root/reference against the
                 VTK-m stand-in of oracle/vtkm_min/ and driven in the reference's launch order by
                 oracle/ref_harness.cxx (only generated when /root/reference is present; the reference as a whole
                 needs VTK-m and cannot be built here).  These pin the C oracle to the reference's code.
@@ -72,6 +72,10 @@ def main():
         # primary-ray closest distances at 256x256 (45 rays depend on the leaf-box gate, 1 on tree shape)
         _, _, rt0, rhit0 = R.render(sc, O.Camera(256, 256), 1, 1)
         np.save(os.path.join(HERE, "primary_t_256_refworklets.npy"), rt0)
+        # the reference's own scene builder (CornellBox.cpp compiled where it lies, oracle/ref_scene.cxx): bit patterns
+        rs = R.cornell_scene()
+        r["cornell_scene"] = {k: (v.view(np.uint32) if v.dtype == np.float32 else v).ravel().tolist()
+                              for k, v in rs.items()}
     else:
         with open(os.path.join(HERE, "golden.json")) as f:
             old = json.load(f)
