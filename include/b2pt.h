@@ -50,6 +50,7 @@ typedef enum b2pt_status
 #define B2PT_FLAG_NO_TAIL 0x20u             /* never switch deep bounces to the global-queue tail mode (A/B parity checks) */
 #define B2PT_FLAG_NO_OVERLAP 0x40u          /* run the sample batches one after the other on the context's stream */
 #define B2PT_FLAG_GPU_LBVH 0x80u            /* build the BVH on the device (Morton LBVH) instead of the host binned-SAH builder */
+#define B2PT_FLAG_VIEWS_NORMALIZE 0x100u     /* b2pt_render_views: apply b2pt_normalize's sqrt(de_nan(sum)/spp) to every view */
 #define B2PT_FLAG_NO_AA 0x10u               /* do not use the axis-aligned quad specialisation (A/B parity checks) */
 
 typedef struct b2pt_stats
@@ -114,6 +115,18 @@ int b2pt_render(b2pt_ctx* ctx, int spp, int maxDepth, uint32_t flags);
 /* Same without clearing, rendering global sample indices [sampleBegin, sampleBegin+sampleCount):
  * the multi-GPU sharding primitive (each rank renders a disjoint sample range of every pixel). */
 int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDepth, uint32_t flags);
+/* View-batched render.  Replaces the camera loop around runPath of generateHemisphere / fibonacciHemisphere
+ * (main.cc:431-561 calling generate() :386-429): nViews independent path-traced images of the resident scene, every
+ * one bit-identical to b2pt_set_camera(view) + b2pt_render(spp, maxDepth, flags).  views holds 10 floats per view
+ * (pos[3], lookAt[3], up[3], fovDeg); all views share the canvas size W x H.  While W*H*spp fits a sample batch,
+ * (view, sample, pixel) is one flat path index space and many views share each launch, so small canvases (the
+ * reference's 128 x 128 x 10 spp default) fill the GPU; larger views are rendered one after the other.  The sums land
+ * in a library-owned device array [nViews][W*H] of float4 (b2pt_views_device_ptr) and, when rgbaOut is not NULL, are
+ * copied to the host array rgbaOut[nViews*W*H*4] (the call then synchronises).  The context's own camera and canvas
+ * are left untouched.  B2PT_FLAG_REFERENCE_STREAM is rejected (B2PT_ERR_BAD_VALUE). */
+int b2pt_render_views(b2pt_ctx* ctx, int nViews, const float* views, int W, int H, int spp, int maxDepth,
+                      uint32_t flags, float* rgbaOut);
+void* b2pt_views_device_ptr(b2pt_ctx* ctx);
 int b2pt_clear_color(b2pt_ctx* ctx);
 /* Attach a caller-owned device buffer of W*H float4 as the radiance sum (NULL detaches). */
 int b2pt_set_color_buffer(b2pt_ctx* ctx, void* deviceFloat4);

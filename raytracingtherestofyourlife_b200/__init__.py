@@ -25,6 +25,7 @@ FLAG_NO_AA = 0x10
 FLAG_NO_TAIL = 0x20
 FLAG_NO_OVERLAP = 0x40
 FLAG_GPU_LBVH = 0x80
+FLAG_VIEWS_NORMALIZE = 0x100
 
 ERR_BAD_VALUE, ERR_CUDA, ERR_STATE, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 
@@ -60,6 +61,8 @@ SIGNATURES = {
     "b2pt_seed": (_i32, [_vp, C.c_uint32]),
     "b2pt_render": (_i32, [_vp, _i32, _i32, C.c_uint32]),
     "b2pt_render_range": (_i32, [_vp, _i32, _i32, _i32, C.c_uint32]),
+    "b2pt_render_views": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, C.c_uint32, _vp]),
+    "b2pt_views_device_ptr": (_vp, [_vp]),
     "b2pt_clear_color": (_i32, [_vp]),
     "b2pt_set_color_buffer": (_i32, [_vp, _vp]),
     "b2pt_color_device_ptr": (_vp, [_vp]),
@@ -226,6 +229,16 @@ class Context:
 
     def render_range(self, begin, count, max_depth, flags=0):
         _check(lib().b2pt_render_range(self._h, begin, count, max_depth, flags))
+
+    def render_views(self, views, W, H, spp, max_depth, flags=0, out=None):
+        """b2pt_render_views: `views` is [nViews, 10] float32 (pos, lookAt, up, fovDeg); returns the [nViews, H*W, 4]
+        radiance sums (un-normalised unless FLAG_VIEWS_NORMALIZE), each bit-identical to set_camera + render."""
+        v = np.ascontiguousarray(views, np.float32).reshape(-1, 10)
+        if out is None:
+            out = np.empty((v.shape[0], W * H, 4), np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == v.shape[0] * W * H * 4
+        _check(lib().b2pt_render_views(self._h, v.shape[0], _p(v), W, H, spp, max_depth, flags, _p(out)))
+        return out
 
     def clear_color(self):
         _check(lib().b2pt_clear_color(self._h))

@@ -149,6 +149,10 @@ struct b2pt_ctx
   DevBuf<uint32_t> seeds;
   DevBuf<unsigned long long> nanCounter;
   std::vector<uint32_t> hCounters;
+  // view-batched render (b2pt_render_views): camera bases and the [nViews][W*H] radiance sums
+  DevBuf<B2Camera> dViews;
+  DevBuf<float4> viewColor;
+  int64_t viewCount = 0, viewPixels = 0;
 
   // tail-mode depths chosen by the last render with the same scene / canvas / depth / batch shape (reused without
   // a new synchronisation; they are heuristics, any value is correct)
@@ -970,11 +974,11 @@ int b2pt_build_bvh_ex(b2pt_ctx* ctx, uint32_t flags)
 
 int b2pt_build_bvh(b2pt_ctx* ctx) { return b2pt_build_bvh_ex(ctx, 0); }
 
-int b2pt_set_camera(b2pt_ctx* ctx, const float pos[3], const float lookAt[3], const float up[3], float fovDeg, int W,
-                    int H)
+// Camera.cxx:913-914 Look; :803-811 SetUp; RayGen ctor :438-476 with fovX = fovY (:936-938), zoom off.
+// Validation messages are the reference's (Camera.cxx:645, 667, 720-724).
+static int make_camera(const float pos[3], const float lookAt[3], const float up[3], float fovDeg, int W, int H,
+                       B2Camera& c)
 {
-  if (int rc = bind(ctx))
-    return rc;
   if (!pos || !lookAt || !up)
     return fail(B2PT_ERR_BAD_VALUE, "null camera vector");
   if (H <= 0)
@@ -987,7 +991,6 @@ int b2pt_set_camera(b2pt_ctx* ctx, const float pos[3], const float lookAt[3], co
     return fail(B2PT_ERR_BAD_VALUE, "Camera feild of view must be less than 180."); // Camera.cxx:724
   if ((int64_t)W * H > (int64_t)1 << 26)
     return fail(B2PT_ERR_BAD_VALUE, "canvas larger than 2^26 pixels");
-  // Camera.cxx:913-914 Look; :803-811 SetUp; RayGen ctor :438-476 with fovX = fovY (:936-938), zoom off
   H3 look = hnormalize(hsub({ lookAt[0], lookAt[1], lookAt[2] }, { pos[0], pos[1], pos[2] }));
   H3 upv = { up[0], up[1], up[2] };
   if (!(upv.x == 0.f && upv.y == 1.f && upv.z == 0.f))
@@ -997,13 +1000,24 @@ int b2pt_set_camera(b2pt_ctx* ctx, const float pos[3], const float lookAt[3], co
   const float thy = std::tan((fovDeg * pi180) * .5f);
   H3 u = hnormalize(hcross(look, upv));
   H3 v = hnormalize(hcross(u, look));
-  B2Camera c{};
+  c = B2Camera{};
   hst(c.dx, hscale(u, 2 * thx / (float)W));
   hst(c.dy, hscale(v, 2 * thy / (float)H));
   hst(c.nlook, hnormalize(look));
   c.pos[0] = pos[0], c.pos[1] = pos[1], c.pos[2] = pos[2];
   c.W = W;
   c.H = H;
+  return B2PT_OK;
+}
+
+int b2pt_set_camera(b2pt_ctx* ctx, const float pos[3], const float lookAt[3], const float up[3], float fovDeg, int W,
+                    int H)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  B2Camera c{};
+  if (int rc = make_camera(pos, lookAt, up, fovDeg, W, H, c))
+    return rc;
   const bool resized = (W != ctx->cam.W || H != ctx->cam.H);
   ctx->cam = c;
   ctx->haveCamera = true;
@@ -1107,7 +1121,11 @@ static int64_t batch_target_paths(b2pt_ctx* ctx)
   return target;
 }
 
-int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDepth, uint32_t flags)
+// One render of the current scene.  nViews == 0: the context's camera, samples [sampleBegin, sampleBegin+sampleCount)
+// accumulated into the context's canvas.  nViews > 0 (b2pt_render_views): the same sample range for every camera of
+// ctx->dViews, accumulated into ctx->viewColor[view]; a batch holds whole views (viewsPerBatch x sampleCount sample
+// slots), so the caller guarantees W*H*sampleCount <= the batch target.
+static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDepth, uint32_t flags, int64_t nViews)
 {
   if (int rc = bind(ctx))
     return rc;
@@ -1133,15 +1151,27 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
       return rc;
     ctx->haveBvh = true;
   }
-  if (int rc = ensure_color(ctx))
-    return rc;
+  const bool viewMode = nViews > 0;
+  if (!viewMode)
+    if (int rc = ensure_color(ctx))
+      return rc;
 
   const int64_t N = (int64_t)ctx->cam.W * ctx->cam.H;
+  // B = sample slots per batch (view mode: whole views, viewsPerBatch x sampleCount slots)
   int64_t B = refStream ? 1 : std::max<int64_t>(1, batch_target_paths(ctx) / N);
-  B = std::min<int64_t>(B, std::max(sampleCount, 1));
+  int64_t viewsPerBatch = 0;
+  if (viewMode)
+  {
+    if (refStream)
+      return fail(B2PT_ERR_BAD_VALUE, "REFERENCE_STREAM cannot be combined with a view-batched render");
+    viewsPerBatch = std::min<int64_t>(nViews, std::max<int64_t>(1, std::min<int64_t>(B, 0xfffffff0LL / N) / std::max(sampleCount, 1)));
+    B = viewsPerBatch * sampleCount;
+  }
+  else
+    B = std::min<int64_t>(B, std::max(sampleCount, 1));
   if (N * B > 0xfffffff0LL)
     B = 0xfffffff0LL / N;
-  const int64_t nBatches = sampleCount == 0 ? 0 : (sampleCount + B - 1) / B;
+  const int64_t nBatches = sampleCount == 0 ? 0 : (viewMode ? (nViews + viewsPerBatch - 1) / viewsPerBatch : (sampleCount + B - 1) / B);
   const int64_t pathsPerBatch = N * B;
 
   // Static partition of the queue and the bins into one region per persistent warp (b2pt_types.h).
@@ -1205,11 +1235,14 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
   }
   const int profDepths = std::min(maxDepth - 1, (int)b2pt_ctx::kProfDepths); // events 0..profDepths bracket that many bounces
   ctx->profDepths = nBatches > 0 ? profDepths : 0;
-  ctx->profPaths = nBatches > 0 ? N * std::min<int64_t>(B, sampleCount) : 0;
+  ctx->profPaths = nBatches > 0 ? N * (viewMode ? B : std::min<int64_t>(B, sampleCount)) : 0;
   for (int64_t batch = 0; batch < nBatches; ++batch)
   {
-    const int64_t s0 = batch * B;
-    const int64_t nb = std::min<int64_t>(B, sampleCount - s0);
+    // view mode: views [v0, v0+nv) with all their samples; otherwise samples [s0, s0+nb) of the one view
+    const int64_t v0 = batch * viewsPerBatch;
+    const int64_t nv = viewMode ? std::min<int64_t>(viewsPerBatch, nViews - v0) : 0;
+    const int64_t s0 = viewMode ? 0 : batch * B;
+    const int64_t nb = viewMode ? nv * sampleCount : std::min<int64_t>(B, sampleCount - s0);
     const int set = (int)(batch % nSets);
     b2pt_ctx::BatchBufs& bb = ctx->bufs[set];
     cudaStream_t bs = set ? ctx->extra[set] : ctx->stream;
@@ -1229,6 +1262,8 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
     A.nPaths = N * nb;
     A.nPixels = (int32_t)N;
     A.sampleBase = (int32_t)(sampleBegin + s0);
+    A.views = viewMode ? ctx->dViews.p + v0 : nullptr;
+    A.sppPerView = viewMode ? sampleCount : 0;
     A.maxDepth = maxDepth;
     A.seedOffset = ctx->seedOffset;
     A.flags = flags;
@@ -1262,9 +1297,14 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
       launches += 2;
     }
     // the canvas is accumulated in batch order (sample-order sums): wait for the previous batch's accumulate
-    if (overlap && batch > 0)
+    // (view batches write disjoint canvases: no order needed)
+    if (overlap && batch > 0 && !viewMode)
       CU(cudaStreamWaitEvent(bs, ctx->evAcc[(set + nSets - 1) % nSets], 0));
-    CU(b2pt::launch_accumulate(ctx->color(), bb.rad.p, (int)N, (int)nb, ctx->nanCounter.p, bs));
+    if (viewMode)
+      CU(b2pt::launch_accumulate(ctx->viewColor.p + v0 * N, bb.rad.p, (int)N, sampleCount, (int)nv,
+                                 ctx->nanCounter.p, bs));
+    else
+      CU(b2pt::launch_accumulate(ctx->color(), bb.rad.p, (int)N, (int)nb, 1, ctx->nanCounter.p, bs));
     ++launches;
     if (overlap)
       CU(cudaEventRecord(ctx->evAcc[set], bs));
@@ -1304,7 +1344,7 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
   CU(cudaEventRecord(ctx->evStop, ctx->stream));
 
   ctx->stats = b2pt_stats{};
-  ctx->stats.paths = N * (int64_t)sampleCount;
+  ctx->stats.paths = N * (int64_t)sampleCount * (viewMode ? nViews : 1);
   ctx->stats.launches = launches;
   ctx->stats.batches = (int32_t)nBatches;
   ctx->stats.samplesPerBatch = (int32_t)B;
@@ -1319,6 +1359,101 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
   ctx->pendingMaxDepth = maxDepth;
   ctx->pendingPathsPerBatch = pathsPerBatch;
   return B2PT_OK;
+}
+
+int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDepth, uint32_t flags)
+{
+  return render_impl(ctx, sampleBegin, sampleCount, maxDepth, flags, 0);
+}
+
+int b2pt_render_views(b2pt_ctx* ctx, int nViews, const float* views, int W, int H, int spp, int maxDepth,
+                      uint32_t flags, float* rgbaOut)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (nViews < 0 || (nViews > 0 && !views))
+    return fail(B2PT_ERR_BAD_VALUE, "b2pt_render_views: bad view list");
+  if (spp < 0)
+    return fail(B2PT_ERR_BAD_VALUE, "negative sample range");
+  if (flags & B2PT_FLAG_REFERENCE_STREAM)
+    return fail(B2PT_ERR_BAD_VALUE, "REFERENCE_STREAM cannot be combined with a view-batched render");
+  std::vector<B2Camera> cams((size_t)nViews);
+  for (int v = 0; v < nViews; ++v)
+  {
+    const float* p = views + 10 * (size_t)v;
+    if (int rc = make_camera(p, p + 3, p + 6, p[9], W, H, cams[(size_t)v]))
+      return rc;
+  }
+  if (nViews == 0)
+  {
+    ctx->viewCount = 0;
+    return B2PT_OK;
+  }
+  const int64_t N = (int64_t)W * H;
+  if (N * nViews > (int64_t)1 << 30)
+    return fail(B2PT_ERR_BAD_VALUE, "b2pt_render_views: more than 2^30 output pixels (16 GiB); split the view list");
+  CU(ctx->viewColor.reserve((size_t)(N * nViews)));
+  CU(ctx->dViews.reserve((size_t)nViews));
+  ctx->viewCount = nViews;
+  ctx->viewPixels = N;
+  // the context's own camera gives the canvas shape to the launches; it is restored afterwards
+  const B2Camera savedCam = ctx->cam;
+  const bool savedHave = ctx->haveCamera;
+  float4* const savedExt = ctx->colorExt;
+  CU(cudaMemsetAsync(ctx->viewColor.p, 0, sizeof(float4) * (size_t)(N * nViews), ctx->stream));
+  ctx->cam = cams[0];
+  ctx->haveCamera = true;
+  int rc = B2PT_OK;
+  auto restore = [&]() {
+    ctx->cam = savedCam;
+    ctx->haveCamera = savedHave;
+    ctx->colorExt = savedExt;
+  };
+  if (spp > 0 && N * spp <= std::min<int64_t>(batch_target_paths(ctx), 0xfffffff0LL))
+  { // whole views fit a batch: (view, sample, pixel) is one flat index space, one set of launches per batch of views
+    // (pageable source: the copy is staged before the call returns, so `cams` may go out of scope)
+    cudaError_t e = cudaMemcpyAsync(ctx->dViews.p, cams.data(), sizeof(B2Camera) * (size_t)nViews,
+                                    cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess)
+    {
+      restore();
+      return fail(B2PT_ERR_CUDA, "cudaMemcpyAsync(views): %s", cudaGetErrorString(e));
+    }
+    rc = render_impl(ctx, 0, spp, maxDepth, flags, nViews);
+  }
+  else
+  { // a single view already fills several batches: one ordinary render per view into its slice
+    int64_t paths = 0, launches = 0;
+    for (int v = 0; v < nViews && rc == B2PT_OK; ++v)
+    {
+      ctx->cam = cams[(size_t)v];
+      ctx->colorExt = ctx->viewColor.p + (size_t)v * N;
+      rc = render_impl(ctx, 0, spp, maxDepth, flags, 0);
+      paths += ctx->stats.paths;
+      launches += ctx->stats.launches;
+    }
+    ctx->stats.paths = paths;
+    ctx->stats.launches = launches;
+  }
+  restore();
+  if (rc != B2PT_OK)
+    return rc;
+  if (flags & B2PT_FLAG_VIEWS_NORMALIZE)
+    CU(b2pt::launch_normalize(ctx->viewColor.p, N * nViews, spp, ctx->stream));
+  if (rgbaOut)
+  {
+    CU(cudaMemcpyAsync(rgbaOut, ctx->viewColor.p, sizeof(float4) * (size_t)(N * nViews), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return B2PT_OK;
+}
+
+void* b2pt_views_device_ptr(b2pt_ctx* ctx)
+{
+  if (bind(ctx) != B2PT_OK || ctx->viewCount == 0)
+    return nullptr;
+  return ctx->viewColor.p;
 }
 
 int b2pt_render(b2pt_ctx* ctx, int spp, int maxDepth, uint32_t flags)

@@ -110,13 +110,24 @@ __device__ __forceinline__ void load_ray(const B2Camera& cam, const B2RenderArgs
   {
     pid = (uint32_t)idx; // path id chosen by the caller (tile-interleaved over the warps' regions)
     const uint32_t pixel = pid % (uint32_t)A.nPixels;
-    const uint32_t b = pid / (uint32_t)A.nPixels;
-    // MapperPathTracer.cxx:265-267: seeds[i] = i.  Production stream: one stream per (pixel, sample).
-    rng = (A.flags & B2PT_FLAG_REFERENCE_STREAM_DEV)
-      ? A.seeds[pixel]
-      : pixel + A.seedOffset + (uint32_t)(A.sampleBase + (int)b) * B2PT_GOLDEN;
-    d = raygen(cam, (int)pixel, rng);
-    o = ld3(cam.pos);
+    uint32_t b = pid / (uint32_t)A.nPixels;
+    if (A.views)
+    { // view-batched render: every view is an independent render with the same per-(pixel, sample) streams
+      const B2Camera vc = A.views[b / (uint32_t)A.sppPerView];
+      b = b % (uint32_t)A.sppPerView;
+      rng = pixel + A.seedOffset + (uint32_t)(A.sampleBase + (int)b) * B2PT_GOLDEN;
+      d = raygen(vc, (int)pixel, rng);
+      o = ld3(vc.pos);
+    }
+    else
+    {
+      // MapperPathTracer.cxx:265-267: seeds[i] = i.  Production stream: one stream per (pixel, sample).
+      rng = (A.flags & B2PT_FLAG_REFERENCE_STREAM_DEV)
+        ? A.seeds[pixel]
+        : pixel + A.seedOffset + (uint32_t)(A.sampleBase + (int)b) * B2PT_GOLDEN;
+      d = raygen(cam, (int)pixel, rng);
+      o = ld3(cam.pos);
+    }
     T = mk3(1.f, 1.f, 1.f);
   }
   else
@@ -676,23 +687,27 @@ __global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kTailBloc
 }
 
 __global__ void __launch_bounds__(256)
-  k_accumulate(float4* __restrict__ color, const float4* __restrict__ rad, int nPixels, int samplesInBatch,
+  k_accumulate(float4* __restrict__ color, const float4* __restrict__ rad, int nPixels, int samplesPerView, int nViews,
                unsigned long long* nanCounter)
 {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= nPixels)
+  // canvas entry P = view * nPixels + pixel (one view unless the render is view-batched); the view's samples are
+  // the slots [view * samplesPerView, (view + 1) * samplesPerView) of the batch
+  const int64_t P = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (P >= (int64_t)nPixels * nViews)
     return;
-  float4 c = color[p];
+  const int64_t view = P / nPixels;
+  const float4* r0 = rad + view * samplesPerView * (int64_t)nPixels + (P - view * nPixels);
+  float4 c = color[P];
   int nan = 0;
-  for (int b = 0; b < samplesInBatch; ++b)
+  for (int b = 0; b < samplesPerView; ++b)
   {
-    const float4 r = rad[(size_t)b * nPixels + p];
+    const float4 r = r0[(size_t)b * nPixels];
     nan += (r.x != r.x || r.y != r.y || r.z != r.z) ? 1 : 0;
     c.x += r.x; // cols += sumtotl, MapperPathTracer.cxx:350, in sample order
     c.y += r.y;
     c.z += r.z;
   }
-  color[p] = c;
+  color[P] = c;
   if (nan)
     atomicAdd(nanCounter, (unsigned long long)nan);
 }
@@ -884,10 +899,12 @@ cudaError_t launch_bounce(const LaunchCfg& cfg, bool primary, int mode, const B2
 
 int warps_per_block() { return kWarps; }
 
-cudaError_t launch_accumulate(float4* color, const float4* rad, int nPixels, int samplesInBatch,
+cudaError_t launch_accumulate(float4* color, const float4* rad, int nPixels, int samplesPerView, int nViews,
                               unsigned long long* nanCounter, cudaStream_t stream)
 {
-  k_accumulate<<<(nPixels + 255) / 256, 256, 0, stream>>>(color, rad, nPixels, samplesInBatch, nanCounter);
+  const int64_t n = (int64_t)nPixels * nViews;
+  k_accumulate<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(color, rad, nPixels, samplesPerView, nViews,
+                                                                nanCounter);
   return cudaGetLastError();
 }
 

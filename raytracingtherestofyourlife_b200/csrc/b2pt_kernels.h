@@ -39,7 +39,7 @@ cudaError_t launch_tail_loop(const B2Camera& cam, const B2SmallScene* small, con
                              const B2Lights& lights, const B2RenderArgs& args, cudaStream_t stream);
 // K4: color[p] += sum_b rad[b*N + p] in sample order; counts NaN samples into *nanCounter.
 int warps_per_block();
-cudaError_t launch_accumulate(float4* color, const float4* rad, int nPixels, int samplesInBatch,
+cudaError_t launch_accumulate(float4* color, const float4* rad, int nPixels, int samplesPerView, int nViews,
                               unsigned long long* nanCounter, cudaStream_t stream);
 cudaError_t launch_primary_hits(const B2Camera& cam, const B2SmallScene* small, const B2BvhScene* bvh,
                                 uint32_t seedOffset, int32_t* primOut, float* tOut, cudaStream_t stream);

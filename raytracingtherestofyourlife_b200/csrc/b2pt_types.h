@@ -219,6 +219,9 @@ struct B2RenderArgs
   uint32_t* binTotals;   // [maxDepth*4] of this batch: tail mode, records appended to global bin k at bounce d
   float4* rad;          // per-path radiance, [b*N + pixel]
   uint32_t* seeds;      // per-pixel persistent RNG state (reference-stream mode)
+  // view-batched render (b2pt_render_views): sample slot b of the batch belongs to view b / sppPerView of this
+  // array and is that view's sample b % sppPerView; nullptr = single view, the camera kernel parameter
+  const B2Camera* views;
   int64_t binStride;    // numWarps * regionCap
   int64_t nPaths;       // paths in this batch (N * samplesInBatch)
   int32_t numWarps;
@@ -227,6 +230,7 @@ struct B2RenderArgs
   int32_t sampleBase;   // global index of the batch's first sample
   int32_t depth;        // this bounce
   int32_t maxDepth;
+  int32_t sppPerView;
   uint32_t seedOffset;
   uint32_t flags;
 };

@@ -1,6 +1,7 @@
 // MapperPathTracer.cxx -- see MapperPathTracer.h.  Host-side marshalling only; every computation happens in
 // libb2pt (sm_100a kernels) through the C-ABI.
 #include "MapperPathTracer.h"
+#include <cstring>
 
 #include <cfloat>
 #include <string>
@@ -242,6 +243,53 @@ void MapperPathTracer::RenderCells(const vtkm::cont::DynamicCellSet& cellset, co
     throw vtkm::cont::ErrorBadValue("MapperPathTracer: no canvas set");
   Internals->RayCamera.SetParameters(camera, *Internals->Canvas); // validates like the reference (:372)
   RenderCellsImpl(cellset, coords, scalarField, camera);
+}
+
+void MapperPathTracer::RenderCellsViews(const vtkm::cont::DynamicCellSet& cellset,
+                                        const vtkm::cont::CoordinateSystem& coords,
+                                        const std::vector<vtkm::rendering::Camera>& cameras,
+                                        std::vector<vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Float32, 4>>>& colors)
+{
+  if (Internals->Canvas == nullptr)
+    throw vtkm::cont::ErrorBadValue("MapperPathTracer: no canvas set");
+  auto* canvas = Internals->Canvas;
+  const vtkm::Id nx = canvas->GetWidth(), ny = canvas->GetHeight();
+  for (const auto& camera : cameras)
+    Internals->RayCamera.SetParameters(camera, *canvas); // validates every view like the reference (:372)
+  auto tup = extract(cellset);
+  auto SphereIds = std::get<0>(tup);
+  auto SphereRadii = std::get<1>(tup);
+  auto QuadIds = std::get<3>(tup);
+  vtkm::cont::ArrayHandle<vtkm::Int32> matIdArray, texIdArray;
+  matIdArray.Allocate(nx * ny);
+  texIdArray.Allocate(nx * ny);
+  buildBVH(coords, QuadIds, SphereIds, SphereRadii, matIdArray, texIdArray, MatIdx, TexIdx);
+
+  std::vector<float> views(cameras.size() * 10);
+  for (size_t v = 0; v < cameras.size(); ++v)
+  {
+    const auto pos = cameras[v].GetPosition(), at = cameras[v].GetLookAt(), up = cameras[v].GetViewUp();
+    float* p = &views[10 * v];
+    for (int k = 0; k < 3; ++k)
+      p[k] = pos[k], p[3 + k] = at[k], p[6 + k] = up[k];
+    p[9] = cameras[v].GetFieldOfView();
+  }
+  b2pt_ctx* ctx = b2pt_facade::Context();
+  b2pt_facade::Check(b2pt_seed(ctx, 0)); // seeds[i] = i, MapperPathTracer.cxx:265-267
+  std::vector<float> rgba(cameras.size() * static_cast<size_t>(nx * ny) * 4);
+  b2pt_facade::Check(b2pt_render_views(ctx, static_cast<int>(cameras.size()), views.data(), static_cast<int>(nx),
+                                       static_cast<int>(ny), samplecount, depthcount, RenderFlags, rgba.data()));
+  colors.resize(cameras.size());
+  for (size_t v = 0; v < cameras.size(); ++v)
+  {
+    colors[v].Allocate(nx * ny);
+    std::memcpy(colors[v].GetStorage(), &rgba[v * static_cast<size_t>(nx * ny) * 4],
+                sizeof(float) * 4 * static_cast<size_t>(nx * ny));
+  }
+  b2pt_stats st;
+  b2pt_facade::Check(b2pt_get_stats(ctx, &st));
+  LastRenderMs = st.renderMs;
+  LastSegments = st.segments;
 }
 
 void MapperPathTracer::SetCompositeBackground(bool on) { Internals->CompositeBackground = on; }

@@ -8,6 +8,7 @@
 #define b2pt_facade_MapperPathTracer_h
 
 #include <memory>
+#include <vector>
 #include <tuple>
 
 #include <vtkm/rendering/Rendering.h>
@@ -90,6 +91,13 @@ public:
 
   // B200 additions (not in the reference): render flags (B2PT_FLAG_*) and the statistics of the last render.
   void SetRenderFlags(unsigned int flags) { RenderFlags = flags; }
+  // Many cameras, one call: what main.cc's generateHemisphere / fibonacciHemisphere loops do by calling RenderCells
+  // per view point (main.cc:431-561).  Every camera renders onto a canvas of the size of the canvas set with
+  // SetCanvas; image v lands in colors[v] exactly as RenderCells would leave it in canvas->GetColorBuffer()
+  // (un-normalised sums, same bits).  Small canvases share GPU launches across views (b2pt_render_views).
+  void RenderCellsViews(const vtkm::cont::DynamicCellSet& cellset, const vtkm::cont::CoordinateSystem& coords,
+                        const std::vector<vtkm::rendering::Camera>& cameras,
+                        std::vector<vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Float32, 4>>>& colors);
   double GetLastRenderMilliseconds() const { return LastRenderMs; }
   long long GetLastSegments() const { return LastSegments; }
 

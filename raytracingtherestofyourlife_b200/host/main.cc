@@ -17,6 +17,7 @@
 #include <sstream>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "CornellBox.h"
 #include "MapperPathTracer.h"
@@ -67,6 +68,23 @@ Options parse(int argc, char** argv)
   return o;
 }
 
+// NormalizeFunctor (main.cc:253-287): sqrt(de_nan(sum) / samplecount), alpha through the same sqrt
+void normalizeColors(vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Float32, 4>>& colors, int samplecount)
+{
+  auto cols = colors.WritePortal();
+  const float sc = static_cast<float>(samplecount);
+  for (vtkm::Id i = 0; i < cols.GetNumberOfValues(); ++i)
+  {
+    auto c = cols.Get(i);
+    for (int k = 0; k < 3; ++k)
+      if (!(c[k] == c[k]))
+        c[k] = 0;
+    for (int k = 0; k < 4; ++k)
+      c[k] = std::sqrt(c[k] / sc);
+    cols.Set(i, c);
+  }
+}
+
 // the reference's runPath (main.cc:289-323): this body is what a reference user already has
 void runPath(CornellBox& cb, int samplecount, int depthcount, vtkm::rendering::Canvas& canvas,
              vtkm::rendering::Camera& cam, bool stats)
@@ -83,22 +101,10 @@ void runPath(CornellBox& cb, int samplecount, int depthcount, vtkm::rendering::C
               << "  path samples/s = " << double(canvas.GetWidth()) * canvas.GetHeight() * samplecount /
         (mapper.GetLastRenderMilliseconds() * 1e-3)
               << "  segments = " << mapper.GetLastSegments() << std::endl;
-  // NormalizeFunctor (main.cc:253-287): sqrt(de_nan(sum) / samplecount), alpha through the same sqrt
-  auto cols = canvas.GetColorBuffer().WritePortal();
-  const float sc = static_cast<float>(samplecount);
-  for (vtkm::Id i = 0; i < cols.GetNumberOfValues(); ++i)
-  {
-    auto c = cols.Get(i);
-    for (int k = 0; k < 3; ++k)
-      if (!(c[k] == c[k]))
-        c[k] = 0;
-    for (int k = 0; k < 4; ++k)
-      c[k] = std::sqrt(c[k] / sc);
-    cols.Set(i, c);
-  }
+  normalizeColors(canvas.GetColorBuffer(), samplecount);
 }
 
-void savePnm(const std::string& stem, int nx, int ny, vtkm::rendering::Canvas& canvas)
+void savePnm(const std::string& stem, int nx, int ny, const vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Float32, 4>>& colors)
 {
   std::ofstream fs(stem + ".pnm");
   if (!fs)
@@ -107,7 +113,7 @@ void savePnm(const std::string& stem, int nx, int ny, vtkm::rendering::Canvas& c
     return;
   }
   fs << "P3\n" << nx << " " << ny << " 255" << std::endl;
-  auto cols = canvas.GetColorBuffer().ReadPortal();
+  auto cols = colors.ReadPortal();
   for (vtkm::Id i = 0; i < cols.GetNumberOfValues(); ++i)
   {
     auto col = cols.Get(i);
@@ -133,7 +139,10 @@ int generateHemisphere(CornellBox& cb, const Options& o)
   const float rTheta = thetaEnd / static_cast<float>(o.thetaCount);
   const float rPhi = (phiEnd - phiBegin) / float(o.phiCount);
   const float r = static_cast<float>(-1078 / 555.0);
-  int views = 0;
+  // the reference renders and saves inside the loop (generate(), main.cc:386-429); here the loop only collects the
+  // view points and ONE call renders them all (small canvases share GPU launches across views)
+  std::vector<vtkm::rendering::Camera> cameras;
+  std::vector<std::string> names;
   for (float phi = phiBegin; phi < (phiEnd - 0.5 * rPhi); phi += rPhi)
     for (float theta = thetaBegin; theta < thetaEnd; theta += rTheta)
     {
@@ -144,11 +153,24 @@ int generateHemisphere(CornellBox& cb, const Options& o)
       std::stringstream name; // generate(): "output-" << fixed << setw(4) << setprecision(4) << phi << "-" << theta
       name << o.out << "-" << std::fixed << std::setw(4) << std::setprecision(4) << phi << "-";
       name << std::fixed << std::setw(4) << std::setprecision(4) << theta;
-      runPath(cb, o.samples, o.depth, canvas, cam, o.stats);
-      savePnm(name.str(), o.x, o.y, canvas);
-      ++views;
+      cameras.push_back(cam);
+      names.push_back(name.str());
     }
-  return views;
+  vtkm::rendering::MapperPathTracer mapper(o.samples, o.depth, cb.matIdx, cb.texIdx, cb.matType, cb.texType, cb.tex);
+  mapper.SetCanvas(&canvas);
+  std::vector<vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Float32, 4>>> colors;
+  mapper.RenderCellsViews(cb.ds.GetCellSet(), cb.coord, cameras, colors);
+  if (o.stats)
+    std::cout << " GPU render ms = " << mapper.GetLastRenderMilliseconds() << " for " << cameras.size() << " views"
+              << "  path samples/s = " << double(o.x) * o.y * o.samples * double(cameras.size()) /
+        (mapper.GetLastRenderMilliseconds() * 1e-3)
+              << "  segments = " << mapper.GetLastSegments() << std::endl;
+  for (size_t v = 0; v < cameras.size(); ++v)
+  {
+    normalizeColors(colors[v], o.samples);
+    savePnm(names[v], o.x, o.y, colors[v]);
+  }
+  return static_cast<int>(cameras.size());
 }
 
 } // namespace
@@ -178,7 +200,7 @@ int main(int argc, char* argv[])
     cam.SetViewUp(vec3(0, 1, 0));
     cam.SetLookAt(vec3(278 / 555.0, 278 / 555.0, 278 / 555.0));
     runPath(*cb, o.samples, o.depth, canvas, cam, o.stats);
-    savePnm(o.out, o.x, o.y, canvas);
+    savePnm(o.out, o.x, o.y, canvas.GetColorBuffer());
   }
   catch (const vtkm::cont::Error& e)
   {

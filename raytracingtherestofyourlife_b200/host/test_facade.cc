@@ -245,6 +245,23 @@ static void testGpu(const std::string& prefix)
     else
       CHECK(atten.Get(i + rays.NumRays * 2)[0] == -7.f);
   CHECK(missed > 0 && missed < W * H);
+  // RenderCellsViews: three cameras in one call, each image the same bits as its own RenderCells call
+  {
+    std::vector<vtkm::rendering::Camera> cams(3, cam);
+    cams[1].SetPosition(vec3(0.9, 0.6, -1.3));
+    cams[2].SetPosition(vec3(0.1, 0.4, -1.5));
+    cams[2].SetFieldOfView(50.);
+    std::vector<vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Float32, 4>>> colors;
+    mapper.RenderCellsViews(cb.ds.GetCellSet(), cb.coord, cams, colors);
+    CHECK(colors.size() == 3);
+    for (size_t v = 0; v < colors.size(); ++v)
+    {
+      mapper.RenderCells(cb.ds.GetCellSet(), cb.coord, field, ct, cams[v], sr);
+      CHECK(colors[v].GetNumberOfValues() == W * H);
+      CHECK(std::memcmp(colors[v].GetStorage(), canvas.GetColorBuffer().GetStorage(), sizeof(float) * 4 * W * H) == 0);
+    }
+    CHECK(std::memcmp(colors[0].GetStorage(), colors[1].GetStorage(), sizeof(float) * 4 * W * H) != 0);
+  }
   // error mapping: invalid canvas size surfaces as ErrorBadValue with the reference's message
   vtkm::rendering::pathtracing::Camera bad;
   CHECK(throwsBadValue([&] { bad.SetWidth(0); }, "Camera width must be greater than zero."));
