@@ -51,6 +51,7 @@ typedef enum b2pt_status
 #define B2PT_FLAG_NO_OVERLAP 0x40u          /* run the sample batches one after the other on the context's stream */
 #define B2PT_FLAG_GPU_LBVH 0x80u            /* build the BVH on the device (Morton LBVH) instead of the host binned-SAH builder */
 #define B2PT_FLAG_VIEWS_NORMALIZE 0x100u     /* b2pt_render_views: apply b2pt_normalize's sqrt(de_nan(sum)/spp) to every view */
+#define B2PT_FLAG_VIEWS_PNM16 0x200u         /* b2pt_render_views: rgbaOut receives uint16_t[nViews*W*H*3], the integers of b2pt_read_pnm16 */
 #define B2PT_FLAG_NO_AA 0x10u               /* do not use the axis-aligned quad specialisation (A/B parity checks) */
 
 typedef struct b2pt_stats
@@ -122,10 +123,11 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
  * (view, sample, pixel) is one flat path index space and many views share each launch, so small canvases (the
  * reference's 128 x 128 x 10 spp default) fill the GPU; larger views are rendered one after the other.  The sums land
  * in a library-owned device array [nViews][W*H] of float4 (b2pt_views_device_ptr) and, when rgbaOut is not NULL, are
- * copied to the host array rgbaOut[nViews*W*H*4] (the call then synchronises).  The context's own camera and canvas
+ * copied to the host array rgbaOut = float[nViews*W*H*4] (the call then synchronises); with B2PT_FLAG_VIEWS_PNM16
+ * rgbaOut is uint16_t[nViews*W*H*3] instead (see b2pt_read_pnm16).  The context's own camera and canvas
  * are left untouched.  B2PT_FLAG_REFERENCE_STREAM is rejected (B2PT_ERR_BAD_VALUE). */
 int b2pt_render_views(b2pt_ctx* ctx, int nViews, const float* views, int W, int H, int spp, int maxDepth,
-                      uint32_t flags, float* rgbaOut);
+                      uint32_t flags, void* rgbaOut);
 void* b2pt_views_device_ptr(b2pt_ctx* ctx);
 int b2pt_clear_color(b2pt_ctx* ctx);
 /* Attach a caller-owned device buffer of W*H float4 as the radiance sum (NULL detaches). */
@@ -137,6 +139,11 @@ int b2pt_read_color(b2pt_ctx* ctx, float* rgba);
 int b2pt_write_color(b2pt_ctx* ctx, const float* rgba);
 /* Replaces NormalizeFunctor (main.cc:253-287): in-place sqrt(de_nan(sum)/spp) on the device buffer. */
 int b2pt_normalize(b2pt_ctx* ctx, int spp);
+/* Replaces NormalizeFunctor + the per-pixel arithmetic of save() (main.cc:253-287, 325-384) without touching the
+ * canvas: rgb[3*i+k] = int(255.99 * sqrt(de_nan(sum[i][k]) / spp)), the integers the reference prints into its P3
+ * file (Float64 product, truncated; not clamped to 255 -- the light prints 991 -- but saturating at 65535).
+ * 6 B per pixel cross PCIe instead of 16.  Synchronises the stream. */
+int b2pt_read_pnm16(b2pt_ctx* ctx, int spp, uint16_t* rgb);
 int b2pt_synchronize(b2pt_ctx* ctx);
 int b2pt_get_stats(b2pt_ctx* ctx, b2pt_stats* out);
 /* Per-launch CUDA-event durations (ms, on the context's stream) and input ray counts of the first bounce

@@ -26,6 +26,7 @@ FLAG_NO_TAIL = 0x20
 FLAG_NO_OVERLAP = 0x40
 FLAG_GPU_LBVH = 0x80
 FLAG_VIEWS_NORMALIZE = 0x100
+FLAG_VIEWS_PNM16 = 0x200
 
 ERR_BAD_VALUE, ERR_CUDA, ERR_STATE, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 
@@ -69,6 +70,7 @@ SIGNATURES = {
     "b2pt_read_color": (_i32, [_vp, _vp]),
     "b2pt_write_color": (_i32, [_vp, _vp]),
     "b2pt_normalize": (_i32, [_vp, _i32]),
+    "b2pt_read_pnm16": (_i32, [_vp, _i32, _vp]),
     "b2pt_synchronize": (_i32, [_vp]),
     "b2pt_get_stats": (_i32, [_vp, C.POINTER(Stats)]),
     "b2pt_build_bvh_ex": (_i32, [_vp, C.c_uint32]),
@@ -234,9 +236,11 @@ class Context:
         """b2pt_render_views: `views` is [nViews, 10] float32 (pos, lookAt, up, fovDeg); returns the [nViews, H*W, 4]
         radiance sums (un-normalised unless FLAG_VIEWS_NORMALIZE), each bit-identical to set_camera + render."""
         v = np.ascontiguousarray(views, np.float32).reshape(-1, 10)
+        pnm = bool(flags & FLAG_VIEWS_PNM16)  # uint16 [nViews, H*W, 3]: the integers of the reference's P3 writer
+        dt, ch = (np.uint16, 3) if pnm else (np.float32, 4)
         if out is None:
-            out = np.empty((v.shape[0], W * H, 4), np.float32)
-        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == v.shape[0] * W * H * 4
+            out = np.empty((v.shape[0], W * H, ch), dt)
+        assert out.dtype == dt and out.flags.c_contiguous and out.size == v.shape[0] * W * H * ch
         _check(lib().b2pt_render_views(self._h, v.shape[0], _p(v), W, H, spp, max_depth, flags, _p(out)))
         return out
 
@@ -262,6 +266,12 @@ class Context:
     def write_color(self, rgba):
         rgba = np.ascontiguousarray(rgba, np.float32)
         _check(lib().b2pt_write_color(self._h, _p(rgba)))
+
+    def read_pnm16(self, spp):
+        """uint16 [H*W, 3]: int(255.99 * sqrt(de_nan(sum)/spp)), what the reference's save() prints (main.cc:325-384)."""
+        out = np.zeros((self.W * self.H, 3), np.uint16)
+        _check(lib().b2pt_read_pnm16(self._h, spp, _p(out)))
+        return out
 
     def normalize(self, spp):
         _check(lib().b2pt_normalize(self._h, spp))

@@ -152,6 +152,7 @@ struct b2pt_ctx
   // view-batched render (b2pt_render_views): camera bases and the [nViews][W*H] radiance sums
   DevBuf<B2Camera> dViews;
   DevBuf<float4> viewColor;
+  DevBuf<uint16_t> pnm; // packed PNM integers (b2pt_read_pnm16, B2PT_FLAG_VIEWS_PNM16)
   int64_t viewCount = 0, viewPixels = 0;
 
   // tail-mode depths chosen by the last render with the same scene / canvas / depth / batch shape (reused without
@@ -1367,7 +1368,7 @@ int b2pt_render_range(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxDe
 }
 
 int b2pt_render_views(b2pt_ctx* ctx, int nViews, const float* views, int W, int H, int spp, int maxDepth,
-                      uint32_t flags, float* rgbaOut)
+                      uint32_t flags, void* rgbaOut)
 {
   if (int rc = bind(ctx))
     return rc;
@@ -1438,6 +1439,20 @@ int b2pt_render_views(b2pt_ctx* ctx, int nViews, const float* views, int W, int 
   restore();
   if (rc != B2PT_OK)
     return rc;
+  if (flags & B2PT_FLAG_VIEWS_PNM16)
+  { // the integers of the reference's P3 writer instead of the float sums: 6 B instead of 16 B per pixel to the host
+    if (spp <= 0)
+      return fail(B2PT_ERR_BAD_VALUE, "spp must be positive");
+    CU(ctx->pnm.reserve((size_t)(N * nViews) * 3));
+    CU(b2pt::launch_pnm16(ctx->viewColor.p, N * nViews, spp, ctx->pnm.p, ctx->stream));
+    if (rgbaOut)
+    {
+      CU(cudaMemcpyAsync(rgbaOut, ctx->pnm.p, sizeof(uint16_t) * 3 * (size_t)(N * nViews), cudaMemcpyDeviceToHost,
+                         ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return B2PT_OK;
+  }
   if (flags & B2PT_FLAG_VIEWS_NORMALIZE)
     CU(b2pt::launch_normalize(ctx->viewColor.p, N * nViews, spp, ctx->stream));
   if (rgbaOut)
@@ -1587,6 +1602,26 @@ int b2pt_normalize(b2pt_ctx* ctx, int spp)
   if (int rc = ensure_color(ctx))
     return rc;
   CU(b2pt::launch_normalize(ctx->color(), (int64_t)ctx->cam.W * ctx->cam.H, spp, ctx->stream));
+  return B2PT_OK;
+}
+
+int b2pt_read_pnm16(b2pt_ctx* ctx, int spp, uint16_t* rgb)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (spp <= 0)
+    return fail(B2PT_ERR_BAD_VALUE, "spp must be positive");
+  if (!rgb)
+    return fail(B2PT_ERR_BAD_VALUE, "null output");
+  if (!ctx->haveCamera)
+    return fail(B2PT_ERR_STATE, "b2pt_read_pnm16 before b2pt_set_camera");
+  if (int rc = ensure_color(ctx))
+    return rc;
+  const int64_t N = (int64_t)ctx->cam.W * ctx->cam.H;
+  CU(ctx->pnm.reserve((size_t)N * 3));
+  CU(b2pt::launch_pnm16(ctx->color(), N, spp, ctx->pnm.p, ctx->stream));
+  CU(cudaMemcpyAsync(rgb, ctx->pnm.p, sizeof(uint16_t) * 3 * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return B2PT_OK;
 }
 

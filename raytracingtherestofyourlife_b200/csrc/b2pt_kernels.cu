@@ -14,7 +14,7 @@
 //   k_accumulate                  per pixel: sum the batch's samples in registers (sample order) and do a
 //                                 single read-modify-write of the canvas float4.
 //   k_primary_hits                parity hook: production raygen + trace, writes hit primitive id / t.
-//   k_create_rays, k_intersect, k_normalize, k_fill_seeds, k_sum_peers: stage-level API kernels.
+//   k_create_rays, k_intersect, k_normalize, k_pnm16, k_fill_seeds, k_sum_peers: stage-level API kernels.
 //
 // Work distribution: queue and bins are statically partitioned into one region per persistent warp
 // (numSMs x occupancy x 8 regions); a warp consumes and refills only its own region with register counters
@@ -796,6 +796,26 @@ __global__ void __launch_bounds__(256) k_normalize(float4* color, long long n, f
   color[i] = make_float4(sqrtf(c.x / spp), sqrtf(c.y / spp), sqrtf(c.z / spp), sqrtf(c.w / spp));
 }
 
+// main.cc:325-384 save(): the three integers the reference prints per pixel of a P3 file, int(255.99 * col[k]) with
+// col = NormalizeFunctor(sum) (de_nan, /spp, sqrt); the product is Float64 as in the reference (255.99 is a double
+// literal), truncated toward zero; values past 65535 (radiance sums beyond 6.5e4 x spp) saturate.
+__global__ void __launch_bounds__(256)
+  k_pnm16(const float4* __restrict__ color, long long n, float spp, uint16_t* __restrict__ rgb)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const float4 c = color[i];
+  const float v[3] = { c.x, c.y, c.z };
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    const float x = (v[k] == v[k]) ? v[k] : 0.f;
+    const double p = 255.99 * (double)sqrtf(x / spp);
+    rgb[3 * i + k] = (uint16_t)(p >= 65535.0 ? 65535 : __double2int_rz(p));
+  }
+}
+
 __global__ void __launch_bounds__(256) k_fill_seeds(uint32_t* seeds, int n, uint32_t seedOffset)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -949,6 +969,14 @@ cudaError_t launch_normalize(float4* color, int64_t n, int spp, cudaStream_t str
   if (n <= 0)
     return cudaSuccess;
   k_normalize<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(color, n, (float)spp);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pnm16(const float4* color, int64_t n, int spp, uint16_t* rgb, cudaStream_t stream)
+{
+  if (n <= 0)
+    return cudaSuccess;
+  k_pnm16<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(color, n, (float)spp, rgb);
   return cudaGetLastError();
 }
 

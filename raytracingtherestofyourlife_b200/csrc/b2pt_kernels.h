@@ -50,6 +50,7 @@ cudaError_t launch_intersect(const B2SmallScene* small, const B2BvhScene* bvh, i
                              float tmin, float tmax, int32_t* primId, float* hrec9, int32_t* matId, int32_t* texId,
                              cudaStream_t stream);
 cudaError_t launch_normalize(float4* color, int64_t n, int spp, cudaStream_t stream);
+cudaError_t launch_pnm16(const float4* color, int64_t n, int spp, uint16_t* rgb, cudaStream_t stream);
 cudaError_t launch_fill_seeds(uint32_t* seeds, int n, uint32_t seedOffset, cudaStream_t stream);
 // dst[i-begin] = sum_g srcs[g][i] over [begin,end) float4 elements; srcs may be peer-device pointers.
 cudaError_t launch_sum_peers(float4* dst, const float4* const* srcs, int G, int64_t begin, int64_t end,

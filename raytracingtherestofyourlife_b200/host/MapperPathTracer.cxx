@@ -245,10 +245,10 @@ void MapperPathTracer::RenderCells(const vtkm::cont::DynamicCellSet& cellset, co
   RenderCellsImpl(cellset, coords, scalarField, camera);
 }
 
-void MapperPathTracer::RenderCellsViews(const vtkm::cont::DynamicCellSet& cellset,
-                                        const vtkm::cont::CoordinateSystem& coords,
-                                        const std::vector<vtkm::rendering::Camera>& cameras,
-                                        std::vector<vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Float32, 4>>>& colors)
+void MapperPathTracer::RenderViewsImpl(const vtkm::cont::DynamicCellSet& cellset,
+                                       const vtkm::cont::CoordinateSystem& coords,
+                                       const std::vector<vtkm::rendering::Camera>& cameras, unsigned int flags,
+                                       void* out)
 {
   if (Internals->Canvas == nullptr)
     throw vtkm::cont::ErrorBadValue("MapperPathTracer: no canvas set");
@@ -276,20 +276,43 @@ void MapperPathTracer::RenderCellsViews(const vtkm::cont::DynamicCellSet& cellse
   }
   b2pt_ctx* ctx = b2pt_facade::Context();
   b2pt_facade::Check(b2pt_seed(ctx, 0)); // seeds[i] = i, MapperPathTracer.cxx:265-267
-  std::vector<float> rgba(cameras.size() * static_cast<size_t>(nx * ny) * 4);
   b2pt_facade::Check(b2pt_render_views(ctx, static_cast<int>(cameras.size()), views.data(), static_cast<int>(nx),
-                                       static_cast<int>(ny), samplecount, depthcount, RenderFlags, rgba.data()));
-  colors.resize(cameras.size());
-  for (size_t v = 0; v < cameras.size(); ++v)
-  {
-    colors[v].Allocate(nx * ny);
-    std::memcpy(colors[v].GetStorage(), &rgba[v * static_cast<size_t>(nx * ny) * 4],
-                sizeof(float) * 4 * static_cast<size_t>(nx * ny));
-  }
+                                       static_cast<int>(ny), samplecount, depthcount, RenderFlags | flags, out));
   b2pt_stats st;
   b2pt_facade::Check(b2pt_get_stats(ctx, &st));
   LastRenderMs = st.renderMs;
   LastSegments = st.segments;
+}
+
+void MapperPathTracer::RenderCellsViews(const vtkm::cont::DynamicCellSet& cellset,
+                                        const vtkm::cont::CoordinateSystem& coords,
+                                        const std::vector<vtkm::rendering::Camera>& cameras,
+                                        std::vector<vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Float32, 4>>>& colors)
+{
+  if (Internals->Canvas == nullptr)
+    throw vtkm::cont::ErrorBadValue("MapperPathTracer: no canvas set");
+  const size_t n = static_cast<size_t>(Internals->Canvas->GetWidth()) * Internals->Canvas->GetHeight();
+  std::vector<float> rgba(cameras.size() * n * 4);
+  RenderViewsImpl(cellset, coords, cameras, 0, rgba.data());
+  colors.resize(cameras.size());
+  for (size_t v = 0; v < cameras.size(); ++v)
+  {
+    colors[v].Allocate(static_cast<vtkm::Id>(n));
+    std::memcpy(colors[v].GetStorage(), &rgba[v * n * 4], sizeof(float) * 4 * n);
+  }
+}
+
+void MapperPathTracer::RenderCellsViewsPnm(const vtkm::cont::DynamicCellSet& cellset,
+                                           const vtkm::cont::CoordinateSystem& coords,
+                                           const std::vector<vtkm::rendering::Camera>& cameras,
+                                           std::vector<unsigned short>& pnm)
+{
+  if (Internals->Canvas == nullptr)
+    throw vtkm::cont::ErrorBadValue("MapperPathTracer: no canvas set");
+  static_assert(sizeof(unsigned short) == 2, "16-bit PNM integers");
+  const size_t n = static_cast<size_t>(Internals->Canvas->GetWidth()) * Internals->Canvas->GetHeight();
+  pnm.assign(cameras.size() * n * 3, 0);
+  RenderViewsImpl(cellset, coords, cameras, B2PT_FLAG_VIEWS_PNM16, pnm.data());
 }
 
 void MapperPathTracer::SetCompositeBackground(bool on) { Internals->CompositeBackground = on; }

@@ -98,6 +98,11 @@ public:
   void RenderCellsViews(const vtkm::cont::DynamicCellSet& cellset, const vtkm::cont::CoordinateSystem& coords,
                         const std::vector<vtkm::rendering::Camera>& cameras,
                         std::vector<vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Float32, 4>>>& colors);
+  // Same, returning for every view the integers main.cc's save() prints into the P3 file (:325-384) after
+  // NormalizeFunctor (:253-287): pnm[(v * W*H + i) * 3 + k] = int(255.99 * sqrt(de_nan(sum) / samplecount)).
+  // Packed on the GPU, 6 bytes per pixel cross PCIe instead of 16.
+  void RenderCellsViewsPnm(const vtkm::cont::DynamicCellSet& cellset, const vtkm::cont::CoordinateSystem& coords,
+                           const std::vector<vtkm::rendering::Camera>& cameras, std::vector<unsigned short>& pnm);
   double GetLastRenderMilliseconds() const { return LastRenderMs; }
   long long GetLastSegments() const { return LastSegments; }
 
@@ -113,6 +118,8 @@ public:
 private:
   struct InternalsType;
   std::shared_ptr<InternalsType> Internals;
+  void RenderViewsImpl(const vtkm::cont::DynamicCellSet& cellset, const vtkm::cont::CoordinateSystem& coords,
+                       const std::vector<vtkm::rendering::Camera>& cameras, unsigned int flags, void* out);
   void RenderCellsImpl(const vtkm::cont::DynamicCellSet& cellset, const vtkm::cont::CoordinateSystem& coords,
                        const vtkm::cont::Field& scalarField, const vtkm::rendering::Camera& camera);
   void UploadScene(const vtkm::cont::CoordinateSystem& coord, vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Id, 5>>& QuadIds,

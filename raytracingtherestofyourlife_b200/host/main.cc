@@ -123,6 +123,36 @@ void savePnm(const std::string& stem, int nx, int ny, const vtkm::cont::ArrayHan
   }
 }
 
+// The same file from the integers packed on the GPU (RenderCellsViewsPnm): "r g b\n" per pixel, formatted into one
+// buffer and written once.
+void savePnm16(const std::string& stem, int nx, int ny, const unsigned short* rgb)
+{
+  std::ofstream fs(stem + ".pnm", std::ios::binary);
+  if (!fs)
+  {
+    std::cout << "Couldn't save pnm." << std::endl;
+    return;
+  }
+  std::string buf = "P3\n" + std::to_string(nx) + " " + std::to_string(ny) + " 255\n";
+  const size_t n = static_cast<size_t>(nx) * ny;
+  buf.reserve(buf.size() + n * 18);
+  char tmp[8];
+  for (size_t i = 0; i < 3 * n; ++i)
+  {
+    unsigned v = rgb[i];
+    int len = 0;
+    do
+    {
+      tmp[len++] = static_cast<char>('0' + v % 10);
+      v /= 10;
+    } while (v);
+    while (len)
+      buf.push_back(tmp[--len]);
+    buf.push_back(i % 3 == 2 ? '\n' : ' ');
+  }
+  fs.write(buf.data(), static_cast<std::streamsize>(buf.size()));
+}
+
 // the reference's generateHemisphere (main.cc:504-561) for the path-traced output: view points on a sphere of
 // radius 1078/555 around the box centre, phi in [0,1) in phiCount steps, theta in [0,2pi) in thetaCount steps
 int generateHemisphere(CornellBox& cb, const Options& o)
@@ -158,18 +188,16 @@ int generateHemisphere(CornellBox& cb, const Options& o)
     }
   vtkm::rendering::MapperPathTracer mapper(o.samples, o.depth, cb.matIdx, cb.texIdx, cb.matType, cb.texType, cb.tex);
   mapper.SetCanvas(&canvas);
-  std::vector<vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Float32, 4>>> colors;
-  mapper.RenderCellsViews(cb.ds.GetCellSet(), cb.coord, cameras, colors);
+  // NormalizeFunctor and the integer conversion of save() (main.cc:253-287, 325-384) run on the GPU
+  std::vector<unsigned short> pnm;
+  mapper.RenderCellsViewsPnm(cb.ds.GetCellSet(), cb.coord, cameras, pnm);
   if (o.stats)
     std::cout << " GPU render ms = " << mapper.GetLastRenderMilliseconds() << " for " << cameras.size() << " views"
               << "  path samples/s = " << double(o.x) * o.y * o.samples * double(cameras.size()) /
         (mapper.GetLastRenderMilliseconds() * 1e-3)
               << "  segments = " << mapper.GetLastSegments() << std::endl;
   for (size_t v = 0; v < cameras.size(); ++v)
-  {
-    normalizeColors(colors[v], o.samples);
-    savePnm(names[v], o.x, o.y, colors[v]);
-  }
+    savePnm16(names[v], o.x, o.y, &pnm[v * static_cast<size_t>(o.x) * o.y * 3]);
   return static_cast<int>(cameras.size());
 }
 

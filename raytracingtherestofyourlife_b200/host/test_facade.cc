@@ -2,6 +2,7 @@
 //   test_facade --cpu            host-only behaviour (containers, validation, error messages); no GPU needed
 //   test_facade --gpu <prefix>   renders through MapperPathTracer / Camera::CreateRays / intersect on cuda:0 and
 //                                writes <prefix>_*.bin for tests/test_facade.py to compare with the oracle
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -261,6 +262,23 @@ static void testGpu(const std::string& prefix)
       CHECK(std::memcmp(colors[v].GetStorage(), canvas.GetColorBuffer().GetStorage(), sizeof(float) * 4 * W * H) == 0);
     }
     CHECK(std::memcmp(colors[0].GetStorage(), colors[1].GetStorage(), sizeof(float) * 4 * W * H) != 0);
+    // the packed integers equal save()'s arithmetic (main.cc:253-287, 325-384) applied to those sums
+    std::vector<unsigned short> pnm;
+    mapper.RenderCellsViewsPnm(cb.ds.GetCellSet(), cb.coord, cams, pnm);
+    CHECK(pnm.size() == size_t(3) * W * H * 3);
+    size_t bad = 0;
+    for (size_t v = 0; v < 3; ++v)
+      for (vtkm::Id i = 0; i < vtkm::Id(W) * H; ++i)
+      {
+        auto c = colors[v].ReadPortal().Get(i);
+        for (int k = 0; k < 3; ++k)
+        {
+          float x = (c[k] == c[k]) ? c[k] : 0.f;
+          x = std::sqrt(x / static_cast<float>(spp));
+          bad += (int(255.99 * x) != int(pnm[(v * size_t(W) * H + size_t(i)) * 3 + k])) ? 1 : 0;
+        }
+      }
+    CHECK(bad == 0);
   }
   // error mapping: invalid canvas size surfaces as ErrorBadValue with the reference's message
   vtkm::rendering::pathtracing::Camera bad;

@@ -1,6 +1,7 @@
 """Time the hemisphere sweep (the reference's dataset-generation use, main.cc:431-561) two ways on cuda:0:
   loop    one b2pt_set_camera + b2pt_render + b2pt_read_color per view (what a port of the reference's loop does)
   views   one b2pt_render_views call for the whole list (view-batched launches, one D2H)
+  pnm16   the same with B2PT_FLAG_VIEWS_PNM16 (the P3 writer's integers packed on the GPU, 6 B/pixel to the host)
 Prints one JSON line per canvas configuration.  Host wall clock around complete calls (results on the host)."""
 import json
 import math
@@ -50,9 +51,15 @@ def main():
             got = ctx.render_views(views, W, H, spp, depth, out=out)
             res["views"] = time.perf_counter() - t0
         st = ctx.stats()
+        out16 = np.empty((V, W * H, 3), np.uint16)
+        for rep in range(3):
+            t0 = time.perf_counter()
+            ctx.render_views(views, W, H, spp, depth, flags=B.FLAG_VIEWS_PNM16, out=out16)
+            res["pnm16"] = time.perf_counter() - t0
         same = bool(np.array_equal(got.view(np.uint32), loop_img.view(np.uint32)))
         print(json.dumps({"canvas": [W, H], "spp": spp, "depth": depth, "views": V,
                           "loop_views_per_s": V / res["loop"], "batched_views_per_s": V / res["views"],
+                          "batched_pnm16_views_per_s": V / res["pnm16"],
                           "loop_paths_per_s": V * W * H * spp / res["loop"],
                           "batched_paths_per_s": V * W * H * spp / res["views"],
                           "speedup": res["loop"] / res["views"], "bit_identical": same,

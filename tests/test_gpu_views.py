@@ -121,3 +121,46 @@ def test_views_errors(gpu_ctx, b2pt):
         gpu_ctx.render_views(bad, 32, 32, 2, 3)
     with pytest.raises(b2pt.B2ptError):
         gpu_ctx.render_views(views, 0, 32, 2, 3)
+
+
+def pnm_integers(rgba_sum, spp, oracle):
+    """numpy restatement of save() (main.cc:325-384) after NormalizeFunctor (:253-287, through the C oracle)."""
+    n = oracle.normalize(np.ascontiguousarray(rgba_sum, np.float32), spp)[:, :3].astype(np.float64)
+    with np.errstate(invalid="ignore", over="ignore"):
+        p = 255.99 * n
+    return np.where(p >= 65535.0, 65535, np.trunc(np.minimum(p, 65535.0))).astype(np.uint16)
+
+
+def test_read_pnm16_matches_reference_writer_arithmetic(gpu_ctx, b2pt, oracle):
+    W, H, spp = 64, 32, 7
+    gpu_ctx.set_camera(b2pt.Camera(W, H))
+    gpu_ctx.render(spp, 6)
+    sums = gpu_ctx.read_color().copy()
+    got = gpu_ctx.read_pnm16(spp)
+    assert got.shape == (W * H, 3) and np.array_equal(got, pnm_integers(sums, spp, oracle))
+    assert got.max() > 255  # the light is not clamped (the reference prints 991 there)
+    assert same_bits(gpu_ctx.read_color(), sums)  # the canvas is left un-normalised
+    # corner cases of the arithmetic: NaN channels, zeros, exact integer boundaries, huge and infinite sums
+    rng = np.random.default_rng(5)
+    c = (rng.random((W * H, 4)) * 3 * spp).astype(np.float32)
+    c[0] = [np.nan, 1.0, 2.0, 0.0]
+    c[1] = [0.0, -0.0, np.nan, 0.0]
+    c[2] = [spp, spp * 4.0, spp * 15.0, 0.0]
+    c[3] = [np.inf, 1e30, spp * 65535.0, 0.0]
+    c[4] = [spp * (1.0 / 255.99) ** 2, spp * (2.0 / 255.99) ** 2, spp * (255.0 / 255.99) ** 2, 0.0]
+    gpu_ctx.write_color(c)
+    got = gpu_ctx.read_pnm16(spp)
+    assert np.array_equal(got, pnm_integers(c, spp, oracle))
+    assert list(got[0]) == [0, 96, 136] and list(got[3][:2]) == [65535, 65535]
+    with pytest.raises(b2pt.B2ptError):
+        gpu_ctx.read_pnm16(0)
+
+
+def test_views_pnm16_output(gpu_ctx, b2pt, oracle):
+    W, H, spp, depth = 48, 40, 5, 6
+    views = hemisphere_views(2, 2)
+    sums = gpu_ctx.render_views(views, W, H, spp, depth)
+    got = gpu_ctx.render_views(views, W, H, spp, depth, flags=b2pt.FLAG_VIEWS_PNM16)
+    assert got.dtype == np.uint16 and got.shape == (4, W * H, 3)
+    for k in range(4):
+        assert np.array_equal(got[k], pnm_integers(sums[k], spp, oracle))
