@@ -31,6 +31,20 @@ sys.path.insert(0, ROOT)
 
 METRIC = "cornell_1024_path_samples_per_s"
 UNIT = "path samples/s"
+
+
+def metric_name(size):
+    return METRIC if size == 1024 else "cornell_%d_path_samples_per_s" % size
+
+
+def config_label(size, spp_per_gpu, world, depth):
+    """Which BASELINE.json configuration the run is (configs[1] = the bench workload, configs[2] = its multi-GPU
+    4096x4096 x 4096 spp form); anything else is labelled as a variation."""
+    if size == 1024 and spp_per_gpu == 1024 and depth == 50:
+        return "BASELINE.json configs[1]" + ("" if world == 1 else " per GPU, weak scaling")
+    if size == 4096 and spp_per_gpu * world == 4096 and depth == 50 and world > 1:
+        return "BASELINE.json configs[2]"
+    return "a variation of BASELINE.json configs[1]"
 ALGO_BYTES_PER_SEGMENT = 88  # SURVEY.md 8d: 44 B ray record read + 44 B written per live segment
 
 
@@ -153,11 +167,12 @@ def run_reference(args):
     sample = "%dx%d, depth %d, %d spp per step (cost is exactly linear in spp; full workload is %d spp)" % (
         args.size, args.size, args.depth, args.ref_spp, args.spp)
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args.size), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Cornell box %dx%d, %d spp, max depth %d (BASELINE.json configs[1])" % (
-            args.size, args.size, args.spp, args.depth), "reference_arm": desc},
+        "config": {"workload": "Cornell box %dx%d, %d spp, max depth %d (%s)" % (
+            args.size, args.size, args.spp, args.depth, config_label(args.size, args.spp, 1, args.depth)),
+                   "reference_arm": desc},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -323,11 +338,11 @@ def main():
         step_gbs = segments_per_step * args.steps * ALGO_BYTES_PER_SEGMENT / (ms * 1e-3) / 1e9 / world
         traffic = ncu_traffic()
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(args.size), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Cornell box %dx%d, %d spp per GPU (%d total), max depth %d "
-                                   "(BASELINE.json configs[1])" % (W, H, args.spp, total_spp, args.depth),
+            "config": {"workload": "Cornell box %dx%d, %d spp per GPU (%d total), max depth %d (%s)" % (
+                W, H, args.spp, total_spp, args.depth, config_label(args.size, args.spp, world, args.depth)),
                        "parallelism": "samples sharded across %d GPU(s), one NCCL all-reduce of %d B" % (world, N * 16),
                        "l2": "working set of the batches in flight (ray queue + hit bins + radiance, 272 B per path, "
                              "%.1f GB per batch) exceeds the 126 MB L2" % (st.samplesPerBatch * N * 272 / 1e9),

@@ -81,20 +81,27 @@ for key, (e, t, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
 # ---- optional: attribute to the innermost NON-helper function (helpers = vector math lines < 100)
 if "--func" in sys.argv:
     import bisect
-    src = open(os.path.join(os.path.dirname(cubin), "..", "..", "raytracingtherestofyourlife_b200", "csrc",
-                            "b2pt_device.cuh")).read().splitlines() if False else None
-    funcs = [(105, "raygen"), (127, "quad_hit"), (167, "quad_accept/normal"), (186, "sphere_accept"), (213, "slab_hit/rcp_safe"),
-             (225, "Hit"), (237, "aa_quad_hit"), (265, "aa_permute"), (283, "trace_small"), (384, "trace_bvh"),
-             (520, "onb_from_w"), (536, "random_cosine/to_sphere"), (557, "quad_pdf_value"), (578, "sphere_pdf_value"),
-             (595, "dielectric"), (640, "bounce")]
+    # function table of b2pt_device.cuh built from its own text: every line that starts a __device__ definition
+    hdr_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "raytracingtherestofyourlife_b200", "csrc",
+                            "b2pt_device.cuh")
+    funcs = [(1, "header-top")]
+    for n, line in enumerate(open(hdr_path).read().splitlines(), 1):
+        m = re.match(r"^__device__[^(]*?(\w+)\(", line)
+        if m:
+            funcs.append((n, m.group(1)))
+    helpers = {"dot3", "cross3", "mk3", "ld3", "operator", "rcp_fast", "pk2", "upk2", "fma2", "add2", "sub2", "rcp_safe",
+               "normalize3", "length3", "mul3", "rmag3", "unit3", "denan3"}
     starts = [f[0] for f in funcs]
     agg2 = collections.defaultdict(lambda: [0, 0])
     for k, r in enumerate(data):
         chain = chains[k] if k < len(chains) else []
         name = "kernel/other"
         for loc in chain:
-            if loc[0] == "b2pt_device.cuh" and loc[1] >= 100:
-                name = funcs[bisect.bisect_right(starts, loc[1]) - 1][1]
+            if loc[0] == "b2pt_device.cuh":
+                cand = funcs[bisect.bisect_right(starts, loc[1]) - 1][1]
+                if cand in helpers or cand.startswith("operator"):
+                    continue
+                name = cand
                 break
         agg2[name][0] += int(r[iE])
         agg2[name][1] += int(r[iT])

@@ -18,7 +18,7 @@ def test_reference_arm_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "path samples/s" and d["higher_is_better"] is True
-    assert d["metric"] == "cornell_1024_path_samples_per_s" and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["metric"] == "cornell_64_path_samples_per_s" and d["value"] > 0 and d["gpu_launches"] == 0
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
