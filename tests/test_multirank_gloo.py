@@ -55,6 +55,62 @@ def test_two_rank_sharded_render_equals_single_rank(tmp_path, oracle, spp):
     assert np.allclose(r0[ok], single[ok], rtol=1e-5, atol=1e-6)
 
 
+def _views_worker(rank, world, port, n_views, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    from raytracingtherestofyourlife_b200.sharding import render_views_sharded, gather_views
+    sc = O.cornell_scene()
+    views = _test_views(n_views)
+
+    def render_views(block):  # stands in for Context.render_views (one image stack per view block)
+        imgs = [O.render(sc, O.Camera(24, 16, pos=v[0:3], lookAt=v[3:6], up=tuple(v[6:9]), fov=float(v[9])), 3, 4,
+                         mode=O.MODE_FORWARD_FAST, threads=2)[0] for v in block]
+        return torch.from_numpy(np.stack(imgs)) if imgs else torch.zeros((0, 24 * 16, 4))
+
+    begin, mine = render_views_sharded(render_views, views, rank, world)
+
+    def all_gather(block):
+        parts = [torch.empty_like(block) for _ in range(world)]
+        dist.all_gather(parts, block)
+        return parts
+
+    full = gather_views(all_gather, mine, n_views, rank, world)
+    np.save(os.path.join(out_dir, "views_rank%d.npy" % rank), full.numpy())
+    np.save(os.path.join(out_dir, "begin_rank%d.npy" % rank), np.array([begin, mine.shape[0]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _test_views(n):
+    c = np.array([278 / 555.0] * 3, np.float32)
+    out = []
+    for k in range(n):
+        pos = c + np.array([0.3 * (k - n / 2.0), 0.1 * k, -1078 / 555.0], np.float32)
+        out.append(np.concatenate([pos, c, [0, 1, 0], [40.0 + k]]).astype(np.float32))
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("n_views", [5, 1])
+def test_two_rank_view_sharding(tmp_path, oracle, n_views):
+    """Views are independent renders: each rank renders a contiguous block of the list (no collective on the data
+    path); the optional gather returns the whole stack, in view order, bit-identical to rendering them on one rank."""
+    world = 2
+    mp.spawn(_views_worker, args=(world, _free_port(), n_views, str(tmp_path)), nprocs=world, join=True)
+    full0, full1 = np.load(tmp_path / "views_rank0.npy"), np.load(tmp_path / "views_rank1.npy")
+    assert full0.shape == (n_views, 24 * 16, 4)
+    assert np.array_equal(full0.view(np.uint32), full1.view(np.uint32))
+    b0, b1 = np.load(tmp_path / "begin_rank0.npy"), np.load(tmp_path / "begin_rank1.npy")
+    assert b0[0] == 0 and b1[0] == b0[1] and b0[1] + b1[1] == n_views
+    sc = oracle.cornell_scene()
+    for k, v in enumerate(_test_views(n_views)):
+        ref, _ = oracle.render(sc, oracle.Camera(24, 16, pos=v[0:3], lookAt=v[3:6], up=tuple(v[6:9]), fov=float(v[9])),
+                               3, 4, mode=oracle.MODE_FORWARD_FAST)
+        assert np.array_equal(full0[k].view(np.uint32), ref.view(np.uint32)), k
+
+
 def test_shard_samples_partition():
     from raytracingtherestofyourlife_b200.sharding import shard_samples
     for spp in (0, 1, 7, 8, 1024, 4096):
