@@ -1378,6 +1378,8 @@ int b2pt_render_views(b2pt_ctx* ctx, int nViews, const float* views, int W, int 
     return fail(B2PT_ERR_BAD_VALUE, "negative sample range");
   if (flags & B2PT_FLAG_REFERENCE_STREAM)
     return fail(B2PT_ERR_BAD_VALUE, "REFERENCE_STREAM cannot be combined with a view-batched render");
+  if ((flags & B2PT_FLAG_VIEWS_PNM16) && spp <= 0)
+    return fail(B2PT_ERR_BAD_VALUE, "spp must be positive"); // the PNM integers divide by spp
   std::vector<B2Camera> cams((size_t)nViews);
   for (int v = 0; v < nViews; ++v)
   {
@@ -1441,8 +1443,6 @@ int b2pt_render_views(b2pt_ctx* ctx, int nViews, const float* views, int W, int 
     return rc;
   if (flags & B2PT_FLAG_VIEWS_PNM16)
   { // the integers of the reference's P3 writer instead of the float sums: 6 B instead of 16 B per pixel to the host
-    if (spp <= 0)
-      return fail(B2PT_ERR_BAD_VALUE, "spp must be positive");
     CU(ctx->pnm.reserve((size_t)(N * nViews) * 3));
     CU(b2pt::launch_pnm16(ctx->viewColor.p, N * nViews, spp, ctx->pnm.p, ctx->stream));
     if (rgbaOut)
