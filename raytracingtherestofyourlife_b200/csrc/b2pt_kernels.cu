@@ -101,6 +101,13 @@ __device__ __forceinline__ const B2Lights& stage_lights(const B2Lights& lights, 
   return a.lights;
 }
 
+// Global tile (32 consecutive path ids) that warp w generates in round j of a PRIMARY launch: slot (w + j) mod numWarps
+// of round j.  For a fixed round the slots of the warps are a permutation, so every tile is generated exactly once.
+__device__ __forceinline__ int64_t primary_tile(int64_t j, int w, int numWarps)
+{
+  return j * numWarps + (int64_t)(((int64_t)w + j) % numWarps);
+}
+
 // Ray `idx` of the warp's region.  PRIMARY: generated from (pixel, sample) -- idx is the path id.
 template <bool PRIMARY>
 __device__ __forceinline__ void load_ray(const B2Camera& cam, const B2RenderArgs& A, int64_t idx, f3& o, f3& d, f3& T,
@@ -222,7 +229,8 @@ __device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhS
       const int64_t r = next + __popc(need & lt);
       if (!has && r < nLocal)
       {
-        const int64_t idx = (PRIMARY || TAIL) ? ((((r >> 5) * stride + w) << 5) + (r & 31)) : base + r;
+        const int64_t idx = PRIMARY ? (primary_tile(r >> 5, w, A.numWarps) << 5) + (r & 31)
+                                    : (TAIL ? ((((r >> 5) * stride + w) << 5) + (r & 31)) : base + r);
         if (PRIMARY ? idx < A.nPaths : (TAIL ? idx < nIn : true))
         {
           load_ray<PRIMARY>(cam, A, idx, o, d, T, pid, rng);
@@ -414,6 +422,7 @@ __device__ __forceinline__ void trace_body(const B2Camera& cam, const SceneT& S,
   const int64_t base = TAIL ? 0 : (int64_t)w * A.regionCap;
   const bool refStream = (A.flags & B2PT_FLAG_REFERENCE_STREAM_DEV) != 0;
   uint32_t cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
+  int slot = w; // PRIMARY: this warp's tile slot within the current round (primary_tile)
   for (int64_t i0 = TAIL ? (int64_t)w * 32 : 0; i0 < nIn; i0 += TAIL ? tailWarps * 32 : 32)
   {
     const int64_t i = i0 + lane;
@@ -422,7 +431,9 @@ __device__ __forceinline__ void trace_body(const B2Camera& cam, const SceneT& S,
     uint32_t pid = 0, rng = 0;
     float t = 0.f;
     int code = B2PT_MISS;
-    const int64_t idx = PRIMARY ? (((i0 >> 5) * A.numWarps + w) << 5) + lane : base + i;
+    const int64_t idx = PRIMARY ? (((i0 >> 5) * A.numWarps + slot) << 5) + lane : base + i;
+    if (PRIMARY)
+      slot = slot + 1 == A.numWarps ? 0 : slot + 1;
     if (!PRIMARY && !TAIL && i + 32 < nIn)
     {
       prefetch_l2(A.q.p0 + idx + 32);
@@ -500,9 +511,11 @@ __global__ void __launch_bounds__(kBlock, kTraceMinBlocksPerSM)
   static_assert(!(PRIMARY && TAIL), "primary rays are never traced in tail mode");
   const int w = blockIdx.x * kWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  // PRIMARY: the batch's 32-path tiles are dealt round-robin to the warps (tile j of warp w is global tile
-  // j*numWarps + w), so every region samples the whole image and the regions shrink at the same rate;
-  // contiguous pixel ranges would leave the regions that cover the image border (rays that miss) empty.
+  // PRIMARY: the batch's 32-path tiles are dealt round by round to the warps, skewed by one slot per round
+  // (primary_tile), so every region samples the whole image and the regions shrink at the same rate; contiguous
+  // pixel ranges would leave the regions that cover the image border (rays that miss) empty, and so would a plain
+  // round-robin whenever numWarps and the tiles per image row share a factor (4736 warps, 32 tiles per 1024-pixel row:
+  // warp w would only ever see column strip w % 32).
   const int64_t tilesTotal = (A.nPaths + 31) >> 5;
   const int64_t tailWarps = (int64_t)gridDim.x * kWarps;
   int64_t nIn;
@@ -515,7 +528,7 @@ __global__ void __launch_bounds__(kBlock, kTraceMinBlocksPerSM)
       return; // no tile for any warp of this CTA
   }
   else if (PRIMARY)
-    nIn = w < A.numWarps && tilesTotal > w ? ((tilesTotal - 1 - w) / A.numWarps + 1) * 32 : 0;
+    nIn = w < A.numWarps ? ((tilesTotal + A.numWarps - 1) / A.numWarps) * 32 : 0; // rounds; the last may be partial
   else
     nIn = w < A.numWarps ? (int64_t)A.qCount[w] : 0;
   // CTAs whose eight regions are all empty (deep bounces) leave before staging the scene.
