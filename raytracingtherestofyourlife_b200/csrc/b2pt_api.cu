@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <limits>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -206,6 +207,16 @@ void precompute_quad(B2Quad& Q, H3 q, H3 r, H3 s, H3 t)
   hst(Q.e21, hsub(r, s));
   hst(Q.e23, hsub(t, s));
   hst(Q.nrm, hnormalize(hcross(hsub(r, q), hsub(s, q)))); // vtkm::TriangleNormal(q,r,s), Normalize
+  // second-triangle shortcut constants (b2pt_types.h): parallelogram iff q + E01 + E03 reproduces s to 1e-6 of the
+  // quad's size
+  const double l01 = std::fabs((double)Q.e01[0]) + std::fabs((double)Q.e01[1]) + std::fabs((double)Q.e01[2]);
+  const double l03 = std::fabs((double)Q.e03[0]) + std::fabs((double)Q.e03[1]) + std::fabs((double)Q.e03[2]);
+  double defect = 0.0;
+  for (int c = 0; c < 3; ++c)
+    defect = std::fmax(defect, std::fabs((double)Q.v00[c] + (double)Q.e01[c] + (double)Q.e03[c] - (double)Q.v11[c]));
+  const bool para = std::isfinite(l01 + l03) && l01 > 0 && l03 > 0 && defect <= 1e-6 * (l01 + l03);
+  Q.secC1 = (float)(2.0 * (l01 + l03));
+  Q.secC2 = para ? (float)(1e-5 * l03) * 1.0000002f : std::numeric_limits<float>::infinity();
 }
 
 // pathtracing/AABBSurface.h:24-78 (FindQuadAABBs): min/max over the four vertices, padded per axis.
@@ -474,7 +485,7 @@ int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t*
     B2Quad& Q = quads[(size_t)q];
     precompute_quad(Q, P(id[1]), P(id[2]), P(id[3]), P(id[4]));
     Q.gate = 0;
-    Q.pad[0] = Q.pad[1] = Q.pad[2] = 0;
+    Q.pad[0] = 0;
     B2GateBox G;
     quad_leaf_box(G, P(id[1]), P(id[2]), P(id[3]), P(id[4]));
     G.quad = (int32_t)q;

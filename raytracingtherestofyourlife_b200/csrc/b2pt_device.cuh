@@ -145,6 +145,13 @@ __device__ __forceinline__ bool quad_hit(const B2Quad& Q, f3 o, f3 d, float& t)
     return false;
   if ((alpha + beta) > 1.0f)
   {
+    // Shortcut (never changes the outcome, B2Quad::secC1): on a parallelogram alpha' = 1 - alpha, beta' = 1 - beta and
+    // det' = det, so while alpha and beta stay below 1 by more than the rounding error of both evaluations the
+    // second triangle's reject tests cannot fire and t below is all that is left.  Near an edge, for |det| close to
+    // the epsilon, for NaNs and for general quads the reference's second-triangle arithmetic runs as written.
+    const float need = ((fabsf(T.x) + fabsf(T.y)) + fabsf(T.z) + Q.secC1) * ((fabsf(d.x) + fabsf(d.y)) + fabsf(d.z)) * Q.secC2;
+    if (!((1.0f - fmaxf(alpha, beta)) * fabsf(det) > need && fabsf(det) >= 2e-5f))
+    {
     const float4 c3 = q4[3], c4 = q4[4]; // v11 e21 | e21 e23 nrm
     const f3 E23 = mk3(c3.w, c4.x, c4.y);
     const f3 E21 = mk3(c3.x, c3.y, c3.z);
@@ -161,6 +168,7 @@ __device__ __forceinline__ bool quad_hit(const B2Quad& Q, f3 o, f3 d, float& t)
     float betap = dot3(d, Qp) * inv_detp;
     if (betap < 0.0f)
       return false;
+    }
   }
   t = dot3(E03, Qv) * inv_det;
   if (t < 0.0f)

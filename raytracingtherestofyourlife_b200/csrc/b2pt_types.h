@@ -38,7 +38,12 @@ struct alignas(16) B2Quad // 32 words = 128 B, 16-byte aligned
   int32_t mat;  // matIdx (HitId M)
   int32_t texi; // texIdx (HitId T)
   int32_t gate; // 0: planar quad, no leaf-box gate needed; k>0: must pass slab test of gate box k-1 first
-  int32_t pad[3];
+  int32_t pad[1]; // pad[0] != 0: non-planar quad (the leaf box is part of its acceptance rule)
+  // Second-triangle shortcut of quad_hit (b2pt_device.cuh): for a parallelogram the second triangle's barycentrics
+  // are 1 - alpha, 1 - beta, so its reject tests cannot fire while  (1 - max(alpha, beta)) * |det|  exceeds
+  // (|T|_1 + secC1) * |d|_1 * secC2, a bound (>= 8x) on the rounding error of both evaluations.
+  // secC1 = 2 (|E01|_1 + |E03|_1), secC2 = 1e-5 |E03|_1; secC2 = +inf for quads that are not parallelograms.
+  float secC1, secC2;
 };
 
 // Leaf AABB of a primitive as the reference's BVH sees it (pathtracing/AABBSurface.h:24-78).  The reference

@@ -81,6 +81,44 @@ def test_intersect_stage_matches_oracle(gpu_ctx, b2pt, oracle):
             assert (mat[k], texi[k]) == (ohid[0], ohid[1])
 
 
+def test_intersect_near_quad_edges_matches_oracle(gpu_ctx, b2pt, oracle):
+    """Rays aimed at the edges, corners and the diagonal of every quad, a few ulps to 1e-3 on either side, grazing
+    ones included: the second-triangle shortcut of quad_hit (B2Quad::secC1) and the candidate filter's margins
+    must leave every accept/reject decision and every t exactly as the reference's Lagae-Dutre test has it."""
+    sc = oracle.cornell_scene()
+    pts = np.asarray(sc.pts, np.float64)
+    rng = np.random.default_rng(23)
+    O, D = [], []
+    offs = [0.0, 1e-7, -1e-7, 1e-6, -1e-6, 3e-6, -3e-6, 1e-5, -1e-5, 1e-4, -1e-4, 1e-3, -1e-3]
+    for qi in range(sc.quadIds.shape[0]):
+        q, r, s_, t = (pts[int(sc.quadIds[qi, k])] for k in (1, 2, 3, 4))
+        e01, e03 = r - q, t - q
+        n = np.cross(e01, e03)
+        n /= np.linalg.norm(n)
+        for (a, b) in [(1.0, 0.3), (1.0, 0.8), (0.3, 1.0), (0.8, 1.0), (1.0, 1.0), (0.5, 0.5), (0.7, 0.3), (0.0, 0.6),
+                       (0.6, 0.0), (0.999, 0.999)]:
+            for off in offs:
+                target = q + (a + off) * e01 + (b + off * 0.5) * e03
+                for graze in (0.0, 0.9, 0.995):
+                    side = rng.normal(size=3)
+                    side -= side.dot(n) * n
+                    side /= np.linalg.norm(side)
+                    dirv = (1 - graze) * n * rng.choice([-1.0, 1.0]) + graze * side
+                    dirv *= rng.uniform(0.2, 2.5)
+                    O.append(target - dirv * rng.uniform(0.05, 0.6))
+                    D.append(dirv)
+    o, d = np.asarray(O, np.float32), np.asarray(D, np.float32)
+    prim, rec, mat, texi = gpu_ctx.intersect(o, d)
+    hits_second = 0
+    for k in range(o.shape[0]):
+        p, orec, ohid = oracle.closest_hit(sc, o[k], d[k])
+        assert prim[k] == p, k
+        if p >= 0:
+            assert rec[2, k].view(np.uint32) == np.float32(orec[2]).view(np.uint32), k
+            hits_second += 1
+    assert hits_second > 0.5 * o.shape[0]
+
+
 def test_config1_reference_stream_matches_golden(gpu_ctx, b2pt, oracle):
     """BASELINE.json configs[0]: 128x128, 10 spp, depth 5 with the reference's per-pixel RNG stream
     (dead paths burn draws): every trajectory equals the reference-faithful pass-per-worklet oracle."""
