@@ -135,7 +135,8 @@ def test_config1_reference_stream_matches_golden(gpu_ctx, b2pt, oracle):
     assert channels_within(g, live, 10) > 0.9995
 
 
-@pytest.mark.parametrize("W,H,spp,depth", [(128, 128, 10, 5), (96, 64, 48, 50), (64, 64, 64, 1), (50, 50, 32, 2)])
+@pytest.mark.parametrize("W,H,spp,depth", [(128, 128, 10, 5), (96, 64, 48, 50), (64, 64, 64, 1), (50, 50, 32, 2),
+                                           (1024, 1024, 3, 50)])  # last: BASELINE configs[1]'s canvas and depth
 def test_production_stream_matches_oracle(gpu_ctx, b2pt, oracle, W, H, spp, depth):
     gpu_ctx.set_camera(b2pt.Camera(W, H))
     gpu_ctx.render(spp, depth, 0)
