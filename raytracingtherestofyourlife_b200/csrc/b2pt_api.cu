@@ -160,6 +160,7 @@ struct b2pt_ctx
   // a new synchronisation; they are heuristics, any value is correct)
   int64_t tailKey[7] = { -1, -1, -1, -1, -1, -1, -1 };
   int64_t sceneVersion = 0;
+  uint64_t sceneHash = 0;
   int tailDepthCached = 0, loopDepthCached = 0;
   int64_t batchTarget = 0; // default paths per batch, chosen at the first render from the free memory
 
@@ -300,6 +301,18 @@ bool same_vertices(const B2Quad& a, const B2Quad& b)
 }
 
 } // namespace
+
+// 64-bit multiplicative hash over 4-byte words (every hashed table is an array of 4-byte fields without holes)
+static uint64_t hash_words(const void* data, size_t bytes, uint64_t h)
+{
+  const uint32_t* w = static_cast<const uint32_t*>(data);
+  for (size_t i = 0; i < bytes / 4; ++i)
+  {
+    h = (h ^ w[i]) * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29;
+  }
+  return h;
+}
 
 extern "C"
 {
@@ -556,7 +569,15 @@ int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t*
   ctx->nSph = nSpheres;
   ctx->haveScene = true;
   ctx->haveBvh = false;
-  ++ctx->sceneVersion;
+  // The tail-mode depths are cached per scene CONTENT: setting the same scene again (a caller that re-uploads its
+  // scene for every frame) keeps them, so the render does not pay the one stream synchronisation that measures them.
+  uint64_t h = hash_words(ctx->quads.data(), ctx->quads.size() * sizeof(B2Quad), 0x9E3779B97F4A7C15ull);
+  h = hash_words(ctx->sph.data(), ctx->sph.size() * sizeof(B2Sphere), h);
+  h = hash_words(ctx->gates.data(), ctx->gates.size() * sizeof(B2GateBox), h);
+  h = hash_words(&ctx->lights, sizeof(B2Lights), h);
+  if (h != ctx->sceneHash || ctx->sceneVersion == 0)
+    ++ctx->sceneVersion;
+  ctx->sceneHash = h;
   return B2PT_OK;
 }
 
