@@ -57,7 +57,7 @@ with open(os.path.join(P, "%s_ncu_full.csv" % tag), "w") as f:
 bench = json.loads(open(os.path.join(G, "bench_%s.json" % tag)).read().strip().splitlines()[-1])
 rays = [p for p in bench["roofline"]["stage_profile_trace_ms_shade_ms_rays"]][1][2]
 json.dump({
-    "kernel": "bounce 1 of a 64-sample batch at 1024x1024 (%d rays in, the launch pair bench.py times for `achieved`): "
+    "kernel": "bounce 1 of a 128-sample batch at 1024x1024 (%d rays in, the launch pair bench.py times for `achieved`): "
               "k_trace<queue> launch + k_shade launch" % rays,
     "dram_bytes_per_launch": traffic["trace"] + traffic["shade"],
     "dram_bytes_k_trace": traffic["trace"], "dram_bytes_k_shade": traffic["shade"],
