@@ -4,11 +4,12 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import raytracingtherestofyourlife_b200 as B
 import numpy as np
+spp = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 ctx = B.Context(0)
 ctx.set_scene(B.Scene.cornell()); ctx.build_bvh(); ctx.set_camera(B.Camera(1024, 1024))
 ms = []
 for rep in range(5):
-    ctx.render(1024, 50, 0)
+    ctx.render(spp, 50, 0)
     st = ctx.stats()
     ms.append(st.renderMs)
 img = ctx.read_color()
