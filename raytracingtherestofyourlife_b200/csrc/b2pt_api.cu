@@ -1207,7 +1207,7 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
   if (!refStream && units > 0)
   {
     int64_t nb = (units + maxPer - 1) / maxPer;
-    nb = std::max<int64_t>(nb, std::min<int64_t>(overlap_sets(), units / minPer));
+    nb = std::max<int64_t>(nb, std::min<int64_t>((flags & B2PT_FLAG_NO_OVERLAP) ? 1 : overlap_sets(), units / minPer));
     nb = std::max<int64_t>(nb, 1);
     per = (units + nb - 1) / nb;
   }

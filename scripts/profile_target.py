@@ -3,7 +3,7 @@ Each render = 50 k_bounce launches + 1 k_accumulate.  Used under ncu (launch lis
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import raytracingtherestofyourlife_b200 as B
-flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+flags = int(sys.argv[1]) if len(sys.argv) > 1 else B.FLAG_NO_OVERLAP  # one batch, launches serialised
 ctx = B.Context(0)
 ctx.set_scene(B.Scene.cornell()); ctx.build_bvh(); ctx.set_camera(B.Camera(1024, 1024))
 for rep in range(2):
