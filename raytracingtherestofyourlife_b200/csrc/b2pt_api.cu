@@ -132,7 +132,7 @@ struct b2pt_ctx
   DevBuf<float4> colorOwn;
   float4* colorExt = nullptr;
   int64_t colorPixels = 0;
-  // Two sets of per-batch buffers: consecutive sample batches run on up to kMaxSets streams, so the poorly occupied tail of
+  // Sets of per-batch buffers: consecutive sample batches run on up to kMaxSets streams, so the poorly occupied tail of
   // batch b overlaps the full-grid head of batch b+1 (set = batch % nSets; sets are allocated on first use)
   static constexpr int kMaxSets = 4;
   struct BatchBufs
@@ -1225,7 +1225,7 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
   int64_t regionCap = (pathsPerBatch + numWarps - 1) / numWarps;
   regionCap = std::max<int64_t>(32, (regionCap + 31) / 32 * 32);
   const int64_t queueCap = numWarps * regionCap;
-  // Consecutive batches alternate between the context's stream and stream2 (own buffers each): the tail of one
+  // Consecutive batches rotate over the context's stream and the extra streams (own buffers each): the tail of one
   // batch (small grids, one cluster) overlaps the head of the next.  Not in reference-stream mode, where sample s+1
   // continues the per-pixel RNG states sample s leaves behind.
   const int nSets = (nBatches > 1 && !refStream && !(flags & B2PT_FLAG_NO_OVERLAP))
@@ -1259,7 +1259,7 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
   }
 
   if (overlap)
-  { // stream2 starts after everything queued so far on the context's stream (clears, seeds, earlier renders)
+  { // the extra streams start after everything queued so far on the context's stream (clears, seeds, earlier renders)
     CU(cudaEventRecord(ctx->evFork, ctx->stream));
     for (int k = 1; k < nSets; ++k)
       CU(cudaStreamWaitEvent(ctx->extra[k], ctx->evFork, 0));
@@ -1376,7 +1376,7 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     }
   }
   if (overlap)
-  { // join: the context's stream continues after everything stream2 did
+  { // join: the context's stream continues after everything the extra streams did
     for (int k = 1; k < nSets; ++k)
     {
       CU(cudaEventRecord(ctx->evJoin[k], ctx->extra[k]));
