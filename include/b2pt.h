@@ -130,6 +130,13 @@ int b2pt_render_views(b2pt_ctx* ctx, int nViews, const float* views, int W, int 
                       uint32_t flags, void* rgbaOut);
 void* b2pt_views_device_ptr(b2pt_ctx* ctx);
 int b2pt_clear_color(b2pt_ctx* ctx);
+/* Host-side planning rule of the renders above, exposed for tests and capacity planning (no GPU needed): `units`
+ * (samples of one view, or whole views) of unitPaths paths each are cut into equal batches -- as few as
+ * maxPathsPerBatch allows, but up to `sets` (buffer sets in flight, 4 by default) while every batch keeps at least
+ * 32 Mi paths.  The reference has no counterpart: it renders one sample of every pixel per pass
+ * (MapperPathTracer.cxx:278). */
+int b2pt_plan_batches(int64_t units, int64_t unitPaths, int64_t maxPathsPerBatch, int sets, int64_t* unitsPerBatch,
+                      int64_t* nBatches);
 /* Attach a caller-owned device buffer of W*H float4 as the radiance sum (NULL detaches). */
 int b2pt_set_color_buffer(b2pt_ctx* ctx, void* deviceFloat4);
 void* b2pt_color_device_ptr(b2pt_ctx* ctx);

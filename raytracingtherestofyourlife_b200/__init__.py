@@ -64,6 +64,7 @@ SIGNATURES = {
     "b2pt_render_range": (_i32, [_vp, _i32, _i32, _i32, C.c_uint32]),
     "b2pt_render_views": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, C.c_uint32, _vp]),
     "b2pt_views_device_ptr": (_vp, [_vp]),
+    "b2pt_plan_batches": (_i32, [_i64, _i64, _i64, _i32, _vp, _vp]),
     "b2pt_clear_color": (_i32, [_vp]),
     "b2pt_set_color_buffer": (_i32, [_vp, _vp]),
     "b2pt_color_device_ptr": (_vp, [_vp]),
@@ -164,6 +165,13 @@ class Scene:
                                         _p(matType), _p(texType), _p(tex)))
         return Scene(pts, quadIds, sphPt, sphR, mq, tq, ms, ts, matType, texType, tex,
                      lightQuadIds=[[0, n, n + 1, n + 2, n + 3]], lightSphPt=[0], lightSphR=[sphR[0]])
+
+
+def plan_batches(units, unit_paths, max_paths_per_batch=1 << 27, sets=4):
+    """(units per batch, number of batches) of the library's batch split (b2pt_plan_batches; host logic, no GPU)."""
+    per, nb = C.c_int64(0), C.c_int64(0)
+    _check(lib().b2pt_plan_batches(units, unit_paths, max_paths_per_batch, sets, C.byref(per), C.byref(nb)))
+    return per.value, nb.value
 
 
 class Camera:

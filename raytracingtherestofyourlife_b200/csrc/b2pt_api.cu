@@ -1156,6 +1156,25 @@ static int64_t batch_target_paths(b2pt_ctx* ctx)
   return target;
 }
 
+// Cut `units` (samples of one view, or whole views) of unitPaths paths each into equal batches: as few as
+// maxPathsPerBatch allows, but up to one per buffer set while every batch keeps at least 32 Mi paths.
+static void plan_batches(int64_t units, int64_t unitPaths, int64_t maxPathsPerBatch, int64_t sets, int64_t& per,
+                         int64_t& nBatches)
+{
+  per = 1;
+  nBatches = 0;
+  if (units <= 0 || unitPaths <= 0)
+    return;
+  maxPathsPerBatch = std::min<int64_t>(std::max<int64_t>(maxPathsPerBatch, 1), 0xfffffff0LL);
+  const int64_t maxPer = std::max<int64_t>(1, maxPathsPerBatch / unitPaths);
+  const int64_t minPer = std::max<int64_t>(1, std::min<int64_t>(maxPer, ((int64_t)1 << 25) / unitPaths));
+  int64_t nb = (units + maxPer - 1) / maxPer;
+  nb = std::max<int64_t>(nb, std::min<int64_t>(std::max<int64_t>(sets, 1), units / minPer));
+  nb = std::max<int64_t>(nb, 1);
+  per = (units + nb - 1) / nb;
+  nBatches = (units + per - 1) / per;
+}
+
 // One render of the current scene.  nViews == 0: the context's camera, samples [sampleBegin, sampleBegin+sampleCount)
 // accumulated into the context's canvas.  nViews > 0 (b2pt_render_views): the same sample range for every camera of
 // ctx->dViews, accumulated into ctx->viewColor[view]; a batch holds whole views (viewsPerBatch x sampleCount sample
@@ -1200,17 +1219,10 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     return fail(B2PT_ERR_BAD_VALUE, "REFERENCE_STREAM cannot be combined with a view-batched render");
   const int64_t unitPaths = viewMode ? N * std::max(sampleCount, 1) : N;
   const int64_t units = viewMode ? nViews : sampleCount;
-  const int64_t maxPathsPerBatch = std::min<int64_t>(batch_target_paths(ctx), 0xfffffff0LL);
-  const int64_t maxPer = std::max<int64_t>(1, maxPathsPerBatch / unitPaths);
-  const int64_t minPer = std::max<int64_t>(1, std::min<int64_t>(maxPer, ((int64_t)1 << 25) / unitPaths));
-  int64_t per = 1;
-  if (!refStream && units > 0)
-  {
-    int64_t nb = (units + maxPer - 1) / maxPer;
-    nb = std::max<int64_t>(nb, std::min<int64_t>((flags & B2PT_FLAG_NO_OVERLAP) ? 1 : overlap_sets(), units / minPer));
-    nb = std::max<int64_t>(nb, 1);
-    per = (units + nb - 1) / nb;
-  }
+  int64_t per = 1, nbPlanned = 0;
+  if (!refStream)
+    plan_batches(units, unitPaths, batch_target_paths(ctx), (flags & B2PT_FLAG_NO_OVERLAP) ? 1 : overlap_sets(), per,
+                 nbPlanned);
   const int64_t viewsPerBatch = viewMode ? per : 0;
   const int64_t B = viewMode ? per * sampleCount : per;
   const int64_t nBatches = (sampleCount == 0 || units == 0) ? 0 : (units + per - 1) / per;
@@ -1400,6 +1412,15 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
   ctx->pendingCounters = nBatches * maxDepth;
   ctx->pendingMaxDepth = maxDepth;
   ctx->pendingPathsPerBatch = pathsPerBatch;
+  return B2PT_OK;
+}
+
+int b2pt_plan_batches(int64_t units, int64_t unitPaths, int64_t maxPathsPerBatch, int sets, int64_t* unitsPerBatch,
+                      int64_t* nBatches)
+{
+  if (!unitsPerBatch || !nBatches || units < 0 || unitPaths <= 0 || maxPathsPerBatch <= 0 || sets <= 0)
+    return fail(B2PT_ERR_BAD_VALUE, "b2pt_plan_batches: bad argument");
+  plan_batches(units, unitPaths, maxPathsPerBatch, sets, *unitsPerBatch, *nBatches);
   return B2PT_OK;
 }
 
