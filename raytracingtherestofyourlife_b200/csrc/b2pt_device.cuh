@@ -406,7 +406,9 @@ __device__ __forceinline__ void filt_axis(const B2SmallScene& S, int pBegin, int
   const float ea = 4e-6f * Sr * fabsf(rdn); // absolute part
   // candidate iff  t' + |t'|*er + ea > tmin  (upper bound of the true distance beyond tmin); as a threshold on t':
   const float bt = tmin - ea;
-  const float tlo = !axisOk ? inf : (bt > 0.f ? bt * (1.0f - er) : (er < 0.5f ? bt * __fmaf_rn(2.0f, er, 1.0f) : -inf));
+  // (bt > 0: t' > bt/(1+er), bounded below by bt*(1-2er); bt <= 0: t' > bt/(1-er), bounded below by bt*(1+2er) while
+  // er < 0.5 -- one branch-free form, bt - 2er*|bt|, covers both signs)
+  const float tlo = !axisOk ? inf : (er < 0.5f ? __fmaf_rn(-2.0f * er, fabsf(bt), bt) : -inf);
   // lower bound of the true distance used for ordering / pruning:  t'*(1-er) - 3*ea  (valid for either sign of t'
   // that passes the threshold); extreme grazing (er >= 0.5) gets -inf, i.e. is never pruned
   const float cLo = er < 0.5f ? 1.0f - er : 0.f;
