@@ -1244,17 +1244,46 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     ? (int)std::min<int64_t>(overlap_sets(), nBatches)
     : 1;
   const bool overlap = nSets > 1;
-  for (int set = 0; set < nSets; ++set)
-  {
-    b2pt_ctx::BatchBufs& bb = ctx->bufs[set];
-    for (int p = 0; p < 3; ++p)
+  auto reserve_sets = [&]() -> cudaError_t {
+    for (int set = 0; set < nSets; ++set)
     {
-      CU(bb.queue[p].reserve((size_t)queueCap));
-      CU(bb.bins[p].reserve((size_t)queueCap * 4));
+      b2pt_ctx::BatchBufs& bb = ctx->bufs[set];
+      cudaError_t e = cudaSuccess;
+      for (int p = 0; p < 3 && e == cudaSuccess; ++p)
+      {
+        e = bb.queue[p].reserve((size_t)queueCap);
+        if (e == cudaSuccess)
+          e = bb.bins[p].reserve((size_t)queueCap * 4);
+      }
+      if (e == cudaSuccess)
+        e = bb.binCode.reserve((size_t)queueCap * 4);
+      if (e == cudaSuccess)
+        e = bb.regionCounts.reserve((size_t)numWarps * 5);
+      if (e == cudaSuccess)
+        e = bb.rad.reserve((size_t)pathsPerBatch);
+      if (e != cudaSuccess)
+        return e;
     }
-    CU(bb.binCode.reserve((size_t)queueCap * 4));
-    CU(bb.regionCounts.reserve((size_t)numWarps * 5));
-    CU(bb.rad.reserve((size_t)pathsPerBatch));
+    return cudaSuccess;
+  };
+  if (cudaError_t me = reserve_sets())
+  {
+    // The batch target was chosen from the memory that was free when the context rendered first; if somebody else took
+    // it since, give every set back, halve the target and plan again (results do not depend on the batch size).
+    if (me == cudaErrorMemoryAllocation && !getenv("B2PT_BATCH_PATHS") && ctx->batchTarget > ((int64_t)1 << 20))
+    {
+      cudaGetLastError(); // clear the sticky-free allocation error
+      CU(cudaStreamSynchronize(ctx->stream));
+      for (b2pt_ctx::BatchBufs& bb : ctx->bufs)
+      {
+        for (int p = 0; p < 3; ++p)
+          bb.queue[p].release(), bb.bins[p].release();
+        bb.binCode.release(), bb.regionCounts.release(), bb.rad.release();
+      }
+      ctx->batchTarget >>= 1;
+      return render_impl(ctx, sampleBegin, sampleCount, maxDepth, flags, nViews);
+    }
+    return fail(B2PT_ERR_CUDA, "allocating the batch buffers failed: %s", cudaGetErrorString(me));
   }
   const int64_t nCounters = std::max<int64_t>(1, nBatches * maxDepth); // rays entering bounce d+1, per batch
   CU(ctx->counters.reserve((size_t)nCounters));

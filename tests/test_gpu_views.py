@@ -164,3 +164,33 @@ def test_views_pnm16_output(gpu_ctx, b2pt, oracle):
     assert got.dtype == np.uint16 and got.shape == (4, W * H, 3)
     for k in range(4):
         assert np.array_equal(got[k], pnm_integers(sums[k], spp, oracle))
+
+
+def test_render_replans_when_memory_was_taken_after_planning(b2pt):
+    """The batch target is chosen from the memory that is free at a context's first render.  If another consumer takes
+    that memory afterwards, the batch buffers no longer fit: the render halves the target until they do, and the
+    image keeps its bits (results never depend on the batch split)."""
+    torch = pytest.importorskip("torch")
+    cams = (b2pt.Camera(96, 96), b2pt.Camera(768, 768))
+    with b2pt.Context(0) as ctx:
+        ctx.set_scene(b2pt.Scene.cornell())
+        ctx.build_bvh()
+        ctx.set_camera(cams[1])
+        ctx.render(48, 6)
+        want = ctx.read_color().copy()
+    with b2pt.Context(0) as ctx:
+        ctx.set_scene(b2pt.Scene.cornell())
+        ctx.build_bvh()
+        ctx.set_camera(cams[0])
+        ctx.render(2, 3)  # plans the batch target now, with the memory still free
+        free, _ = torch.cuda.mem_get_info()
+        hog = torch.empty(max(int(free) - (3 << 30), 1 << 20), dtype=torch.uint8, device="cuda")  # leave 3 GiB
+        try:
+            ctx.set_camera(cams[1])
+            ctx.render(48, 6)  # 27 Mi paths: 7.4 GB in one batch does not fit any more
+            got = ctx.read_color().copy()
+            assert ctx.stats().batches > 1
+        finally:
+            del hog
+            torch.cuda.empty_cache()
+    assert same_bits(got, want)
