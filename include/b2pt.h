@@ -52,6 +52,7 @@ typedef enum b2pt_status
 #define B2PT_FLAG_GPU_LBVH 0x80u            /* build the BVH on the device (Morton LBVH) instead of the host binned-SAH builder */
 #define B2PT_FLAG_VIEWS_NORMALIZE 0x100u     /* b2pt_render_views: apply b2pt_normalize's sqrt(de_nan(sum)/spp) to every view */
 #define B2PT_FLAG_VIEWS_PNM16 0x200u         /* b2pt_render_views: rgbaOut receives uint16_t[nViews*W*H*3], the integers of b2pt_read_pnm16 */
+#define B2PT_FLAG_NO_PRIMARY_MASKS 0x400u    /* trace primary rays with the generic per-ray candidate filter instead of the per-tile candidate masks (A/B parity checks) */
 #define B2PT_FLAG_NO_AA 0x10u               /* do not use the axis-aligned quad specialisation (A/B parity checks) */
 
 typedef struct b2pt_stats

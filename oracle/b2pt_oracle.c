@@ -1058,14 +1058,16 @@ static void st_composite(State* S, int64_t i, float* canvas4, LStats* st)
 /* ------------------------------------------------------------------------------ forward form */
 /* One path sample in forward (throughput) form.  Same stage order, same draws while alive.
  * burnDepths: if nonzero, a terminated path keeps consuming the draws the reference would. */
-static inline void burn_depths(uint32_t* seed, int count, LStats* st)
+static inline void burn_depths(const orc_scene* sc, uint32_t* seed, int count, LStats* st)
 {
   for (int k = 0; k < count; k++)
   {
     int which = (int)(draw(seed, st) * 3 + 1);
     if (which > 3)
       which = 3;
-    int nd = (which == 2) ? 3 : 2;
+    /* the generators loop over every light, dead pixel or not (PdfWorklet.h:122, :203): cosine 2 draws, 3 per light
+     * quad, 2 per light sphere */
+    int nd = (which <= 1) ? 2 : (which == 2 ? 3 * (int)sc->nLightQuads : 2 * (int)sc->nLightSph);
     for (int j = 0; j < nd; j++)
       (void)draw(seed, st);
   }
@@ -1100,7 +1102,7 @@ static void forward_sample(const orc_scene* sc, const cam_basis* cb, int64_t pix
       L = vscale(T, 0.f);
       terminated = 1;
       if (burn)
-        burn_depths(seed, maxDepth - depth, st);
+        burn_depths(sc, seed, maxDepth - depth, st);
       break;
     }
     int mt = sc->matType[hid[0]];
@@ -1113,7 +1115,7 @@ static void forward_sample(const orc_scene* sc, const cam_basis* cb, int64_t pix
       L = V(T.x * em.x, T.y * em.y, T.z * em.z);
       terminated = 1;
       if (burn)
-        burn_depths(seed, maxDepth - depth, st);
+        burn_depths(sc, seed, maxDepth - depth, st);
       break;
     }
     int specular = 0;

@@ -27,6 +27,7 @@ FLAG_NO_OVERLAP = 0x40
 FLAG_GPU_LBVH = 0x80
 FLAG_VIEWS_NORMALIZE = 0x100
 FLAG_VIEWS_PNM16 = 0x200
+FLAG_NO_PRIMARY_MASKS = 0x400
 
 ERR_BAD_VALUE, ERR_CUDA, ERR_STATE, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 

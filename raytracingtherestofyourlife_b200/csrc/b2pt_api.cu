@@ -44,11 +44,34 @@ int fail(int code, const char* fmt, ...)
       return fail(B2PT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);         \
   } while (0)
 
+// Owning device allocation: freed by the destructor (on the device that is current then -- every owner binds its
+// context's device first), movable, not copyable, so a buffer cannot be forgotten on an error path.
 template <class T>
 struct DevBuf
 {
   T* p = nullptr;
   size_t cap = 0; // elements
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept
+    : p(o.p)
+    , cap(o.cap)
+  {
+    o.p = nullptr;
+    o.cap = 0;
+  }
+  DevBuf& operator=(DevBuf&& o) noexcept
+  {
+    if (this != &o)
+    {
+      release();
+      p = o.p, cap = o.cap;
+      o.p = nullptr, o.cap = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
   cudaError_t reserve(size_t n)
   {
     if (n <= cap)
@@ -154,6 +177,8 @@ struct b2pt_ctx
   DevBuf<B2Camera> dViews;
   DevBuf<float4> viewColor;
   DevBuf<uint16_t> pnm; // packed PNM integers (b2pt_read_pnm16, B2PT_FLAG_VIEWS_PNM16)
+  DevBuf<uint2> primMask;         // primary-ray specialisation: [views][tiles] candidate masks (k_primary_prep)
+  DevBuf<B2PrimQuad> primQuads;   // ... and [views][B2PT_SMALL_MAX_QUADS] per-quad constants
   int64_t viewCount = 0, viewPixels = 0;
 
   // tail-mode depths chosen by the last render with the same scene / canvas / depth / batch shape (reused without
@@ -411,6 +436,7 @@ void b2pt_destroy(b2pt_ctx* ctx)
     b.rad.release();
   }
   ctx->counters.release(), ctx->binTotals.release(), ctx->seeds.release(), ctx->nanCounter.release();
+  ctx->dViews.release(), ctx->viewColor.release(), ctx->pnm.release(), ctx->primMask.release(), ctx->primQuads.release(); // (DevBuf's destructor would free them too)
   if (ctx->evFork)
     cudaEventDestroy(ctx->evFork);
   for (int k = 0; k < b2pt_ctx::kMaxSets; ++k)
@@ -1219,76 +1245,109 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     return fail(B2PT_ERR_BAD_VALUE, "REFERENCE_STREAM cannot be combined with a view-batched render");
   const int64_t unitPaths = viewMode ? N * std::max(sampleCount, 1) : N;
   const int64_t units = viewMode ? nViews : sampleCount;
-  int64_t per = 1, nbPlanned = 0;
-  if (!refStream)
-    plan_batches(units, unitPaths, batch_target_paths(ctx), (flags & B2PT_FLAG_NO_OVERLAP) ? 1 : overlap_sets(), per,
-                 nbPlanned);
-  const int64_t viewsPerBatch = viewMode ? per : 0;
-  const int64_t B = viewMode ? per * sampleCount : per;
-  const int64_t nBatches = (sampleCount == 0 || units == 0) ? 0 : (units + per - 1) / per;
-  const int64_t pathsPerBatch = N * B;
-
-  // Static partition of the queue and the bins into one region per persistent warp (b2pt_types.h).
+  // The plan: batch split, per-warp regions and the number of buffer sets in flight.  Results never depend on it.
+  struct Plan
+  {
+    int64_t per = 1, viewsPerBatch = 0, B = 1, nBatches = 0, pathsPerBatch = 0, numWarps = 0, regionCap = 0, queueCap = 0;
+    int nSets = 1;
+  };
   const int blocksPerSM = std::min(ctx->cfg.traceBlocksPerSM[0][ctx->useBvh ? 1 : 0],
                                    ctx->cfg.shadeBlocksPerSM[0][ctx->useBvh ? 1 : 0]);
   const int wpb = b2pt::warps_per_block();
-  int64_t numWarps = (int64_t)ctx->cfg.numSMs * blocksPerSM * wpb;
-  numWarps = std::max<int64_t>(wpb, std::min<int64_t>(numWarps, ((pathsPerBatch + 31) / 32 + wpb - 1) / wpb * wpb));
-  int64_t regionCap = (pathsPerBatch + numWarps - 1) / numWarps;
-  regionCap = std::max<int64_t>(32, (regionCap + 31) / 32 * 32);
-  const int64_t queueCap = numWarps * regionCap;
-  // Consecutive batches rotate over the context's stream and the extra streams (own buffers each): the tail of one
-  // batch (small grids, one cluster) overlaps the head of the next.  Not in reference-stream mode, where sample s+1
-  // continues the per-pixel RNG states sample s leaves behind.
-  const int nSets = (nBatches > 1 && !refStream && !(flags & B2PT_FLAG_NO_OVERLAP))
-    ? (int)std::min<int64_t>(overlap_sets(), nBatches)
-    : 1;
-  const bool overlap = nSets > 1;
-  auto reserve_sets = [&]() -> cudaError_t {
-    for (int set = 0; set < nSets; ++set)
+  auto make_plan = [&](int64_t target, int64_t setsMax) {
+    Plan P;
+    int64_t nbPlanned = 0;
+    if (!refStream)
+      plan_batches(units, unitPaths, target, setsMax, P.per, nbPlanned);
+    P.viewsPerBatch = viewMode ? P.per : 0;
+    P.B = viewMode ? P.per * sampleCount : P.per;
+    P.nBatches = (sampleCount == 0 || units == 0) ? 0 : (units + P.per - 1) / P.per;
+    P.pathsPerBatch = N * P.B;
+    // Static partition of the queue and the bins into one region per persistent warp (b2pt_types.h).
+    P.numWarps = (int64_t)ctx->cfg.numSMs * blocksPerSM * wpb;
+    P.numWarps =
+      std::max<int64_t>(wpb, std::min<int64_t>(P.numWarps, ((P.pathsPerBatch + 31) / 32 + wpb - 1) / wpb * wpb));
+    P.regionCap = (P.pathsPerBatch + P.numWarps - 1) / P.numWarps;
+    P.regionCap = std::max<int64_t>(32, (P.regionCap + 31) / 32 * 32);
+    P.queueCap = P.numWarps * P.regionCap;
+    // Consecutive batches rotate over the context's stream and the extra streams (own buffers each): the tail of one
+    // batch (small grids, one cluster) overlaps the head of the next.  Not in reference-stream mode, where sample s+1
+    // continues the per-pixel RNG states sample s leaves behind.
+    P.nSets = (P.nBatches > 1 && !refStream) ? (int)std::max<int64_t>(1, std::min<int64_t>(setsMax, P.nBatches)) : 1;
+    return P;
+  };
+  auto reserve_sets = [&](const Plan& P) -> cudaError_t {
+    for (int set = 0; set < P.nSets; ++set)
     {
       b2pt_ctx::BatchBufs& bb = ctx->bufs[set];
       cudaError_t e = cudaSuccess;
       for (int p = 0; p < 3 && e == cudaSuccess; ++p)
       {
-        e = bb.queue[p].reserve((size_t)queueCap);
+        e = bb.queue[p].reserve((size_t)P.queueCap);
         if (e == cudaSuccess)
-          e = bb.bins[p].reserve((size_t)queueCap * 4);
+          e = bb.bins[p].reserve((size_t)P.queueCap * 4);
       }
       if (e == cudaSuccess)
-        e = bb.binCode.reserve((size_t)queueCap * 4);
+        e = bb.binCode.reserve((size_t)P.queueCap * 4);
       if (e == cudaSuccess)
-        e = bb.regionCounts.reserve((size_t)numWarps * 5);
+        e = bb.regionCounts.reserve((size_t)P.numWarps * 5);
       if (e == cudaSuccess)
-        e = bb.rad.reserve((size_t)pathsPerBatch);
+        e = bb.rad.reserve((size_t)P.pathsPerBatch);
       if (e != cudaSuccess)
         return e;
     }
     return cudaSuccess;
   };
-  if (cudaError_t me = reserve_sets())
+  // The batch target was chosen from the memory that was free when the context rendered first.  If somebody else took
+  // it since, the buffers no longer fit: give every set back and plan again with a LOCAL target -- halved while that
+  // still shrinks the batches, then with fewer sets in flight -- until the allocation succeeds.  The context's own
+  // target is left alone: the next render tries the full plan again.
+  int64_t target = batch_target_paths(ctx);
+  int64_t setsMax = (flags & B2PT_FLAG_NO_OVERLAP) ? 1 : overlap_sets();
+  Plan P = make_plan(target, setsMax);
+  for (;;)
   {
-    // The batch target was chosen from the memory that was free when the context rendered first; if somebody else took
-    // it since, give every set back, halve the target and plan again (results do not depend on the batch size).
-    if (me == cudaErrorMemoryAllocation && !getenv("B2PT_BATCH_PATHS") && ctx->batchTarget > ((int64_t)1 << 20))
+    const cudaError_t me = reserve_sets(P);
+    if (me == cudaSuccess)
+      break;
+    if (me != cudaErrorMemoryAllocation)
+      return fail(B2PT_ERR_CUDA, "allocating the batch buffers failed: %s", cudaGetErrorString(me));
+    cudaGetLastError(); // the allocation error is not sticky; clear it
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (b2pt_ctx::BatchBufs& bb : ctx->bufs)
     {
-      cudaGetLastError(); // clear the sticky-free allocation error
-      CU(cudaStreamSynchronize(ctx->stream));
-      for (b2pt_ctx::BatchBufs& bb : ctx->bufs)
-      {
-        for (int p = 0; p < 3; ++p)
-          bb.queue[p].release(), bb.bins[p].release();
-        bb.binCode.release(), bb.regionCounts.release(), bb.rad.release();
-      }
-      ctx->batchTarget >>= 1;
-      return render_impl(ctx, sampleBegin, sampleCount, maxDepth, flags, nViews);
+      for (int p = 0; p < 3; ++p)
+        bb.queue[p].release(), bb.bins[p].release();
+      bb.binCode.release(), bb.regionCounts.release(), bb.rad.release();
     }
-    return fail(B2PT_ERR_CUDA, "allocating the batch buffers failed: %s", cudaGetErrorString(me));
+    Plan Q = P;
+    bool changed = false;
+    while (!changed && !getenv("B2PT_BATCH_PATHS") && target > unitPaths && target > ((int64_t)1 << 16))
+    { // halve until the plan really gets smaller (a single unit per batch cannot shrink further)
+      target >>= 1;
+      Q = make_plan(target, setsMax);
+      changed = Q.pathsPerBatch < P.pathsPerBatch || Q.nSets < P.nSets;
+    }
+    while (!changed && setsMax > 1)
+    {
+      --setsMax;
+      Q = make_plan(target, setsMax);
+      changed = Q.nSets < P.nSets;
+    }
+    if (!changed)
+      return fail(B2PT_ERR_ALLOC, "allocating the batch buffers failed (%lld paths per batch, %d set(s)): %s",
+                  (long long)P.pathsPerBatch, P.nSets, cudaGetErrorString(me));
+    P = Q;
   }
+  const int64_t viewsPerBatch = P.viewsPerBatch, B = P.B, nBatches = P.nBatches, pathsPerBatch = P.pathsPerBatch;
+  const int64_t numWarps = P.numWarps, regionCap = P.regionCap, queueCap = P.queueCap;
+  const int nSets = P.nSets;
+  const bool overlap = nSets > 1;
   const int64_t nCounters = std::max<int64_t>(1, nBatches * maxDepth); // rays entering bounce d+1, per batch
   CU(ctx->counters.reserve((size_t)nCounters));
   CU(ctx->binTotals.reserve((size_t)nCounters * 4));
   CU(ctx->nanCounter.reserve(1));
+  int64_t launches0 = 0;
   CU(cudaEventRecord(ctx->evStart, ctx->stream));
   CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(uint32_t) * (size_t)nCounters, ctx->stream));
   CU(cudaMemsetAsync(ctx->binTotals.p, 0, sizeof(uint32_t) * (size_t)nCounters * 4, ctx->stream));
@@ -1298,14 +1357,41 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     CU(ctx->seeds.reserve((size_t)N));
     CU(b2pt::launch_fill_seeds(ctx->seeds.p, (int)N, ctx->seedOffset, ctx->stream));
   }
+  // Primary-ray specialisation (small scenes whose tiles of 32 path ids are tiles of 32 pixels of one view): candidate
+  // masks per tile and quad constants per view, recomputed per render (a few microseconds).
+  const bool primMasks = !ctx->useBvh && (N % 32) == 0 && nBatches > 0 && !(flags & B2PT_FLAG_NO_PRIMARY_MASKS);
+  const int tilesPerView = (int)(N / 32);
+  if (primMasks)
+  {
+    const int nv = viewMode ? (int)nViews : 1;
+    CU(ctx->primMask.reserve((size_t)nv * tilesPerView));
+    CU(ctx->primQuads.reserve((size_t)nv * B2PT_SMALL_MAX_QUADS));
+    CU(b2pt::launch_primary_prep(ctx->small, ctx->cam, viewMode ? ctx->dViews.p : nullptr, nv, tilesPerView,
+                                 ctx->primMask.p, ctx->primQuads.p, ctx->stream));
+    ++launches0;
+  }
 
+  // An error return while batches are in flight on the extra streams must not leave them running behind the caller's
+  // back (later work on the context's stream would race with them): the guard drains them on every early exit.
+  struct DrainGuard
+  {
+    b2pt_ctx* c;
+    int n;
+    bool armed;
+    ~DrainGuard()
+    {
+      if (armed)
+        for (int k = 1; k < n; ++k)
+          cudaStreamSynchronize(c->extra[k]);
+    }
+  } drain{ ctx, nSets, overlap };
   if (overlap)
   { // the extra streams start after everything queued so far on the context's stream (clears, seeds, earlier renders)
     CU(cudaEventRecord(ctx->evFork, ctx->stream));
     for (int k = 1; k < nSets; ++k)
       CU(cudaStreamWaitEvent(ctx->extra[k], ctx->evFork, 0));
   }
-  int64_t launches = refStream ? 1 : 0;
+  int64_t launches = (refStream ? 1 : 0) + launches0;
   int tailDepth = maxDepth; // bounces >= tailDepth run in tail mode; chosen after the first batch
   int loopDepth = maxDepth; // bounces >= loopDepth (>= tailDepth) run inside one persistent cluster launch
   const int64_t tailKey[7] = { ctx->sceneVersion,  N, maxDepth, pathsPerBatch, (int64_t)flags, tail_rays_per_warp(),
@@ -1347,7 +1433,12 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     A.sampleBase = (int32_t)(sampleBegin + s0);
     A.views = viewMode ? ctx->dViews.p + v0 : nullptr;
     A.sppPerView = viewMode ? sampleCount : 0;
+    A.primMask = primMasks ? ctx->primMask.p + (viewMode ? v0 * tilesPerView : 0) : nullptr;
+    A.primQuads = primMasks ? ctx->primQuads.p + (viewMode ? v0 * B2PT_SMALL_MAX_QUADS : 0) : nullptr;
+    A.tilesPerView = tilesPerView;
     A.maxDepth = maxDepth;
+    A.nLightQuads = ctx->lights.nLightQuads;
+    A.nLightSph = ctx->lights.nLightSph;
     A.seedOffset = ctx->seedOffset;
     A.flags = flags;
     for (int depth = 0; depth < maxDepth; ++depth)
@@ -1424,6 +1515,7 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
       CU(cudaStreamWaitEvent(ctx->stream, ctx->evJoin[k], 0));
     }
   }
+  drain.armed = false;
   CU(cudaEventRecord(ctx->evStop, ctx->stream));
 
   ctx->stats = b2pt_stats{};
@@ -1503,7 +1595,8 @@ int b2pt_render_views(b2pt_ctx* ctx, int nViews, const float* views, int W, int 
     ctx->haveCamera = savedHave;
     ctx->colorExt = savedExt;
   };
-  if (spp > 0 && N * spp <= std::min<int64_t>(batch_target_paths(ctx), 0xfffffff0LL))
+  bool perView = !(spp > 0 && N * spp <= std::min<int64_t>(batch_target_paths(ctx), 0xfffffff0LL));
+  if (!perView)
   { // whole views fit a batch: (view, sample, pixel) is one flat index space, one set of launches per batch of views
     // (pageable source: the copy is staged before the call returns, so `cams` may go out of scope)
     cudaError_t e = cudaMemcpyAsync(ctx->dViews.p, cams.data(), sizeof(B2Camera) * (size_t)nViews,
@@ -1514,9 +1607,13 @@ int b2pt_render_views(b2pt_ctx* ctx, int nViews, const float* views, int W, int 
       return fail(B2PT_ERR_CUDA, "cudaMemcpyAsync(views): %s", cudaGetErrorString(e));
     }
     rc = render_impl(ctx, 0, spp, maxDepth, flags, nViews);
+    perView = rc == B2PT_ERR_ALLOC; // the buffers of a whole-view batch could not be allocated: views one by one
   }
-  else
+  if (perView)
   { // a single view already fills several batches: one ordinary render per view into its slice
+    rc = B2PT_OK;
+    if (cudaMemsetAsync(ctx->viewColor.p, 0, sizeof(float4) * (size_t)(N * nViews), ctx->stream) != cudaSuccess)
+      rc = fail(B2PT_ERR_CUDA, "clearing the view canvases failed");
     int64_t paths = 0, launches = 0;
     for (int v = 0; v < nViews && rc == B2PT_OK; ++v)
     {

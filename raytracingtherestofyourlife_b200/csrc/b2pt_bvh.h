@@ -90,7 +90,11 @@ struct BvhBuilder
   std::vector<BvhItem> items;
   std::vector<B2BvhNode>& nodes;
   std::vector<int32_t>& slots;
-  std::atomic<int32_t> nodeCount{ 0 }, slotCount{ 0 };
+  std::atomic<int32_t> nodeCount{ 0 }, slotCount{ 0 }, maxDepth{ 0 };
+  // SAH splits may peel one primitive per level on skewed input; past this depth every split is the balanced median
+  // one, so the tree is never deeper than kSahDepthLimit + ceil(log2 n) <= 32 + 24 levels -- inside the traversal's
+  // stack (64 entries for the binary layout)
+  static constexpr int kSahDepthLimit = 32;
 
   BvhBuilder(std::vector<B2BvhNode>& n, std::vector<int32_t>& s)
     : nodes(n)
@@ -111,9 +115,12 @@ struct BvhBuilder
       slots[(size_t)first + (i - lo)] = items[i].enc;
   }
 
-  void build(size_t wlo, size_t whi, int32_t wnode)
+  void build(size_t wlo, size_t whi, int32_t wnode, int depth = 0)
   {
     const size_t n = whi - wlo;
+    for (int32_t seen = maxDepth.load(); depth > seen && !maxDepth.compare_exchange_weak(seen, depth);)
+    {
+    }
     float bmin[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, bmax[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
     float cmin[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, cmax[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
     for (size_t i = wlo; i < whi; ++i)
@@ -207,7 +214,9 @@ struct BvhBuilder
     if (bestAxis < 0 && n <= (size_t)kLeafMax)
       return make_leaf(wlo, whi, wnode);
     size_t mid;
-    if (bestAxis >= 0 && (splitCost < leafCost || n > (size_t)kLeafMax))
+    if (depth >= kSahDepthLimit && n > (size_t)kLeafMax)
+      mid = wlo; // too deep: the median fallback below
+    else if (bestAxis >= 0 && (splitCost < leafCost || n > (size_t)kLeafMax))
     {
       const float ext = cmax[bestAxis] - cmin[bestAxis];
       const float scale = (float)kBins / ext;
@@ -236,15 +245,15 @@ struct BvhBuilder
     nodes[(size_t)wnode].count = 0;
     if (n >= kTaskMin)
     {
-#pragma omp task default(shared) firstprivate(wlo, mid, left)
-      build(wlo, mid, left);
-      build(mid, whi, left + 1);
+#pragma omp task default(shared) firstprivate(wlo, mid, left, depth)
+      build(wlo, mid, left, depth + 1);
+      build(mid, whi, left + 1, depth + 1);
 #pragma omp taskwait
     }
     else
     {
-      build(wlo, mid, left);
-      build(mid, whi, left + 1);
+      build(wlo, mid, left, depth + 1);
+      build(mid, whi, left + 1, depth + 1);
     }
   }
 };

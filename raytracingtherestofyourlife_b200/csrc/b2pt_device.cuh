@@ -86,16 +86,16 @@ __device__ __forceinline__ int draw_which(uint32_t& seed)
   int w = (int)(randf(seed) * 3.f + 1.f);
   return w > 3 ? 3 : w;
 }
-// Draws a dead pixel still consumes in the reference: per remaining depth 1 (which) + 2/3/2 (generator),
-// SURVEY A.3.  Only used by B2PT_FLAG_REFERENCE_STREAM.
-__device__ __forceinline__ void burn_depths(uint32_t& seed, int count)
+// Draws a dead pixel still consumes in the reference: per remaining depth 1 (which) + the generator's -- cosine 2,
+// 3 per light quad, 2 per light sphere: the generators loop over every light whether the pixel is alive or not
+// (PdfWorklet.h:122, :203).  Only used by B2PT_FLAG_REFERENCE_STREAM.
+__device__ __forceinline__ void burn_depths(uint32_t& seed, int count, int nLightQuads, int nLightSph)
 {
   for (int k = 0; k < count; ++k)
   {
-    int w = draw_which(seed);
-    wang32(seed);
-    wang32(seed);
-    if (w == 2)
+    const int w = draw_which(seed);
+    const int nd = (w <= 1) ? 2 : (w == 2 ? 3 * nLightQuads : 2 * nLightSph);
+    for (int j = 0; j < nd; ++j)
       wang32(seed);
   }
 }
@@ -472,6 +472,10 @@ __device__ __forceinline__ void filt_frame(const B2SmallScene& S, int f, int& pB
 // exact-t tie; quads are tested here in a different order (filter candidates nearest first, then boxed quads),
 // so a tie is resolved explicitly in favour of the lower original index -- the same winner as index order.
 #define B2PT_MISS 0x7fffffff
+#ifdef B2PT_DEBUG_HIST
+// experiment builds only (scripts/build_variant.sh hist -DB2PT_DEBUG_HIST): per-ray counts of the two-phase filter
+__device__ unsigned long long g_debugHist[64];
+#endif
 __device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, float tmin, float tmax, float& tHit)
 {
   float closest = tmax;
@@ -504,14 +508,25 @@ __device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, 
     uint32_t rest = F.mask;
     const int top = S.nVisit - 1;
     int v = F.vb;
+#ifdef B2PT_DEBUG_HIST
+    int iters = 0;
+    atomicAdd(&g_debugHist[__popc(rest) < 15 ? __popc(rest) : 15], 1ull); // [0..15]: candidates per ray
+#endif
     while (rest)
     {
       rest &= ~(1u << (top - v));
       test_quad(S.visitSlot[v]);
+#ifdef B2PT_DEBUG_HIST
+      ++iters;
+#endif
       if (slot >= 0 && F.t2 > closest) // valid from the first iteration on: F.vb is tested first
         break;
       v = top - (__ffs((int)rest) - 1);
     }
+#ifdef B2PT_DEBUG_HIST
+    atomicAdd(&g_debugHist[16 + (iters < 15 ? iters : 15)], 1ull); // [16..31]: exact tests per ray
+    atomicAdd(&g_debugHist[32 + (slot >= 0 ? 1 : 0)], 1ull);       // [32],[33]: filtered quads gave no hit / a hit
+#endif
   }
   // ---- remaining quads behind the slab test of their own leaf box (BVHTraverser.h:35-79, 143-157), then the
   // spheres behind theirs (sphere_gate)
@@ -536,6 +551,113 @@ __device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, 
     }
     for (int s = 0; s < S.nSph; ++s)
     {
+      float tn, t;
+      if (slab_hit(S.sphGate[s].bmin, S.sphGate[s].bmax, inv, od, tmin, tmax, tn) &&
+          sphere_accept(ld3(S.sph[s].c), S.sph[s].r, o, d, tmin, closest, t))
+      {
+        closest = t;
+        slot = S.nQuads + s;
+      }
+    }
+  }
+  tHit = closest;
+  return slot < 0 ? B2PT_MISS : slot;
+}
+// ---- primary rays: quad_hit with the origin-dependent terms read from B2PrimQuad (same operations in the same order
+// as quad_hit, so the outcome and t are bit-identical), and the closest hit over a tile's candidate mask.
+__device__ __forceinline__ bool quad_hit_primary(const B2Quad& Q, const B2PrimQuad& C, f3 o, f3 d, float& t)
+{
+  const float4* q4 = reinterpret_cast<const float4*>(&Q);
+  const float4 c0 = q4[0], c1 = q4[1], c2 = q4[2]; // v00 e01 | e01 e03 | e03 v11
+  const float4 k0 = reinterpret_cast<const float4*>(&C)[0], k1 = reinterpret_cast<const float4*>(&C)[1];
+  const f3 E03 = mk3(c1.z, c1.w, c2.x);
+  f3 P = cross3(d, E03);
+  const f3 E01 = mk3(c0.w, c1.x, c1.y);
+  float det = dot3(E01, P);
+  if (fabsf(det) < 1e-5f)
+    return false;
+  float inv_det = 1.0f / det;
+  const f3 T = mk3(k0.x, k0.y, k0.z);
+  float alpha = dot3(T, P) * inv_det;
+  if (alpha < 0.0f)
+    return false;
+  const f3 Qv = mk3(k1.x, k1.y, k1.z);
+  float beta = dot3(d, Qv) * inv_det;
+  if (beta < 0.0f)
+    return false;
+  if ((alpha + beta) > 1.0f)
+  {
+    const float need = k1.w * ((fabsf(d.x) + fabsf(d.y)) + fabsf(d.z)) * Q.secC2;
+    if (!((1.0f - fmaxf(alpha, beta)) * fabsf(det) > need && fabsf(det) >= 2e-5f))
+    { // near an edge / general quad: the reference's second-triangle arithmetic as written (see quad_hit)
+      const float4 c3 = q4[3], c4 = q4[4];
+      const f3 E23 = mk3(c3.w, c4.x, c4.y);
+      const f3 E21 = mk3(c3.x, c3.y, c3.z);
+      f3 Pp = cross3(d, E21);
+      float detp = dot3(E23, Pp);
+      if (fabsf(detp) < 1e-5f)
+        return false;
+      float inv_detp = 1.0f / detp;
+      f3 Tp = o - mk3(c2.y, c2.z, c2.w);
+      float alphap = dot3(Tp, Pp) * inv_detp;
+      if (alphap < 0.0f)
+        return false;
+      f3 Qp = cross3(Tp, E23);
+      float betap = dot3(d, Qp) * inv_detp;
+      if (betap < 0.0f)
+        return false;
+    }
+  }
+  t = k0.w * inv_det;
+  if (t < 0.0f)
+    return false;
+  return true;
+}
+// Closest hit of a primary ray over the candidates of its tile.  The exact tests run on a SUPERSET of the quads the
+// per-ray filter of closest_small would keep, the winner is "smallest t, exact ties to the lowest original index"
+// either way, boxed quads and spheres follow with the same rules, so the result equals closest_small's bit for bit.
+__device__ __forceinline__ int closest_small_masked(const B2SmallScene& S, const B2PrimQuad* __restrict__ pq, uint2 mask,
+                                                    f3 o, f3 d, float tmin, float tmax, float& tHit)
+{
+  float closest = tmax;
+  int slot = -1;
+  int bestPrim = 0x7fffffff;
+  for (uint32_t m = mask.x; m; m &= m - 1u) // warp-uniform loop: the mask belongs to the tile
+  {
+    const int q = S.visitSlot[__ffs((int)m) - 1];
+    const B2Quad& Q = S.quads[q];
+    const B2PrimQuad C = pq[q];
+    float t;
+    if (quad_hit_primary(Q, C, o, d, t) && t > tmin && (t < closest || (t == closest && Q.prim < bestPrim)))
+    {
+      closest = t;
+      slot = q;
+      bestPrim = Q.prim;
+    }
+  }
+  if (mask.y)
+  {
+    const f3 inv = mk3(rcp_safe(d.x), rcp_safe(d.y), rcp_safe(d.z));
+    const f3 od = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+    for (int q = S.firstBoxed; q < S.nQuads; ++q)
+    {
+      const B2Quad& Q = S.quads[q];
+      if (!((mask.y >> (Q.gate - 1)) & 1u))
+        continue;
+      float tn, t;
+      if (!slab_hit(S.gate[Q.gate - 1].bmin, S.gate[Q.gate - 1].bmax, inv, od, tmin, closest, tn))
+        continue;
+      if (quad_hit(Q, o, d, t) && t > tmin && (t < closest || (t == closest && Q.pad[0] == 0 && Q.prim < bestPrim)))
+      {
+        closest = t;
+        slot = q;
+        bestPrim = Q.prim;
+      }
+    }
+    for (int s = 0; s < S.nSph; ++s)
+    {
+      if (!((mask.y >> (B2PT_PRIM_SPH_SHIFT + s)) & 1u))
+        continue;
       float tn, t;
       if (slab_hit(S.sphGate[s].bmin, S.sphGate[s].bmax, inv, od, tmin, tmax, tn) &&
           sphere_accept(ld3(S.sph[s].c), S.sph[s].r, o, d, tmin, closest, t))

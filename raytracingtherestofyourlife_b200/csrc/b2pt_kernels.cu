@@ -160,7 +160,7 @@ __device__ __forceinline__ void finish_path(const B2RenderArgs& A, uint32_t pid,
   A.rad[pid] = make_float4(L.x, L.y, L.z, 0.f);
   if (refStream)
   {
-    burn_depths(rng, depthsToBurn);
+    burn_depths(rng, depthsToBurn, A.nLightQuads, A.nLightSph);
     A.seeds[pid % (uint32_t)A.nPixels] = rng;
   }
 }
@@ -443,7 +443,21 @@ __device__ __forceinline__ void trace_body(const B2Camera& cam, const SceneT& S,
     if (PRIMARY ? idx < A.nPaths : i < nIn)
     {
       load_ray<PRIMARY>(cam, A, idx, o, d, T, pid, rng);
-      code = closest_hit(S, o, d, 0.001f, FLT_MAX, t);
+      bool masked = false;
+      if constexpr (PRIMARY && std::is_same<SceneT, B2SmallScene>::value)
+        masked = A.primMask != nullptr;
+      if constexpr (PRIMARY && std::is_same<SceneT, B2SmallScene>::value)
+        if (masked)
+      { // the tile's candidate mask and the view's per-quad constants (warp-uniform; nPixels % 32 == 0)
+        const int64_t tileBase = idx - lane;
+        const uint32_t slotB = (uint32_t)(tileBase / A.nPixels);
+        const uint32_t view = A.views ? slotB / (uint32_t)A.sppPerView : 0u;
+        const uint32_t tileInView = (uint32_t)((tileBase - (int64_t)slotB * A.nPixels) >> 5);
+        const uint2 mask = __ldg(A.primMask + (size_t)view * A.tilesPerView + tileInView);
+        code = closest_small_masked(S, A.primQuads + (size_t)view * B2PT_SMALL_MAX_QUADS, mask, o, d, 0.001f, FLT_MAX, t);
+      }
+      if (!masked)
+        code = closest_hit(S, o, d, 0.001f, FLT_MAX, t);
       if (code == B2PT_MISS)
         finish_path(A, pid, T * 0.f, rng, refStream, A.maxDepth - depth); // a[d]=1, e[d]=0
       else
@@ -699,6 +713,179 @@ __global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kTailBloc
   }
 }
 
+// Per view and per tile of 32 consecutive pixels: which primitives of a small scene can any primary ray of the tile
+// hit (B2RenderArgs::primMask), plus the per-view constants of quad_hit_primary (B2PrimQuad).  One thread per
+// (view, tile); double precision, a few hundred operations per quad.  The rule is a rigorous superset of what the
+// per-ray candidate filter of closest_small keeps (DESIGN.md "primary tiles"):
+//  * The float direction of a primary ray (Camera.cxx:483-524 in float, then normalised) is parallel, to within
+//    2e-6 rad, to  nlook + dx*sx + dy*sy  for some (sx, sy) in the tile's jitter rectangle; widening the rectangle by
+//    `grow` pixels (>= 4x that angle) makes it exactly parallel to a direction of the widened frustum, and the hit
+//    point on a plane does not depend on the direction's length.
+//  * For a plane  x_n = c  of a filter frame the hit coordinates  o_u + (c - o_n) d_u/d_n  are linear-fractional in
+//    (sx, sy) while d_n keeps its sign, so their range over the frustum is attained at its four corner directions.
+//  * The per-ray filter passes a quad iff its (float) hit point lies in the quad's rectangle widened by
+//    marg = S (2e-5 + 2e-5 D), D = |d|_1/|d_n|, which bounds its own evaluation error too; the tile keeps the quad iff
+//    the corner range meets the rectangle widened by 2.02 marg(D_max).  d_n changing sign (or nearly grazing) keeps
+//    every quad of that axis.  A plane wholly behind the tile (t < 0 everywhere, by more than 1e-3 S, D < 50) is
+//    dropped: the exact test rejects t < 0.
+//  * Gate boxes (boxed quads, spheres): interval slab test of the frustum against the box widened by 1e-5 S, far
+//    beyond the rounding of the per-ray float slab test that remains the acceptance rule.
+__global__ void __launch_bounds__(128)
+  k_primary_prep(const __grid_constant__ B2SmallScene S, const __grid_constant__ B2Camera cam0, const B2Camera* views,
+                 int nViews, int tilesPerView, uint2* masks, B2PrimQuad* pq)
+{
+  const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (int64_t)nViews * tilesPerView)
+    return;
+  const int view = (int)(id / tilesPerView), tile = (int)(id - (int64_t)view * tilesPerView);
+  const B2Camera cam = views ? views[view] : cam0;
+  for (int q = tile; q < S.nQuads; q += tilesPerView)
+  { // per-view quad constants, dealt over the view's threads; the float arithmetic of quad_hit (this file is compiled
+    // without FMA contraction)
+    const B2Quad& Q = S.quads[q];
+    const f3 o = ld3(cam.pos);
+    const f3 T = o - ld3(Q.v00);
+    const f3 Qv = cross3(T, ld3(Q.e01));
+    B2PrimQuad C;
+    C.T[0] = T.x, C.T[1] = T.y, C.T[2] = T.z;
+    C.tnum = dot3(ld3(Q.e03), Qv);
+    C.Qv[0] = Qv.x, C.Qv[1] = Qv.y, C.Qv[2] = Qv.z;
+    C.tn1 = (fabsf(T.x) + fabsf(T.y)) + fabsf(T.z) + Q.secC1;
+    pq[(size_t)view * B2PT_SMALL_MAX_QUADS + q] = C;
+  }
+  // pixel rectangle of the tile (a tile that wraps to the next row covers whole rows)
+  const int W = cam.W, H = cam.H;
+  const int64_t p0 = (int64_t)tile * 32, p1 = min(p0 + 31, (int64_t)W * H - 1);
+  int i0 = (int)(p0 % W), i1 = (int)(p1 % W);
+  const int j0 = (int)(p0 / W), j1 = (int)(p1 / W);
+  if (j1 != j0)
+    i0 = 0, i1 = W - 1;
+  const double dxl = sqrt((double)cam.dx[0] * cam.dx[0] + (double)cam.dx[1] * cam.dx[1] + (double)cam.dx[2] * cam.dx[2]);
+  const double dyl = sqrt((double)cam.dy[0] * cam.dy[0] + (double)cam.dy[1] * cam.dy[1] + (double)cam.dy[2] * cam.dy[2]);
+  const double growx = fmax(0.01, 1.6e-5 / fmax(dxl, 1e-300)), growy = fmax(0.01, 1.6e-5 / fmax(dyl, 1e-300));
+  // sx = i + (1 - ru) - W/2 in [i - W/2, i + 1 - W/2], sy = j + rv - H/2 (Camera.cxx:508-509)
+  const double sx[2] = { (double)i0 - 0.5 * W - growx, (double)i1 + 1.0 - 0.5 * W + growx };
+  const double sy[2] = { (double)j0 - 0.5 * H - growy, (double)j1 + 1.0 - 0.5 * H + growy };
+  double dw[4][3]; // corner directions, world frame
+  for (int k = 0; k < 4; ++k)
+    for (int c = 0; c < 3; ++c)
+      dw[k][c] = (double)cam.nlook[c] + (double)cam.dx[c] * sx[k & 1] + (double)cam.dy[c] * sy[k >> 1];
+  const double ow[3] = { cam.pos[0], cam.pos[1], cam.pos[2] };
+  const double Sr = fmax((double)S.sceneAbs, fmax(fabs(ow[0]), fmax(fabs(ow[1]), fabs(ow[2]))));
+  uint32_t mx = 0u, my = 0u;
+  int pBegin = 0;
+  for (int f = 0; f < S.nFrames; ++f)
+  {
+    const B2Frame& Fr = S.frames[f];
+    double ol[3], dl[4][3];
+    double Sf = Sr;
+    if (Fr.identity)
+    {
+      for (int c = 0; c < 3; ++c)
+      {
+        ol[c] = ow[c];
+        for (int k = 0; k < 4; ++k)
+          dl[k][c] = dw[k][c];
+      }
+    }
+    else
+    {
+      for (int a = 0; a < 3; ++a)
+      {
+        ol[a] = (double)Fr.R[3 * a] * (ow[0] - Fr.org[0]) + (double)Fr.R[3 * a + 1] * (ow[1] - Fr.org[1]) +
+          (double)Fr.R[3 * a + 2] * (ow[2] - Fr.org[2]);
+        for (int k = 0; k < 4; ++k)
+          dl[k][a] = (double)Fr.R[3 * a] * dw[k][0] + (double)Fr.R[3 * a + 1] * dw[k][1] + (double)Fr.R[3 * a + 2] * dw[k][2];
+      }
+      Sf = 4.0 * Sr;
+    }
+    double dabsMax = 0.0;
+    for (int k = 0; k < 4; ++k)
+      dabsMax = fmax(dabsMax, fabs(dl[k][0]) + fabs(dl[k][1]) + fabs(dl[k][2]));
+    for (int n = 0; n < 3; ++n)
+    {
+      const int pEnd = Fr.axisEnd[n];
+      if (pEnd <= pBegin)
+        continue;
+      const int u = (n + 1) % 3, v = (n + 2) % 3;
+      double dnMin = 1e300;
+      bool pos = true, neg = true;
+      for (int k = 0; k < 4; ++k)
+      {
+        dnMin = fmin(dnMin, fabs(dl[k][n]));
+        pos = pos && dl[k][n] > 0.0;
+        neg = neg && dl[k][n] < 0.0;
+      }
+      const bool oneSign = (pos || neg) && dnMin > 1e-9 * dabsMax;
+      const double D = oneSign ? dabsMax / dnMin : 1e300;
+      const double M = 2.02 * Sf * (2e-5 * D + 2e-5);
+      for (int p = pBegin; p < pEnd; ++p)
+        for (int h = 0; h < 2; ++h)
+        {
+          const int vis = 2 * p + h;
+          if (S.visitSlot[vis] < 0)
+            continue;
+          bool keep = true;
+          if (oneSign && D < 1e6)
+          {
+            const double kk = (double)S.pairs[p].c[h] - ol[n];
+            double umin = 1e300, umax = -1e300, vmin = 1e300, vmax = -1e300;
+            for (int k = 0; k < 4; ++k)
+            {
+              const double tt = kk / dl[k][n];
+              const double hu = ol[u] + tt * dl[k][u], hv = ol[v] + tt * dl[k][v];
+              umin = fmin(umin, hu), umax = fmax(umax, hu), vmin = fmin(vmin, hv), vmax = fmax(vmax, hv);
+            }
+            const double uc = S.pairs[p].uc[h], hu = (double)S.pairs[p].hu[h] + M;
+            const double vc = S.pairs[p].vc[h], hv = (double)S.pairs[p].hv[h] + M;
+            keep = umax >= uc - hu && umin <= uc + hu && vmax >= vc - hv && vmin <= vc + hv;
+            const bool behind = (kk > 0.0) != pos; // c - o_n and d_n of opposite sign at every corner: t < 0
+            if (behind && fabs(kk) > 1e-3 * Sf && D < 50.0)
+              keep = false;
+          }
+          if (keep)
+            mx |= 1u << vis;
+        }
+      pBegin = pEnd;
+    }
+    pBegin = max(pBegin, Fr.axisEnd[2]);
+  }
+  // gate boxes of the boxed quads and of the spheres: conservative interval slab test in world coordinates
+  double dlo[3], dhi[3];
+  for (int c = 0; c < 3; ++c)
+  {
+    dlo[c] = fmin(fmin(dw[0][c], dw[1][c]), fmin(dw[2][c], dw[3][c]));
+    dhi[c] = fmax(fmax(dw[0][c], dw[1][c]), fmax(dw[2][c], dw[3][c]));
+  }
+  auto box_may_hit = [&](const float* bmin, const float* bmax) -> bool {
+    double enter = 0.0, leave = 1e300; // lowest possible entry, highest possible exit over the direction box
+    for (int c = 0; c < 3; ++c)
+    {
+      const double pad = 1e-5 * Sr + 1e-5 * ((double)bmax[c] - (double)bmin[c]);
+      const double lo = (double)bmin[c] - pad - ow[c], hi = (double)bmax[c] + pad - ow[c];
+      if (dlo[c] > 0.0 || dhi[c] < 0.0)
+      { // the component keeps its sign: t = (plane - o)/d over d in [dlo, dhi]
+        const double a[4] = { lo / dlo[c], lo / dhi[c], hi / dlo[c], hi / dhi[c] };
+        const double tnearLo = fmin(fmin(a[0], a[1]), fmin(a[2], a[3]));
+        const double tfarHi = fmax(fmax(a[0], a[1]), fmax(a[2], a[3]));
+        // (entry and exit of one direction are the smaller / larger of its two plane distances; the extremes over
+        // the interval bound them from below / above)
+        enter = fmax(enter, tnearLo);
+        leave = fmin(leave, tfarHi);
+      }
+      // a component that may vanish puts no constraint (conservative)
+    }
+    return enter <= leave;
+  };
+  for (int g = 0; g < S.nGate; ++g)
+    if (box_may_hit(S.gate[g].bmin, S.gate[g].bmax))
+      my |= 1u << g;
+  for (int s = 0; s < S.nSph; ++s)
+    if (box_may_hit(S.sphGate[s].bmin, S.sphGate[s].bmax))
+      my |= 1u << (B2PT_PRIM_SPH_SHIFT + s);
+  masks[id] = make_uint2(mx, my);
+}
+
 __global__ void __launch_bounds__(256)
   k_accumulate(float4* __restrict__ color, const float4* __restrict__ rad, int nPixels, int samplesPerView, int nViews,
                unsigned long long* nanCounter)
@@ -931,6 +1118,31 @@ cudaError_t launch_bounce(const LaunchCfg& cfg, bool primary, int mode, const B2
 }
 
 int warps_per_block() { return kWarps; }
+
+#ifdef B2PT_DEBUG_HIST
+extern "C" int b2pt_debug_hist(unsigned long long* out, int reset)
+{
+  if (out && cudaMemcpyFromSymbol(out, g_debugHist, sizeof(g_debugHist)) != cudaSuccess)
+    return -1;
+  if (reset)
+  {
+    unsigned long long z[64] = {};
+    if (cudaMemcpyToSymbol(g_debugHist, z, sizeof(z)) != cudaSuccess)
+      return -1;
+  }
+  return 0;
+}
+#endif
+
+cudaError_t launch_primary_prep(const B2SmallScene& S, const B2Camera& cam, const B2Camera* views, int nViews,
+                                int tilesPerView, uint2* masks, B2PrimQuad* pq, cudaStream_t stream)
+{
+  const int64_t n = (int64_t)nViews * tilesPerView;
+  if (n <= 0)
+    return cudaSuccess;
+  k_primary_prep<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(S, cam, views, nViews, tilesPerView, masks, pq);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_accumulate(float4* color, const float4* rad, int nPixels, int samplesPerView, int nViews,
                               unsigned long long* nanCounter, cudaStream_t stream)

@@ -37,6 +37,10 @@ cudaError_t launch_bounce(const LaunchCfg& cfg, bool primary, int mode, const B2
 // cluster; stops early when the queue runs empty.
 cudaError_t launch_tail_loop(const B2Camera& cam, const B2SmallScene* small, const B2BvhScene* bvh,
                              const B2Lights& lights, const B2RenderArgs& args, cudaStream_t stream);
+// Primary-ray specialisation of small scenes: per (view, tile of 32 pixels) candidate masks + per-view quad constants
+// (views == nullptr: the one camera `cam`).
+cudaError_t launch_primary_prep(const B2SmallScene& S, const B2Camera& cam, const B2Camera* views, int nViews,
+                                int tilesPerView, uint2* masks, B2PrimQuad* pq, cudaStream_t stream);
 // K4: color[p] += sum_b rad[b*N + p] in sample order; counts NaN samples into *nanCounter.
 int warps_per_block();
 cudaError_t launch_accumulate(float4* color, const float4* rad, int nPixels, int samplesPerView, int nViews,

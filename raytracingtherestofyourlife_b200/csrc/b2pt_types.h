@@ -175,6 +175,23 @@ struct alignas(16) B2SmallScene
   B2GateBox sphGate[B2PT_SMALL_MAX_SPH]; // the spheres' own leaf boxes (centre +- radius, unpadded; sphere_gate)
 };
 
+// Primary-ray specialisation of the small-scene trace (k_primary_prep -> k_trace<PRIMARY>).  Every primary ray of a
+// view leaves the camera position, so the origin-dependent part of the Lagae-Dutre test is a per-quad constant:
+// T = o - v00, Qv = T x E01, tnum = E03 . Qv (Surface.h:62-66, 100-101), evaluated once per view with the same float
+// operations quad_hit performs per ray (bit-identical), plus tn1 = (|T|_1 + secC1) of the second-triangle shortcut.
+struct alignas(16) B2PrimQuad // 32 B, by slot of B2SmallScene::quads
+{
+  float T[3];
+  float tnum;
+  float Qv[3];
+  float tn1;
+};
+// ... and the 32 rays of a tile (32 consecutive pixels) span a narrow frustum, so the set of quads any of them can hit
+// is a per-tile constant: a bit mask computed once per view by k_primary_prep with a rigorous superset rule
+// (DESIGN.md "primary tiles").  x: bit v = filter visit index v (B2SmallScene::visitSlot); y: bit g = gate box g of a
+// boxed quad (g < B2PT_SMALL_MAX_GATES), bit 24+s = sphere s.
+#define B2PT_PRIM_SPH_SHIFT 24
+
 // BVH scene: global-memory primitive arrays + 32-byte nodes (see b2pt_bvh.h)
 struct B2BvhNode // 32 B, two 16-byte loads
 {
@@ -227,6 +244,10 @@ struct B2RenderArgs
   // view-batched render (b2pt_render_views): sample slot b of the batch belongs to view b / sppPerView of this
   // array and is that view's sample b % sppPerView; nullptr = single view, the camera kernel parameter
   const B2Camera* views;
+  // primary-ray specialisation (small scenes, nPixels % 32 == 0; nullptr = generic path): per view, tilesPerView
+  // candidate masks and B2PT_SMALL_MAX_QUADS per-quad constants
+  const uint2* primMask;
+  const B2PrimQuad* primQuads;
   int64_t binStride;    // numWarps * regionCap
   int64_t nPaths;       // paths in this batch (N * samplesInBatch)
   int32_t numWarps;
@@ -236,6 +257,8 @@ struct B2RenderArgs
   int32_t depth;        // this bounce
   int32_t maxDepth;
   int32_t sppPerView;
+  int32_t tilesPerView; // nPixels / 32
+  int32_t nLightQuads, nLightSph; // light counts (reference-stream mode: draws a dead pixel still burns per depth)
   uint32_t seedOffset;
   uint32_t flags;
 };
