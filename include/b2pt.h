@@ -53,6 +53,7 @@ typedef enum b2pt_status
 #define B2PT_FLAG_VIEWS_NORMALIZE 0x100u     /* b2pt_render_views: apply b2pt_normalize's sqrt(de_nan(sum)/spp) to every view */
 #define B2PT_FLAG_VIEWS_PNM16 0x200u         /* b2pt_render_views: rgbaOut receives uint16_t[nViews*W*H*3], the integers of b2pt_read_pnm16 */
 #define B2PT_FLAG_NO_PRIMARY_MASKS 0x400u    /* trace primary rays with the generic per-ray candidate filter instead of the per-tile candidate masks (A/B parity checks) */
+#define B2PT_FLAG_SPLIT_BOUNCE 0x800u        /* small scenes: two kernels per bounce (k_trace + k_shade with a ray queue in between) instead of the one-kernel pipeline (A/B runs; BVH scenes always use it) */
 #define B2PT_FLAG_NO_AA 0x10u               /* do not use the axis-aligned quad specialisation (A/B parity checks) */
 
 typedef struct b2pt_stats
@@ -107,6 +108,10 @@ int b2pt_build_bvh_ex(b2pt_ctx* ctx, uint32_t flags);
  * 880-960) and the RayGen constructor (:438-476).  fovDeg in (0,180]; W,H > 0 else B2PT_ERR_BAD_VALUE. */
 int b2pt_set_camera(b2pt_ctx* ctx, const float pos[3], const float lookAt[3], const float up[3], float fovDeg, int W,
                     int H);
+/* Upper bound, in bytes, of the device memory the context's batch buffers (ray records in flight) may take; 0 = 0.85
+ * of the memory that is free at the context's first render.  The reference has no counterpart (its buffers are sized
+ * by the canvas, MapperPathTracer.cxx:94-149); results never depend on it. */
+int b2pt_set_memory_budget(b2pt_ctx* ctx, int64_t bytes);
 /* seeds[i] = i + seedOffset (0 = the reference, MapperPathTracer.cxx:265-267). */
 int b2pt_seed(b2pt_ctx* ctx, uint32_t seedOffset);
 

@@ -28,6 +28,7 @@ FLAG_GPU_LBVH = 0x80
 FLAG_VIEWS_NORMALIZE = 0x100
 FLAG_VIEWS_PNM16 = 0x200
 FLAG_NO_PRIMARY_MASKS = 0x400
+FLAG_SPLIT_BOUNCE = 0x800
 
 ERR_BAD_VALUE, ERR_CUDA, ERR_STATE, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 
@@ -61,6 +62,7 @@ SIGNATURES = {
     "b2pt_build_bvh": (_i32, [_vp]),
     "b2pt_set_camera": (_i32, [_vp, _vp, _vp, _vp, _f, _i32, _i32]),
     "b2pt_seed": (_i32, [_vp, C.c_uint32]),
+    "b2pt_set_memory_budget": (_i32, [_vp, _i64]),
     "b2pt_render": (_i32, [_vp, _i32, _i32, C.c_uint32]),
     "b2pt_render_range": (_i32, [_vp, _i32, _i32, _i32, C.c_uint32]),
     "b2pt_render_views": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, C.c_uint32, _vp]),
@@ -231,6 +233,9 @@ class Context:
     def set_camera(self, cam):
         _check(lib().b2pt_set_camera(self._h, _p(cam.pos), _p(cam.lookAt), _p(cam.up), cam.fov, cam.W, cam.H))
         self.W, self.H = cam.W, cam.H
+
+    def set_memory_budget(self, nbytes):
+        _check(lib().b2pt_set_memory_budget(self._h, nbytes))
 
     def seed(self, offset):
         _check(lib().b2pt_seed(self._h, offset))

@@ -160,11 +160,24 @@ struct b2pt_ctx
   static constexpr int kMaxSets = 4;
   struct BatchBufs
   {
-    DevBuf<uint4> queue[3];  // the compact ray queue (three 16-byte planes)
-    DevBuf<uint4> bins[3];   // sorted hit queues: 4 bins x pathsPerBatch records per plane
-    DevBuf<uint32_t> binCode;
-    DevBuf<uint32_t> regionCounts; // qCount[numWarps] + binCount[4*numWarps]
+    DevBuf<uint4> queue[3];   // two-kernel pipeline: the compact ray queue (three 16-byte planes)
+    DevBuf<uint4> bins[2][3]; // sorted hit bins: 4 bins x pathsPerBatch records per plane; the one-kernel pipeline
+                              // ping-pongs between two sets, the two-kernel pipeline uses set 0
+    DevBuf<uint32_t> binCode[2];
+    DevBuf<uint32_t> regionCounts; // qCount[numWarps] + two sets of bin counts [4*numWarps]
     DevBuf<float4> rad;
+    void release_all()
+    {
+      for (auto& q : queue)
+        q.release();
+      for (auto& set : bins)
+        for (auto& p : set)
+          p.release();
+      for (auto& c : binCode)
+        c.release();
+      regionCounts.release();
+      rad.release();
+    }
   } bufs[kMaxSets];
   cudaStream_t extra[kMaxSets] = {}; // own non-blocking streams of sets 1.. (set 0 runs on `stream`)
   cudaEvent_t evFork = nullptr, evJoin[kMaxSets] = {}, evAcc[kMaxSets] = {};
@@ -187,7 +200,8 @@ struct b2pt_ctx
   int64_t sceneVersion = 0;
   uint64_t sceneHash = 0;
   int tailDepthCached = 0, loopDepthCached = 0;
-  int64_t batchTarget = 0; // default paths per batch, chosen at the first render from the free memory
+  int64_t memBudget = 0;  // 0.85 of the memory free at the first render: bounds the default batch size
+  int64_t userBudget = 0; // b2pt_set_memory_budget (0 = automatic)
 
   b2pt_stats stats{};
   bool statsPending = false;
@@ -426,15 +440,7 @@ void b2pt_destroy(b2pt_ctx* ctx)
   ctx->dNodes.release(), ctx->dSlots.release(), ctx->dLeafSph.release(), ctx->dQuads.release(), ctx->dSph.release(), ctx->dGates.release();
   ctx->colorOwn.release();
   for (auto& b : ctx->bufs)
-  {
-    for (auto& p : b.queue)
-      p.release();
-    for (auto& p : b.bins)
-      p.release();
-    b.binCode.release();
-    b.regionCounts.release();
-    b.rad.release();
-  }
+    b.release_all();
   ctx->counters.release(), ctx->binTotals.release(), ctx->seeds.release(), ctx->nanCounter.release();
   ctx->dViews.release(), ctx->viewColor.release(), ctx->pnm.release(), ctx->primMask.release(), ctx->primQuads.release(); // (DevBuf's destructor would free them too)
   if (ctx->evFork)
@@ -1085,6 +1091,16 @@ int b2pt_set_camera(b2pt_ctx* ctx, const float pos[3], const float lookAt[3], co
   return B2PT_OK;
 }
 
+int b2pt_set_memory_budget(b2pt_ctx* ctx, int64_t bytes)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (bytes < 0)
+    return fail(B2PT_ERR_BAD_VALUE, "negative memory budget");
+  ctx->userBudget = bytes;
+  return B2PT_OK;
+}
+
 int b2pt_seed(b2pt_ctx* ctx, uint32_t seedOffset)
 {
   if (int rc = bind(ctx))
@@ -1156,7 +1172,11 @@ static int64_t tail_loop_rays()
   return 24576; // ~break-even between one 8-SM cluster pass and a full-grid launch pair
 }
 
-static int64_t batch_target_paths(b2pt_ctx* ctx)
+// Bytes of batch buffers per path in flight: one-kernel pipeline = two sets of four bins (52 B records) + radiance
+// 16 B; two-kernel pipeline = ray queue 48 B + one set of bins + radiance.
+static double bytes_per_path(bool fused) { return fused ? 2 * 4 * 52.0 + 16.0 : 48.0 + 4 * 52.0 + 16.0; }
+
+static int64_t batch_target_paths(b2pt_ctx* ctx, bool fused)
 {
   const char* e = getenv("B2PT_BATCH_PATHS");
   if (e)
@@ -1165,20 +1185,20 @@ static int64_t batch_target_paths(b2pt_ctx* ctx)
     if (v > 0)
       return v;
   }
-  // 128 Mi paths per batch, four batches in flight: 272 B per path (queue 48 B + 4 bins x 52 B + radiance 16 B) =
-  // 36.5 GB per batch, 146 GB of the 180 GB HBM: the card is there to be used, and larger batches amortise the tail of
-  // the bounce loop (measured per 1024-spp step: 16 Mi 238.3 ms, 32 Mi 227.2, 64 Mi 220.3, 96 Mi 217.8, 128 Mi 215.1).
-  // Halved until the four sets fit 0.85 of the free memory.  Folding the four bins of a region into two arrays
-  // (168 B per path) was measured: each kernel 1.4 % slower, a wash at equal memory.
-  // Decided once per context (before its own buffers exist).
-  if (ctx->batchTarget > 0)
-    return ctx->batchTarget;
-  int64_t target = (int64_t)1 << 27;
-  size_t freeB = 0, totalB = 0;
-  if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess)
-    while (target > ((int64_t)1 << 20) && (double)target * 272.0 * (double)overlap_sets() > 0.85 * (double)freeB)
-      target >>= 1;
-  ctx->batchTarget = target;
+  // Up to 128 Mi paths per batch, four batches in flight, inside a memory budget: 0.85 of the memory that is free when
+  // the context first renders (before its own buffers exist), or what b2pt_set_memory_budget says.  The card's HBM is
+  // there to be used -- larger batches amortise the tail of the bounce loop (measured per 1024-spp step with the
+  // two-kernel pipeline: 16 Mi 238.3 ms, 32 Mi 227.2, 64 Mi 220.3, 96 Mi 217.8, 128 Mi 215.1) -- but a co-tenant can
+  // cap it.  Folding the four bins of a region into two arrays was measured: each kernel 1.4 % slower.
+  if (ctx->memBudget <= 0)
+  {
+    size_t freeB = 0, totalB = 0;
+    ctx->memBudget = cudaMemGetInfo(&freeB, &totalB) == cudaSuccess ? (int64_t)(0.85 * (double)freeB) : ((int64_t)32 << 30);
+  }
+  const int64_t budget = ctx->userBudget > 0 ? ctx->userBudget : ctx->memBudget;
+  int64_t target = (int64_t)((double)budget / (bytes_per_path(fused) * (double)overlap_sets()));
+  target = std::min<int64_t>(target, (int64_t)1 << 27);
+  target = std::max<int64_t>(target & ~(((int64_t)1 << 20) - 1), (int64_t)1 << 20); // whole Mi paths, at least one
   return target;
 }
 
@@ -1251,8 +1271,12 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     int64_t per = 1, viewsPerBatch = 0, B = 1, nBatches = 0, pathsPerBatch = 0, numWarps = 0, regionCap = 0, queueCap = 0;
     int nSets = 1;
   };
-  const int blocksPerSM = std::min(ctx->cfg.traceBlocksPerSM[0][ctx->useBvh ? 1 : 0],
-                                   ctx->cfg.shadeBlocksPerSM[0][ctx->useBvh ? 1 : 0]);
+  // Small scenes: one kernel per bounce (k_bounce); BVH scenes (and B2PT_FLAG_SPLIT_BOUNCE, for A/B runs): k_trace +
+  // k_shade per bounce with a ray queue in between.
+  const bool fused = !ctx->useBvh && !(flags & B2PT_FLAG_SPLIT_BOUNCE);
+  const int blocksPerSM = fused ? std::min(ctx->cfg.traceBlocksPerSM[1][0], ctx->cfg.bounceBlocksPerSM)
+                                : std::min(ctx->cfg.traceBlocksPerSM[0][ctx->useBvh ? 1 : 0],
+                                           ctx->cfg.shadeBlocksPerSM[0][ctx->useBvh ? 1 : 0]);
   const int wpb = b2pt::warps_per_block();
   auto make_plan = [&](int64_t target, int64_t setsMax) {
     Plan P;
@@ -1281,16 +1305,26 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     {
       b2pt_ctx::BatchBufs& bb = ctx->bufs[set];
       cudaError_t e = cudaSuccess;
+      if (fused) // buffers only the other pipeline needs go back first
+        for (auto& q : bb.queue)
+          q.release();
+      else
+      {
+        for (auto& p : bb.bins[1])
+          p.release();
+        bb.binCode[1].release();
+      }
       for (int p = 0; p < 3 && e == cudaSuccess; ++p)
       {
-        e = bb.queue[p].reserve((size_t)P.queueCap);
-        if (e == cudaSuccess)
-          e = bb.bins[p].reserve((size_t)P.queueCap * 4);
+        if (!fused)
+          e = bb.queue[p].reserve((size_t)P.queueCap);
+        for (int h = 0; h < (fused ? 2 : 1) && e == cudaSuccess; ++h)
+          e = bb.bins[h][p].reserve((size_t)P.queueCap * 4);
       }
+      for (int h = 0; h < (fused ? 2 : 1) && e == cudaSuccess; ++h)
+        e = bb.binCode[h].reserve((size_t)P.queueCap * 4);
       if (e == cudaSuccess)
-        e = bb.binCode.reserve((size_t)P.queueCap * 4);
-      if (e == cudaSuccess)
-        e = bb.regionCounts.reserve((size_t)P.numWarps * 5);
+        e = bb.regionCounts.reserve((size_t)P.numWarps * 9);
       if (e == cudaSuccess)
         e = bb.rad.reserve((size_t)P.pathsPerBatch);
       if (e != cudaSuccess)
@@ -1302,7 +1336,7 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
   // it since, the buffers no longer fit: give every set back and plan again with a LOCAL target -- halved while that
   // still shrinks the batches, then with fewer sets in flight -- until the allocation succeeds.  The context's own
   // target is left alone: the next render tries the full plan again.
-  int64_t target = batch_target_paths(ctx);
+  int64_t target = batch_target_paths(ctx, fused);
   int64_t setsMax = (flags & B2PT_FLAG_NO_OVERLAP) ? 1 : overlap_sets();
   Plan P = make_plan(target, setsMax);
   for (;;)
@@ -1315,11 +1349,7 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     cudaGetLastError(); // the allocation error is not sticky; clear it
     CU(cudaStreamSynchronize(ctx->stream));
     for (b2pt_ctx::BatchBufs& bb : ctx->bufs)
-    {
-      for (int p = 0; p < 3; ++p)
-        bb.queue[p].release(), bb.bins[p].release();
-      bb.binCode.release(), bb.regionCounts.release(), bb.rad.release();
-    }
+      bb.release_all();
     Plan Q = P;
     bool changed = false;
     while (!changed && !getenv("B2PT_BATCH_PATHS") && target > unitPaths && target > ((int64_t)1 << 16))
@@ -1392,8 +1422,11 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
       CU(cudaStreamWaitEvent(ctx->extra[k], ctx->evFork, 0));
   }
   int64_t launches = (refStream ? 1 : 0) + launches0;
-  int tailDepth = maxDepth; // bounces >= tailDepth run in tail mode; chosen after the first batch
-  int loopDepth = maxDepth; // bounces >= loopDepth (>= tailDepth) run inside one persistent cluster launch
+  // bounces >= tailDepth run in tail mode, bounces >= loopDepth (>= tailDepth) inside one persistent cluster launch;
+  // chosen after the first batch.  "Never" is maxDepth for the two-kernel pipeline and maxDepth + 1 for the one-kernel
+  // pipeline, whose closing pass is launch number maxDepth.
+  const int never = maxDepth + (fused ? 1 : 0);
+  int tailDepth = never, loopDepth = never;
   const int64_t tailKey[7] = { ctx->sceneVersion,  N, maxDepth, pathsPerBatch, (int64_t)flags, tail_rays_per_warp(),
                                tail_loop_rays() };
   const bool tailAllowed = nBatches > 1 && !(flags & B2PT_FLAG_NO_TAIL) && maxDepth > 2;
@@ -1419,12 +1452,12 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     A.depthTotals = ctx->counters.p + batch * maxDepth;
     A.binTotals = ctx->binTotals.p + batch * maxDepth * 4;
     A.rad = bb.rad.p;
-    A.bin0 = bb.bins[0].p, A.bin1 = bb.bins[1].p, A.bin2 = bb.bins[2].p;
-    A.binCode = bb.binCode.p;
+    for (int h = 0; h < 2; ++h)
+      A.bins[h] = { bb.bins[h][0].p, bb.bins[h][1].p, bb.bins[h][2].p, bb.binCode[h].p,
+                    bb.regionCounts.p + numWarps * (1 + 4 * h) };
     A.binStride = queueCap;
     A.q = { bb.queue[0].p, bb.queue[1].p, bb.queue[2].p };
     A.qCount = bb.regionCounts.p;
-    A.binCount = bb.regionCounts.p + numWarps;
     A.numWarps = (int32_t)numWarps;
     A.regionCap = (int32_t)regionCap;
     A.seeds = ctx->seeds.p;
@@ -1441,7 +1474,8 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     A.nLightSph = ctx->lights.nLightSph;
     A.seedOffset = ctx->seedOffset;
     A.flags = flags;
-    for (int depth = 0; depth < maxDepth; ++depth)
+    // fused: launches 0 (primary) .. maxDepth (the closing shade pass); split: bounces 0 .. maxDepth-1, two launches each
+    for (int depth = 0; depth < maxDepth + (fused ? 1 : 0); ++depth)
     {
       if (batch == 0 && depth <= b2pt_ctx::kProfDepths && depth <= profDepths)
       { // per-launch CUDA events of the first bounces of batch 0 (b2pt_get_bounce_profile)
@@ -1457,6 +1491,25 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
         mid = ctx->evMid[depth];
       }
       A.depth = depth;
+      const int mode = depth >= tailDepth ? b2pt::B2PT_BOUNCE_TAIL
+                                          : (depth == tailDepth - 1 ? b2pt::B2PT_BOUNCE_TO_GLOBAL : b2pt::B2PT_BOUNCE_REGIONS);
+      if (fused)
+      {
+        if (depth == 0)
+          CU(b2pt::launch_primary(ctx->cfg, ctx->cam, ctx->small, A, bs));
+        else if (depth >= loopDepth)
+        { // every remaining bounce and the closing pass in one cluster launch
+          CU(b2pt::launch_bounce_tail_loop(ctx->small, ctx->lights, A, bs));
+          ++launches;
+          break;
+        }
+        else
+          CU(b2pt::launch_bounce_fused(ctx->cfg, mode, ctx->small, ctx->lights, A, bs));
+        ++launches;
+        if (mid) // one launch per bounce: the whole bounce is reported as the "trace" stage
+          CU(cudaEventRecord(mid, bs));
+        continue;
+      }
       if (depth >= loopDepth)
       { // every remaining bounce in one cluster launch
         CU(b2pt::launch_tail_loop(ctx->cam, ctx->useBvh ? nullptr : &ctx->small, ctx->useBvh ? &ctx->bvh : nullptr,
@@ -1464,8 +1517,6 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
         ++launches;
         break;
       }
-      const int mode = depth >= tailDepth ? b2pt::B2PT_BOUNCE_TAIL
-                                          : (depth == tailDepth - 1 ? b2pt::B2PT_BOUNCE_TO_GLOBAL : b2pt::B2PT_BOUNCE_REGIONS);
       CU(b2pt::launch_bounce(ctx->cfg, depth == 0, mode, ctx->cam, ctx->useBvh ? nullptr : &ctx->small,
                              ctx->useBvh ? &ctx->bvh : nullptr, ctx->lights, A, bs, mid));
       launches += 2;
@@ -1482,7 +1533,7 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     ++launches;
     if (overlap)
       CU(cudaEventRecord(ctx->evAcc[set], bs));
-    if (batch == 0 && tailAllowed && tailDepth == maxDepth && !std::equal(tailKey, tailKey + 7, ctx->tailKey))
+    if (batch == 0 && tailAllowed && tailDepth == never && !std::equal(tailKey, tailKey + 7, ctx->tailKey))
     { // Tail mode for the remaining batches: from the first bounce that less than tailRaysPerWarp rays per region
       // enter, rays live in one flat global queue (k_trace TAIL).  Decided from the first batch's own counters: one
       // stream synchronisation per render.
@@ -1490,7 +1541,8 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
       std::vector<uint32_t> first((size_t)maxDepth);
       CU(cudaMemcpy(first.data(), ctx->counters.p, sizeof(uint32_t) * (size_t)maxDepth, cudaMemcpyDeviceToHost));
       const int64_t threshold = numWarps * tail_rays_per_warp();
-      for (int d = 1; d < maxDepth; ++d) // first[d-1] = rays entering bounce d
+      // (the one-kernel pipeline bins bounce 0 per region, so its first global-bin launch is bounce 1: tailDepth >= 2)
+      for (int d = fused ? 2 : 1; d < maxDepth; ++d) // first[d-1] = rays entering bounce d
         if ((int64_t)first[(size_t)d - 1] < threshold)
         {
           tailDepth = d;
@@ -1524,8 +1576,9 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
   ctx->stats.batches = (int32_t)nBatches;
   ctx->stats.samplesPerBatch = (int32_t)B;
   ctx->stats.tracePath = ctx->useBvh ? 1 : 0;
-  ctx->stats.tailDepth = tailDepth;
-  ctx->stats.loopDepth = loopDepth;
+  ctx->stats.tailDepth = std::min(tailDepth, maxDepth);
+  ctx->stats.loopDepth = std::min(loopDepth, maxDepth);
+  ctx->stats.tracePath = ctx->useBvh ? 1 : 0;
   ctx->stats.bvhNodes = ctx->bvhNodes;
   ctx->stats.tracedQuads = ctx->tracedQuads;
   ctx->stats.tracedSpheres = ctx->tracedSph;
@@ -1595,7 +1648,7 @@ int b2pt_render_views(b2pt_ctx* ctx, int nViews, const float* views, int W, int 
     ctx->haveCamera = savedHave;
     ctx->colorExt = savedExt;
   };
-  bool perView = !(spp > 0 && N * spp <= std::min<int64_t>(batch_target_paths(ctx), 0xfffffff0LL));
+  bool perView = !(spp > 0 && N * spp <= std::min<int64_t>(batch_target_paths(ctx, true), 0xfffffff0LL));
   if (!perView)
   { // whole views fit a batch: (view, sample, pixel) is one flat index space, one set of launches per batch of views
     // (pageable source: the copy is staged before the call returns, so `cams` may go out of scope)

@@ -49,6 +49,14 @@ __device__ __forceinline__ f3 cross3(f3 a, f3 b)
 // vtkm::RMagnitude = RSqrt(MagnitudeSquared), host form 1/sqrt (not rsqrtf: keeps CPU bit-parity)
 __device__ __forceinline__ float rmag3(f3 a) { return 1.0f / sqrtf(dot3(a, a)); }
 __device__ __forceinline__ f3 unit3(f3 a) { return a * rmag3(a); } // vec3.h:38-42, vtkm::Normalize
+// Radiance-only arithmetic (pdf values, cosines, attenuation: numbers that are multiplied into the throughput and never
+// decide a hit, a branch or a direction) uses the hardware reciprocal / reciprocal square root (MUFU, <= 2 ulp) instead
+// of the IEEE-rounded sequences: the reference itself evaluates these in a mix of Float32 and Float64 (vtkm::Pi()), so
+// they were never bit-comparable; signs, exact zeros, infinities and NaNs -- everything the NaN-poisoning semantics and
+// the comparisons depend on -- are preserved.
+__device__ __forceinline__ float rmag3_fast(f3 a) { return rsqrtf(dot3(a, a)); }
+__device__ __forceinline__ f3 unit3_fast(f3 a) { return a * rmag3_fast(a); }
+__device__ __forceinline__ float div_fast(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ f3 denan3(f3 c) // PdfWorklet.h:39-45
 {
   if (!(c.x == c.x))
@@ -929,8 +937,8 @@ __device__ __forceinline__ float quad_pdf_value(const B2LightQuad& L, f3 o, f3 v
     return 0.f;
   f3 n = quad_normal(L.geo, v);
   float dist2 = t * t * dot3(v, v);
-  float cosine = fabsf(dot3(v, n) * rmag3(v));
-  return dist2 / (cosine * L.area);
+  float cosine = fabsf(dot3(v, n) * rmag3_fast(v));
+  return div_fast(dist2, cosine * L.area);
 }
 // PdfWorklet.h:333-347 (SpherePDFWorklet::pdf_value)
 __device__ __forceinline__ float sphere_pdf_value(const B2LightSphere& L, f3 o, f3 v)
@@ -940,9 +948,9 @@ __device__ __forceinline__ float sphere_pdf_value(const B2LightSphere& L, f3 o, 
   if (!sphere_accept(c, L.r, o, v, 0.001f, FLT_MAX, t))
     return 0.f;
   f3 co = c - o;
-  float cos_theta_max = sqrtf(1.f - L.r * L.r / dot3(co, co));
-  float solid_angle = (float)(B2PT_TWO_PI_D * (double)(1.f - cos_theta_max));
-  return 1.f / solid_angle;
+  float cos_theta_max = sqrtf(1.f - div_fast(L.r * L.r, dot3(co, co)));
+  float solid_angle = 6.28318530717958647692f * (1.f - cos_theta_max);
+  return div_fast(1.f, solid_angle);
 }
 
 // EmitWorklet.h:152-226 (DielectricWorklet): returns the specular direction (reflect or refract).
@@ -1061,13 +1069,13 @@ __device__ __forceinline__ BounceResult shade_lambert(const B2Lights& lights, co
     if (l < lights.nLightSph)
       sum += lights.weight * sphere_pdf_value(lights.ls[l], hit.p, g);
   // ScatterWorklet.h:20-28, 52-58, 95-110
-  f3 ug = unit3(g);
-  float cosw = dot3(ug, unit3(hit.n));
+  f3 ug = unit3_fast(g);
+  float cosw = dot3(ug, unit3_fast(hit.n));
   float value = (cosw > 0.f) ? cosw * B2PT_INV_PI_F : 0.f;
   float pdf_val = 0.5f * sum + 0.5f * value;
   float c2 = dot3(hit.n, ug);
   float spdf = (c2 < 0.f) ? 0.f : c2 * B2PT_INV_PI_F;
-  float sctr = spdf / pdf_val;
+  float sctr = div_fast(spdf, pdf_val);
   T = mk3(T.x * (hit.alb.x * sctr), T.y * (hit.alb.y * sctr), T.z * (hit.alb.z * sctr));
   o = hit.p;
   d = g;

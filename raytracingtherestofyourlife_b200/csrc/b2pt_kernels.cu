@@ -41,6 +41,9 @@ constexpr int kMinBlocksPerSM = B2PT_MIN_BLOCKS; // register cap = 65536 / (256 
 #define B2PT_TRACE_MIN_BLOCKS 4
 #endif
 constexpr int kTraceMinBlocksPerSM = B2PT_TRACE_MIN_BLOCKS;
+// the deep tail of a batch runs inside one launch of a single thread-block cluster (k_tail_loop, k_bounce_tail_loop)
+constexpr int kTailCluster = 8;
+constexpr int kTailBlock = 512;
 
 struct PeerPtrs
 {
@@ -392,20 +395,20 @@ __device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhS
       const unsigned mine = bin == 0 ? b0 : (bin == 1 ? b1 : (bin == 2 ? b2 : b3));
       const uint32_t cnt = bin == 0 ? cnt0 : (bin == 1 ? cnt1 : (bin == 2 ? cnt2 : cnt3));
       const int64_t j = (int64_t)bin * A.binStride + base + cnt + __popc(mine & lt);
-      A.bin0[j] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
-      A.bin1[j] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
-      A.bin2[j] = make_uint4(__float_as_uint(T.z), pid, rng, __float_as_uint(closest));
-      A.binCode[j] = (uint32_t)code;
+      A.bins[0].p0[j] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
+      A.bins[0].p1[j] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
+      A.bins[0].p2[j] = make_uint4(__float_as_uint(T.z), pid, rng, __float_as_uint(closest));
+      A.bins[0].code[j] = (uint32_t)code;
     }
     if (!TAIL)
       cnt0 += __popc(b0), cnt1 += __popc(b1), cnt2 += __popc(b2), cnt3 += __popc(b3);
   }
   if (!TAIL && lane == 0)
   {
-    A.binCount[0 * A.numWarps + w] = cnt0;
-    A.binCount[1 * A.numWarps + w] = cnt1;
-    A.binCount[2 * A.numWarps + w] = cnt2;
-    A.binCount[3 * A.numWarps + w] = cnt3;
+    A.bins[0].count[0 * A.numWarps + w] = cnt0;
+    A.bins[0].count[1 * A.numWarps + w] = cnt1;
+    A.bins[0].count[2 * A.numWarps + w] = cnt2;
+    A.bins[0].count[3 * A.numWarps + w] = cnt3;
   }
 }
 
@@ -500,20 +503,20 @@ __device__ __forceinline__ void trace_body(const B2Camera& cam, const SceneT& S,
       const unsigned mine = bin == 0 ? b0 : (bin == 1 ? b1 : (bin == 2 ? b2 : b3));
       const uint32_t cnt = bin == 0 ? cnt0 : (bin == 1 ? cnt1 : (bin == 2 ? cnt2 : cnt3));
       const int64_t j = (int64_t)bin * A.binStride + base + cnt + __popc(mine & lt);
-      A.bin0[j] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
-      A.bin1[j] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
-      A.bin2[j] = make_uint4(__float_as_uint(T.z), pid, rng, __float_as_uint(t));
-      A.binCode[j] = (uint32_t)code;
+      A.bins[0].p0[j] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
+      A.bins[0].p1[j] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
+      A.bins[0].p2[j] = make_uint4(__float_as_uint(T.z), pid, rng, __float_as_uint(t));
+      A.bins[0].code[j] = (uint32_t)code;
     }
     if (!TAIL)
       cnt0 += __popc(b0), cnt1 += __popc(b1), cnt2 += __popc(b2), cnt3 += __popc(b3);
   }
   if (!TAIL && lane == 0)
   {
-    A.binCount[0 * A.numWarps + w] = cnt0;
-    A.binCount[1 * A.numWarps + w] = cnt1;
-    A.binCount[2 * A.numWarps + w] = cnt2;
-    A.binCount[3 * A.numWarps + w] = cnt3;
+    A.bins[0].count[0 * A.numWarps + w] = cnt0;
+    A.bins[0].count[1 * A.numWarps + w] = cnt1;
+    A.bins[0].count[2 * A.numWarps + w] = cnt2;
+    A.bins[0].count[3 * A.numWarps + w] = cnt3;
   }
 }
 
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(kBlock, kTraceMinBlocksPerSM)
   {
     if (w < A.numWarps && lane == 0)
       for (int k = 0; k < 4; ++k)
-        A.binCount[k * A.numWarps + w] = 0;
+        A.bins[0].count[k * A.numWarps + w] = 0;
     return;
   }
   __shared__ StageArea<SceneT> sStage;
@@ -580,7 +583,7 @@ __device__ __forceinline__ void shade_body(const SceneT& S, const B2Lights& LT, 
   for (int k = 0; k < 4; ++k)
   {
     const int64_t nk =
-      TAIL_IN ? (int64_t)__ldcg(&A.binTotals[depth * 4 + k]) : (int64_t)A.binCount[k * A.numWarps + w];
+      TAIL_IN ? (int64_t)__ldcg(&A.binTotals[depth * 4 + k]) : (int64_t)A.bins[0].count[k * A.numWarps + w];
     const int64_t binBase = (int64_t)k * A.binStride + base;
     // TAIL_IN: tile t of bin k goes to warp (t + k*tailWarps/4) mod tailWarps
     const int64_t wk = TAIL_IN ? (w + tailWarps - (k * tailWarps) / 4) % tailWarps : 0;
@@ -592,22 +595,22 @@ __device__ __forceinline__ void shade_body(const SceneT& S, const B2Lights& LT, 
       uint32_t pid = 0, rng = 0;
       if (!TAIL_IN && i + 32 < nk)
       {
-        prefetch_l2(A.bin0 + binBase + i + 32);
-        prefetch_l2(A.bin1 + binBase + i + 32);
-        prefetch_l2(A.bin2 + binBase + i + 32);
-        prefetch_l2(A.binCode + binBase + i + 32);
+        prefetch_l2(A.bins[0].p0 + binBase + i + 32);
+        prefetch_l2(A.bins[0].p1 + binBase + i + 32);
+        prefetch_l2(A.bins[0].p2 + binBase + i + 32);
+        prefetch_l2(A.bins[0].code + binBase + i + 32);
       }
       if (i < nk)
       {
         const int64_t j = binBase + i;
-        const uint4 a = __ldcg(A.bin0 + j), b = __ldcg(A.bin1 + j), c = __ldcg(A.bin2 + j);
+        const uint4 a = __ldcg(A.bins[0].p0 + j), b = __ldcg(A.bins[0].p1 + j), c = __ldcg(A.bins[0].p2 + j);
         o = mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
         d = mk3(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
         T = mk3(__uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(c.x));
         pid = c.y;
         rng = c.z;
         Hit hit;
-        fill_hit(S, (int)__ldcg(A.binCode + j), o, d, __uint_as_float(c.w), hit);
+        fill_hit(S, (int)__ldcg(A.bins[0].code + j), o, d, __uint_as_float(c.w), hit);
         f3 L;
         BounceResult r = (k == 0) ? shade_specular(LT, hit, o, d, rng) : shade_lambert(LT, hit, o, d, T, rng, A.flags, L);
         if (r == BOUNCE_CONTINUE && lastDepth)
@@ -661,7 +664,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM)
     uint32_t nAny = 0;
     if (w < A.numWarps)
       nAny =
-        A.binCount[w] | A.binCount[A.numWarps + w] | A.binCount[2 * A.numWarps + w] | A.binCount[3 * A.numWarps + w];
+        A.bins[0].count[w] | A.bins[0].count[A.numWarps + w] | A.bins[0].count[2 * A.numWarps + w] | A.bins[0].count[3 * A.numWarps + w];
     if (!__syncthreads_or(nAny != 0))
     { // nothing binned for any warp of this CTA: its queue regions become empty, no staging needed
       if (!GLOBAL_OUT && w < A.numWarps && lane == 0)
@@ -678,13 +681,204 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM)
   shade_body<SceneT, TAIL_IN, GLOBAL_OUT>(S, LT, A, A.depth, w, lane, tailWarps);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Small scenes: ONE kernel per bounce.  k_bounce at depth d shades the hits the trace of bounce d-1 binned (bin set
+// (d-1)&1: K3, warp-uniform per bin), traces the scattered ray at once (K2, the ray never leaves the registers) and
+// bins the new hit into set d&1 (the sorting half of K5).  Nothing dies in the shade stage (every binned hit scatters),
+// so there is no compaction and no ray queue between the stages: a survivor costs one 52-byte record read and one
+// written per bounce where the two-kernel pipeline moved four (bin + queue, 200 B).  d == maxDepth is the closing
+// launch: the hits of the last bounce are shaded (their attenuation can still poison the sum, their draws still
+// advance a reference-stream state) and finish with e[D-1] = 0.
+// IN_GLOBAL / OUT_GLOBAL: the tail of the bounce loop keeps its records in flat global bins (counters in binTotals,
+// one warp-aggregated atomicAdd per bin and tile), see k_trace.
+template <class SceneT, bool IN_GLOBAL, bool OUT_GLOBAL>
+__device__ __forceinline__ void bounce_body(const SceneT& S, const B2Lights& LT, const B2RenderArgs& A, int depth, int w,
+                                            int lane, int64_t tailWarps)
+{
+  const B2Bins& Bi = A.bins[(depth - 1) & 1];
+  const B2Bins& Bo = A.bins[depth & 1];
+  const int64_t baseIn = IN_GLOBAL ? 0 : (int64_t)w * A.regionCap;
+  const int64_t baseOut = OUT_GLOBAL ? 0 : (int64_t)w * A.regionCap;
+  const bool closing = depth >= A.maxDepth;
+  const bool refStream = (A.flags & B2PT_FLAG_REFERENCE_STREAM_DEV) != 0;
+  const unsigned lt = (1u << lane) - 1u;
+  uint32_t cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
+  uint32_t processed = 0;
+  for (int k = 0; k < 4; ++k)
+  {
+    const int64_t nk =
+      IN_GLOBAL ? (int64_t)__ldcg(&A.binTotals[(depth - 1) * 4 + k]) : (int64_t)Bi.count[k * A.numWarps + w];
+    const int64_t binBase = (int64_t)k * A.binStride + baseIn;
+    // IN_GLOBAL: tile t of bin k goes to warp (t + k*tailWarps/4) mod tailWarps (the bins of a nearly empty tail land
+    // on different warps)
+    const int64_t wk = IN_GLOBAL ? (w + tailWarps - (k * tailWarps) / 4) % tailWarps : 0;
+    for (int64_t i0 = IN_GLOBAL ? wk * 32 : 0; i0 < nk; i0 += IN_GLOBAL ? tailWarps * 32 : 32)
+    {
+      const int64_t i = i0 + lane;
+      int bin = -1;
+      f3 o, d, T;
+      uint32_t pid = 0, rng = 0;
+      float t = 0.f;
+      int code = B2PT_MISS;
+      if (!IN_GLOBAL && i + 32 < nk)
+      {
+        prefetch_l2(Bi.p0 + binBase + i + 32);
+        prefetch_l2(Bi.p1 + binBase + i + 32);
+        prefetch_l2(Bi.p2 + binBase + i + 32);
+        prefetch_l2(Bi.code + binBase + i + 32);
+      }
+      if (i < nk)
+      {
+        const int64_t j = binBase + i;
+        const uint4 a = __ldcg(Bi.p0 + j), b = __ldcg(Bi.p1 + j), c = __ldcg(Bi.p2 + j);
+        o = mk3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
+        d = mk3(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
+        T = mk3(__uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(c.x));
+        pid = c.y;
+        rng = c.z;
+        Hit hit;
+        fill_hit(S, (int)__ldcg(Bi.code + j), o, d, __uint_as_float(c.w), hit);
+        f3 L;
+        const BounceResult r =
+          (k == 0) ? shade_specular(LT, hit, o, d, rng) : shade_lambert(LT, hit, o, d, T, rng, A.flags, L);
+        if (r == BOUNCE_DONE) // zero-throughput kill (never in reference-stream mode)
+          finish_path(A, pid, L, rng, false, 0);
+        else if (closing) // still alive after maxDepth bounces: e[D-1] = 0 (MapperPathTracer.cxx:328-331)
+          finish_path(A, pid, T * 0.f, rng, refStream, 0);
+        else
+        {
+          code = closest_hit(S, o, d, 0.001f, FLT_MAX, t);
+          if (code == B2PT_MISS)
+            finish_path(A, pid, T * 0.f, rng, refStream, A.maxDepth - depth); // a[d]=1, e[d]=0
+          else
+          {
+            const int kind = hit_kind(S, code);
+            if (kind == 1)
+            { // DiffuseLightWorklet::emit: front face only, but the normal was already flipped -> two-sided
+              Hit h2;
+              fill_hit(S, code, o, d, t, h2);
+              const f3 em = (dot3(h2.n, d) < 0.0f) ? h2.alb : mk3(0.f, 0.f, 0.f);
+              finish_path(A, pid, mul3(T, em), rng, refStream, A.maxDepth - depth);
+            }
+            else
+            {
+              uint32_t peek = rng;
+              bin = (kind == 2) ? 0 : draw_which(peek);
+            }
+          }
+        }
+      }
+      if (closing)
+        continue; // (warp-uniform) nothing is binned by the closing launch
+      const unsigned b0 = __ballot_sync(0xffffffffu, bin == 0), b1 = __ballot_sync(0xffffffffu, bin == 1);
+      const unsigned b2 = __ballot_sync(0xffffffffu, bin == 2), b3 = __ballot_sync(0xffffffffu, bin == 3);
+      if (OUT_GLOBAL)
+      {
+        uint32_t got = 0;
+        if (lane < 4)
+        {
+          const unsigned bk = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
+          if (bk)
+            got = atomicAdd(&A.binTotals[depth * 4 + lane], (uint32_t)__popc(bk));
+        }
+        cnt0 = __shfl_sync(0xffffffffu, got, 0), cnt1 = __shfl_sync(0xffffffffu, got, 1);
+        cnt2 = __shfl_sync(0xffffffffu, got, 2), cnt3 = __shfl_sync(0xffffffffu, got, 3);
+      }
+      if (bin >= 0)
+      {
+        const unsigned mine = bin == 0 ? b0 : (bin == 1 ? b1 : (bin == 2 ? b2 : b3));
+        const uint32_t cnt = bin == 0 ? cnt0 : (bin == 1 ? cnt1 : (bin == 2 ? cnt2 : cnt3));
+        const int64_t j = (int64_t)bin * A.binStride + baseOut + cnt + __popc(mine & lt);
+        Bo.p0[j] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
+        Bo.p1[j] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
+        Bo.p2[j] = make_uint4(__float_as_uint(T.z), pid, rng, __float_as_uint(t));
+        Bo.code[j] = (uint32_t)code;
+      }
+      if (!OUT_GLOBAL)
+        cnt0 += __popc(b0), cnt1 += __popc(b1), cnt2 += __popc(b2), cnt3 += __popc(b3);
+      processed += (uint32_t)min((int64_t)32, nk - i0);
+    }
+  }
+  if (lane == 0)
+  {
+    if (!OUT_GLOBAL && !closing)
+    {
+      Bo.count[0 * A.numWarps + w] = cnt0;
+      Bo.count[1 * A.numWarps + w] = cnt1;
+      Bo.count[2 * A.numWarps + w] = cnt2;
+      Bo.count[3 * A.numWarps + w] = cnt3;
+    }
+    // statistics: rays entering bounce `depth` (b2pt_get_stats: segments; the host's tail-mode decision)
+    if (processed && !closing)
+      atomicAdd(&A.depthTotals[depth - 1], processed);
+  }
+}
+
+template <class SceneT, bool IN_GLOBAL, bool OUT_GLOBAL>
+__global__ void __launch_bounds__(kBlock, kTraceMinBlocksPerSM)
+  k_bounce(const __grid_constant__ SceneT scene, const __grid_constant__ B2Lights lights,
+           const __grid_constant__ B2RenderArgs A)
+{
+  static_assert(OUT_GLOBAL || !IN_GLOBAL, "tail bounces keep their records in the global bins");
+  const int w = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int64_t tailWarps = (int64_t)gridDim.x * kWarps;
+  if (!IN_GLOBAL)
+  {
+    const B2Bins& Bi = A.bins[(A.depth - 1) & 1];
+    uint32_t nAny = 0;
+    if (w < A.numWarps)
+      nAny = Bi.count[w] | Bi.count[A.numWarps + w] | Bi.count[2 * A.numWarps + w] | Bi.count[3 * A.numWarps + w];
+    if (!__syncthreads_or(nAny != 0))
+    { // nothing binned for any warp of this CTA: its regions stay empty, no staging needed
+      if (!OUT_GLOBAL && w < A.numWarps && lane == 0)
+        for (int k = 0; k < 4; ++k)
+          A.bins[A.depth & 1].count[k * A.numWarps + w] = 0;
+      return;
+    }
+  }
+  __shared__ StageArea<SceneT> sStage;
+  const SceneT& S = stage_scene(scene, sStage);
+  const B2Lights& LT = stage_lights(lights, sStage);
+  __syncthreads();
+  if (!IN_GLOBAL && w >= A.numWarps)
+    return;
+  bounce_body<SceneT, IN_GLOBAL, OUT_GLOBAL>(S, LT, A, A.depth, w, lane, tailWarps);
+}
+
+// The deep tail of the one-kernel pipeline in ONE launch (see k_tail_loop): every remaining bounce and the closing
+// shade pass inside a single thread-block cluster, one hardware barrier per bounce.
+template <class SceneT>
+__global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kTailBlock, 1)
+  k_bounce_tail_loop(const __grid_constant__ SceneT scene, const __grid_constant__ B2Lights lights,
+                     const __grid_constant__ B2RenderArgs A)
+{
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int w = blockIdx.x * (kTailBlock / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int64_t tailWarps = (int64_t)gridDim.x * (kTailBlock / 32);
+  __shared__ StageArea<SceneT> sStage;
+  const SceneT& S = stage_scene(scene, sStage);
+  const B2Lights& LT = stage_lights(lights, sStage);
+  __syncthreads();
+  for (int depth = A.depth; depth <= A.maxDepth; ++depth)
+  {
+    const uint32_t* tot = A.binTotals + (depth - 1) * 4;
+    const uint32_t nIn = __ldcg(tot) | __ldcg(tot + 1) | __ldcg(tot + 2) | __ldcg(tot + 3);
+    if (nIn == 0)
+      break; // uniform over the cluster: nobody writes these counters any more
+    bounce_body<SceneT, true, true>(S, LT, A, depth, w, lane, tailWarps);
+    __threadfence();
+    cluster.sync();
+  }
+}
+
 // The deep tail in ONE launch: a single thread-block cluster (kTailCluster CTAs = SMs) runs every remaining bounce
 // of the batch, trace and shade phases separated by the cluster's hardware barrier, and stops as soon as the queue
 // is empty.  Used from the first bounce that fewer than ~24 K rays enter: there a full-grid launch pair costs
 // more in launch latency and per-CTA set-up than the work itself.  Queue/bin data and the counters are read with
 // .cg loads (they were written by other SMs earlier in this launch).
-constexpr int kTailCluster = 8;
-constexpr int kTailBlock = 512;
 template <class SceneT>
 __global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kTailBlock, 1)
   k_tail_loop(const __grid_constant__ B2Camera cam, const __grid_constant__ SceneT scene,
@@ -1060,7 +1254,8 @@ cudaError_t query_launch_cfg(LaunchCfg* cfg)
       (e = occ((const void*)k_trace<true, B2BvhScene, false>, cfg->traceBlocksPerSM[1][1])) != cudaSuccess ||
       (e = occ((const void*)k_trace<false, B2BvhScene, false>, cfg->traceBlocksPerSM[0][1])) != cudaSuccess ||
       (e = occ((const void*)k_shade<B2SmallScene, false, false>, cfg->shadeBlocksPerSM[0][0])) != cudaSuccess ||
-      (e = occ((const void*)k_shade<B2BvhScene, false, false>, cfg->shadeBlocksPerSM[0][1])) != cudaSuccess)
+      (e = occ((const void*)k_shade<B2BvhScene, false, false>, cfg->shadeBlocksPerSM[0][1])) != cudaSuccess ||
+      (e = occ((const void*)k_bounce<B2SmallScene, false, false>, cfg->bounceBlocksPerSM)) != cudaSuccess)
     return e;
   return cudaSuccess;
 }
@@ -1093,6 +1288,41 @@ static cudaError_t launch_bounce_t(const LaunchCfg& cfg, bool primary, int mode,
     k_shade<SceneT, false, true><<<grid, kBlock, 0, stream>>>(S, lights, args);
   else
     k_shade<SceneT, false, false><<<grid, kBlock, 0, stream>>>(S, lights, args);
+  return cudaGetLastError();
+}
+
+// One-kernel pipeline of small scenes.  Bounce 0 = k_trace<PRIMARY> (raygen + closest hit, bins into set 0); bounce
+// d >= 1 = k_bounce (shade the hits of bounce d-1, trace, bin into set d&1); d == maxDepth = the closing shade pass.
+cudaError_t launch_primary(const LaunchCfg& cfg, const B2Camera& cam, const B2SmallScene& S, const B2RenderArgs& args,
+                           cudaStream_t stream)
+{
+  const int grid = (args.numWarps + kWarps - 1) / kWarps;
+  k_trace<true, B2SmallScene, false><<<grid, kBlock, 0, stream>>>(cam, S, args);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bounce_fused(const LaunchCfg& cfg, int mode, const B2SmallScene& S, const B2Lights& lights,
+                                const B2RenderArgs& args, cudaStream_t stream)
+{
+  if (args.depth < 1)
+    return cudaErrorInvalidValue;
+  const int grid = (args.numWarps + kWarps - 1) / kWarps;
+  const int tailGrid = std::max(1, std::min(grid, cfg.numSMs * 2));
+  if (mode == B2PT_BOUNCE_TAIL)
+    k_bounce<B2SmallScene, true, true><<<tailGrid, kBlock, 0, stream>>>(S, lights, args);
+  else if (mode == B2PT_BOUNCE_TO_GLOBAL)
+    k_bounce<B2SmallScene, false, true><<<grid, kBlock, 0, stream>>>(S, lights, args);
+  else
+    k_bounce<B2SmallScene, false, false><<<grid, kBlock, 0, stream>>>(S, lights, args);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bounce_tail_loop(const B2SmallScene& S, const B2Lights& lights, const B2RenderArgs& args,
+                                    cudaStream_t stream)
+{
+  if (args.depth < 2)
+    return cudaErrorInvalidValue;
+  k_bounce_tail_loop<B2SmallScene><<<kTailCluster, kTailBlock, 0, stream>>>(S, lights, args);
   return cudaGetLastError();
 }
 

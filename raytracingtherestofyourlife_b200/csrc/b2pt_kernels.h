@@ -14,6 +14,7 @@ struct LaunchCfg
   int numSMs;
   int traceBlocksPerSM[2][2]; // [primary][bvh]
   int shadeBlocksPerSM[2][2];
+  int bounceBlocksPerSM; // k_bounce (one-kernel pipeline of small scenes)
 };
 
 // Queries occupancy of the bounce kernels on the current device.
@@ -33,6 +34,15 @@ enum
 cudaError_t launch_bounce(const LaunchCfg& cfg, bool primary, int mode, const B2Camera& cam, const B2SmallScene* small,
                           const B2BvhScene* bvh, const B2Lights& lights, const B2RenderArgs& args,
                           cudaStream_t stream, cudaEvent_t betweenStages = nullptr);
+// One-kernel pipeline of small scenes (b2pt_kernels.cu k_bounce): bounce 0, bounce args.depth >= 1 (the closing shade
+// pass when args.depth == args.maxDepth) in one of the three modes above, and every bounce from args.depth >= 2
+// (global bins) to the closing pass inside one cluster launch.
+cudaError_t launch_primary(const LaunchCfg& cfg, const B2Camera& cam, const B2SmallScene& S, const B2RenderArgs& args,
+                           cudaStream_t stream);
+cudaError_t launch_bounce_fused(const LaunchCfg& cfg, int mode, const B2SmallScene& S, const B2Lights& lights,
+                                const B2RenderArgs& args, cudaStream_t stream);
+cudaError_t launch_bounce_tail_loop(const B2SmallScene& S, const B2Lights& lights, const B2RenderArgs& args,
+                                    cudaStream_t stream);
 // Every bounce from args.depth (>= 1, global-queue mode) to args.maxDepth-1 in one launch of a single thread-block
 // cluster; stops early when the queue runs empty.
 cudaError_t launch_tail_loop(const B2Camera& cam, const B2SmallScene* small, const B2BvhScene* bvh,

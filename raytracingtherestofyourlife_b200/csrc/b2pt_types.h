@@ -221,21 +221,31 @@ struct B2Queue
   uint4* p2; // tb pathId rng aux
 };
 
+// One set of the four sorted hit bins: bin k (0 specular hits, 1..3 lambertian hits by sampling strategy), entry
+// [k*binStride + w*regionCap + i], i < count[k*numWarps + w] (tail mode: flat [k*binStride + i], counts in
+// binTotals); a record is three 16-byte planes (ox oy oz dx) (dy dz Tr Tg) (Tb pathId rng t) plus the primitive code.
+struct B2Bins
+{
+  uint4* p0;
+  uint4* p1;
+  uint4* p2;
+  uint32_t* code;
+  uint32_t* count; // [4*numWarps]
+};
+
 // Launch arguments of the bounce kernels.  The ray queue and the four sorted hit bins are statically
 // partitioned into one REGION per persistent warp (numWarps regions of regionCap entries, regionCap a multiple
 // of 32): warp w consumes and refills only region w, with register counters -- no atomics on the data path.
+// Two pipelines share them:
+//  * small scenes, ONE kernel per bounce (k_bounce): the records binned by the trace of bounce d-1 sit in bin set
+//    (d-1)&1, are shaded and traced again, and the new hits go to bin set d&1 -- no ray queue at all;
+//  * BVH scenes, two kernels per bounce (k_trace, k_shade): k_trace bins into set 0, k_shade reads set 0 and compacts
+//    the survivors into the ray queue q.
 struct B2RenderArgs
 {
-  B2Queue q;            // compact ray queue: entry [w*regionCap + i], i < qCount[w]
-  // sorted hit bins written by k_trace, read by k_shade: bin k (0 specular hits, 1..3 lambertian hits by
-  // sampling strategy), entry [k*binStride + w*regionCap + i], i < binCount[k*numWarps + w]; a record is three
-  // 16-byte planes (ox oy oz dx) (dy dz Tr Tg) (Tb pathId rng t) plus the primitive code
-  uint4* bin0;
-  uint4* bin1;
-  uint4* bin2;
-  uint32_t* binCode;
+  B2Queue q;            // BVH pipeline: compact ray queue, entry [w*regionCap + i], i < qCount[w]
+  B2Bins bins[2];
   uint32_t* qCount;     // [numWarps]
-  uint32_t* binCount;   // [4*numWarps]
   uint32_t* depthTotals; // [maxDepth] of this batch: rays entering bounce d+1 (statistics; in tail mode also the
                          // append counter of the global ray queue)
   uint32_t* binTotals;   // [maxDepth*4] of this batch: tail mode, records appended to global bin k at bounce d

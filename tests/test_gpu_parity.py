@@ -205,27 +205,31 @@ def test_axis_aligned_specialisation_is_bit_identical(gpu_ctx, b2pt):
     gpu_ctx.render(1, 1, 0)
 
 
-def test_tail_mode_is_bit_identical(gpu_ctx, b2pt, oracle, monkeypatch):
-    """Deep bounces switch to one flat global queue with atomically appended bins (k_trace/k_shade TAIL); the
-    processing order changes, the paths and the sample-order accumulation do not."""
+@pytest.mark.parametrize("pipeline", ["one_kernel", "two_kernels"])
+def test_tail_mode_is_bit_identical(gpu_ctx, b2pt, oracle, monkeypatch, pipeline):
+    """Deep bounces switch to flat global bins with atomically appended records (k_bounce / k_trace / k_shade TAIL
+    instantiations); the processing order changes, the paths and the sample-order accumulation do not.  Both
+    pipelines: one kernel per bounce (default for small scenes) and k_trace + k_shade (B2PT_FLAG_SPLIT_BOUNCE)."""
     W, spp, depth = 256, 16, 50
+    pf = 0 if pipeline == "one_kernel" else b2pt.FLAG_SPLIT_BOUNCE
+    first = 2 if pipeline == "one_kernel" else 1  # the one-kernel pipeline always bins bounce 0 per region
     monkeypatch.setenv("B2PT_BATCH_PATHS", str(W * W * 4))  # 4 batches: the tail depth is chosen after the first
     gpu_ctx.set_camera(b2pt.Camera(W, W))
-    gpu_ctx.render(spp, depth, b2pt.FLAG_NO_TAIL)
+    gpu_ctx.render(spp, depth, pf | b2pt.FLAG_NO_TAIL)
     a, sa = gpu_ctx.read_color(), gpu_ctx.stats()
-    # default thresholds; everything after bounce 0 in tail mode; everything after bounce 0 inside the persistent
-    # cluster launch; no persistent launch at all
+    # default thresholds; everything after the first bounce(s) in tail mode; everything after them inside the
+    # persistent cluster launch; no persistent launch at all
     for per_warp, loop_rays in (("512", "24576"), ("100000", "24576"), ("100000", "100000000"), ("256", "0")):
         monkeypatch.setenv("B2PT_TAIL_RAYS_PER_WARP", per_warp)
         monkeypatch.setenv("B2PT_TAIL_LOOP_RAYS", loop_rays)
-        gpu_ctx.render(spp, depth, 0)
+        gpu_ctx.render(spp, depth, pf)
         b, sb = gpu_ctx.read_color(), gpu_ctx.stats()
-        assert sa.batches == sb.batches == 4 and sa.tailDepth == depth and 1 <= sb.tailDepth < depth
+        assert sa.batches == sb.batches == 4 and sa.tailDepth == depth and first <= sb.tailDepth < depth
         assert sb.tailDepth <= sb.loopDepth <= depth
         assert sa.segments == sb.segments and sa.nanSamples == sb.nanSamples
         assert np.array_equal(a, b, equal_nan=True)
         if loop_rays == "100000000":
-            assert sb.tailDepth == 1 and sb.loopDepth == 1
+            assert sb.tailDepth == first and sb.loopDepth == first
         if loop_rays == "0":
             assert sb.loopDepth == depth
     monkeypatch.delenv("B2PT_TAIL_RAYS_PER_WARP")
@@ -234,9 +238,9 @@ def test_tail_mode_is_bit_identical(gpu_ctx, b2pt, oracle, monkeypatch):
     assert sa.segments == ost.segments
     # reference-stream mode (one sample per batch) through the tail as well
     gpu_ctx.set_camera(b2pt.Camera(64, 64))
-    gpu_ctx.render(6, 30, b2pt.FLAG_REFERENCE_STREAM | b2pt.FLAG_NO_TAIL)
+    gpu_ctx.render(6, 30, pf | b2pt.FLAG_REFERENCE_STREAM | b2pt.FLAG_NO_TAIL)
     c, sc = gpu_ctx.read_color(), gpu_ctx.stats()
-    gpu_ctx.render(6, 30, b2pt.FLAG_REFERENCE_STREAM)
+    gpu_ctx.render(6, 30, pf | b2pt.FLAG_REFERENCE_STREAM)
     d, sd = gpu_ctx.read_color(), gpu_ctx.stats()
     assert sd.tailDepth < 30 and sc.segments == sd.segments and np.array_equal(c, d, equal_nan=True)
 
@@ -263,18 +267,22 @@ def test_two_stream_batch_overlap_is_bit_identical(gpu_ctx, b2pt, monkeypatch):
 
 
 def test_stage_profile_reports_both_launches(gpu_ctx, b2pt):
-    """b2pt_get_stage_profile: CUDA-event durations of the k_trace and k_shade launch of the first bounces and the
-    rays entering them; consistent with b2pt_get_bounce_profile and with the segment count."""
+    """b2pt_get_stage_profile: CUDA-event durations of the launches of the first bounces and the rays entering them;
+    consistent with b2pt_get_bounce_profile and with the segment count.  Two-kernel pipeline: the k_trace and the
+    k_shade launch; one-kernel pipeline: the whole bounce is the first figure, the second is the empty event gap."""
     gpu_ctx.set_camera(b2pt.Camera(256, 256))
-    gpu_ctx.render(8, 12, b2pt.FLAG_NO_OVERLAP)
-    st = gpu_ctx.stats()
-    prof = gpu_ctx.stage_profile(16)
-    both = gpu_ctx.bounce_profile(16)
-    assert len(prof) == len(both) == 11  # depth - 1 bracketed bounces
-    assert prof[0][2] == 256 * 256 * 8 and all(prof[k][2] >= prof[k + 1][2] for k in range(len(prof) - 1))
-    assert sum(p[2] for p in prof) <= st.segments
-    for (tr, sh, rays), (ms, rays2) in zip(prof, both):
-        assert rays == rays2 and tr > 0 and sh > 0 and abs((tr + sh) - ms) < 0.02
+    for flags, split in ((b2pt.FLAG_NO_OVERLAP, False), (b2pt.FLAG_NO_OVERLAP | b2pt.FLAG_SPLIT_BOUNCE, True)):
+        gpu_ctx.render(8, 12, flags)
+        st = gpu_ctx.stats()
+        prof = gpu_ctx.stage_profile(16)
+        both = gpu_ctx.bounce_profile(16)
+        assert len(prof) == len(both) == 11  # depth - 1 bracketed bounces
+        assert prof[0][2] == 256 * 256 * 8 and all(prof[k][2] >= prof[k + 1][2] for k in range(len(prof) - 1))
+        assert sum(p[2] for p in prof) <= st.segments
+        assert st.launches == (12 + 1 + 2 if not split else 2 * 12 + 2)  # + k_primary_prep + k_accumulate
+        for (tr, sh, rays), (ms, rays2) in zip(prof, both):
+            assert rays == rays2 and tr > 0 and abs((tr + sh) - ms) < 0.02
+            assert sh > 0 if split else 0 <= sh < 0.01
 
 
 def test_edge_cases(gpu_ctx, b2pt):
