@@ -54,6 +54,7 @@ typedef enum b2pt_status
 #define B2PT_FLAG_VIEWS_PNM16 0x200u         /* b2pt_render_views: rgbaOut receives uint16_t[nViews*W*H*3], the integers of b2pt_read_pnm16 */
 #define B2PT_FLAG_NO_PRIMARY_MASKS 0x400u    /* trace primary rays with the generic per-ray candidate filter instead of the per-tile candidate masks (A/B parity checks) */
 #define B2PT_FLAG_SPLIT_BOUNCE 0x800u        /* small scenes: two kernels per bounce (k_trace + k_shade with a ray queue in between) instead of the one-kernel pipeline (A/B runs; BVH scenes always use it) */
+#define B2PT_FLAG_BINARY_BVH 0x1000u         /* BVH scenes: traverse the binary tree (32-byte nodes) instead of the 8-wide compressed tree collapsed from it (A/B runs) */
 #define B2PT_FLAG_NO_AA 0x10u               /* do not use the axis-aligned quad specialisation (A/B parity checks) */
 
 typedef struct b2pt_stats
@@ -199,6 +200,11 @@ int b2pt_scene_cornell(float* pts /*3*89*/, int64_t* quadIds /*5*22*/, int64_t* 
 int b2pt_scene_spheres(int64_t nSpheres, float* pts, int64_t* quadIds, int64_t* spherePt, float* sphereR,
                        int64_t* matIdxQuad, int64_t* texIdxQuad, int64_t* matIdxSph, int64_t* texIdxSph, int* matType,
                        int* texType, float* tex);
+
+/* Host-only self-check of the BVH builders (no GPU): the configs[3]-style scene with nSpheres spheres through the binned-SAH
+ * builder and the collapse into 8-wide compressed nodes, both validated structurally (every primitive reachable exactly
+ * once, boxes nested, quantised boxes conservative).  stats4 = { binary nodes, binary depth, wide nodes, wide depth }. */
+int b2pt_bvh_selfcheck(int64_t nSpheres, int64_t* stats4);
 
 int b2pt_version(void);
 

@@ -29,6 +29,7 @@ FLAG_VIEWS_NORMALIZE = 0x100
 FLAG_VIEWS_PNM16 = 0x200
 FLAG_NO_PRIMARY_MASKS = 0x400
 FLAG_SPLIT_BOUNCE = 0x800
+FLAG_BINARY_BVH = 0x1000
 
 ERR_BAD_VALUE, ERR_CUDA, ERR_STATE, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 
@@ -86,6 +87,7 @@ SIGNATURES = {
     "b2pt_allreduce": (_i32, [C.POINTER(_vp), _i32]),
     "b2pt_scene_cornell": (_i32, [_vp] * 11),
     "b2pt_scene_spheres": (_i32, [_i64] + [_vp] * 11),
+    "b2pt_bvh_selfcheck": (_i32, [_i64, _vp]),
 }
 
 
@@ -168,6 +170,13 @@ class Scene:
                                         _p(matType), _p(texType), _p(tex)))
         return Scene(pts, quadIds, sphPt, sphR, mq, tq, ms, ts, matType, texType, tex,
                      lightQuadIds=[[0, n, n + 1, n + 2, n + 3]], lightSphPt=[0], lightSphR=[sphR[0]])
+
+
+def bvh_selfcheck(n_spheres):
+    """Host-only: (binary nodes, binary depth, wide nodes, wide depth) of the validated trees over n random spheres."""
+    st = np.zeros(4, np.int64)
+    _check(lib().b2pt_bvh_selfcheck(n_spheres, _p(st)))
+    return tuple(int(x) for x in st)
 
 
 def plan_batches(units, unit_paths, max_paths_per_batch=1 << 27, sets=4):

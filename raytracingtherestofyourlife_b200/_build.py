@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("B2PT_LIB") or os.path.join(HERE, "libb2pt.so")  # B2PT_LIB: experiment builds
 SOURCES = ["b2pt_kernels.cu", "b2pt_api.cu", "b2pt_lbvh.cu", "b2pt_scene.cpp"]
-HEADERS = ["b2pt_device.cuh", "b2pt_kernels.h", "b2pt_types.h", "b2pt_bvh.h", "b2pt_lbvh.h", "../../include/b2pt.h"]
+HEADERS = ["b2pt_device.cuh", "b2pt_kernels.h", "b2pt_types.h", "b2pt_bvh.h", "b2pt_wide.h", "b2pt_lbvh.h", "../../include/b2pt.h"]
 NVCC = os.environ.get("B2PT_NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"  # $CXX in this image points at a g++ without OpenMP/specs; use the system one
 

@@ -19,6 +19,7 @@
 #include "b2pt_kernels.h"
 #include "b2pt_lbvh.h"
 #include "b2pt_types.h"
+#include "b2pt_wide.h"
 
 namespace
 {
@@ -139,6 +140,7 @@ struct b2pt_ctx
   B2SmallScene small{};
   B2BvhScene bvh{};
   DevBuf<B2BvhNode> dNodes;
+  DevBuf<uint4> dWide; // 8-wide compressed nodes, 5 x uint4 each
   DevBuf<int32_t> dSlots;
   DevBuf<float4> dLeafSph;
   DevBuf<B2Quad> dQuads;
@@ -437,7 +439,7 @@ void b2pt_destroy(b2pt_ctx* ctx)
   for (cudaStream_t st : ctx->extra)
     if (st)
       cudaStreamSynchronize(st);
-  ctx->dNodes.release(), ctx->dSlots.release(), ctx->dLeafSph.release(), ctx->dQuads.release(), ctx->dSph.release(), ctx->dGates.release();
+  ctx->dNodes.release(), ctx->dWide.release(), ctx->dSlots.release(), ctx->dLeafSph.release(), ctx->dQuads.release(), ctx->dSph.release(), ctx->dGates.release();
   ctx->colorOwn.release();
   for (auto& b : ctx->bufs)
     b.release_all();
@@ -615,7 +617,7 @@ int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t*
 
 static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
 {
-  ctx->builtFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH);
+  ctx->builtFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH | B2PT_FLAG_BINARY_BVH);
   // Drop bit-identical duplicate quads: a later copy computes the same t and loses the strict t<tmax
   // comparison (Surface.h:178-179), so removing it cannot change any result.
   std::vector<int32_t> keptQuads;
@@ -1010,6 +1012,49 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
       return fail(B2PT_ERR_STATE, "BVH validation failed: %zu box violations, %zu of %zu slots reached once", bad, once,
                   nSlots);
   }
+  // The traversal kernels walk the 8-wide compressed tree collapsed from the binary one (b2pt_wide.h); primSlots and
+  // leafSph are rewritten in its leaf order.  B2PT_FLAG_BINARY_BVH keeps the binary tree (A/B runs).
+  ctx->bvh.wide = nullptr;
+  ctx->bvh.nWide = 0;
+  ctx->bvh.wideDepth = 0;
+  if (!(flags & B2PT_FLAG_BINARY_BVH) && nNodes > 0)
+  {
+    const size_t nSlots = treeQuads.size() + ctx->sph.size();
+    if (nodes.empty())
+    { // device-built tree: bring it to the host for the collapse
+      nodes.resize(nNodes);
+      slots.resize(nSlots);
+      CU(cudaMemcpy(nodes.data(), ctx->dNodes.p, nNodes * sizeof(B2BvhNode), cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(slots.data(), ctx->dSlots.p, nSlots * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    b2pt::WideBuildResult wr;
+    if (!b2pt::collapse_to_wide(nodes, slots, ctx->quads, ctx->sph, sceneAbs, wr) || wr.slots.size() != nSlots)
+      return fail(B2PT_ERR_STATE, "collapsing the BVH into 8-wide nodes failed");
+    if (wr.maxDepth > B2PT_WIDE_STACK)
+      return fail(B2PT_ERR_UNSUPPORTED, "8-wide BVH is %d levels deep (limit %d); use B2PT_FLAG_BINARY_BVH", wr.maxDepth,
+                  B2PT_WIDE_STACK);
+    if (getenv("B2PT_VALIDATE_BVH"))
+    {
+      std::string why;
+      if (!b2pt::validate_wide(wr, ctx->quads, ctx->sph, why))
+        return fail(B2PT_ERR_STATE, "8-wide BVH validation failed: %s", why.c_str());
+    }
+    static_assert(sizeof(B2WideNode) == 80, "B2WideNode is five 16-byte chunks");
+    std::vector<float4> leafSph(nSlots, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (size_t i = 0; i < nSlots; ++i)
+      if (wr.slots[i] < 0)
+      {
+        const B2Sphere& sp = ctx->sph[(size_t)(~wr.slots[i])];
+        leafSph[i] = make_float4(sp.c[0], sp.c[1], sp.c[2], sp.r);
+      }
+    CU(ctx->dWide.reserve(wr.nodes.size() * 5));
+    CU(cudaMemcpy(ctx->dWide.p, wr.nodes.data(), wr.nodes.size() * sizeof(B2WideNode), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->dSlots.p, wr.slots.data(), nSlots * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->dLeafSph.p, leafSph.data(), nSlots * sizeof(float4), cudaMemcpyHostToDevice));
+    ctx->bvh.wide = ctx->dWide.p;
+    ctx->bvh.nWide = (int32_t)wr.nodes.size();
+    ctx->bvh.wideDepth = wr.maxDepth;
+  }
   ctx->bvh.nodes = ctx->dNodes.p;
   ctx->bvh.primSlots = ctx->dSlots.p;
   ctx->bvh.leafSph = ctx->dLeafSph.p;
@@ -1031,7 +1076,7 @@ int b2pt_build_bvh_ex(b2pt_ctx* ctx, uint32_t flags)
   if (!ctx->haveScene)
     return fail(B2PT_ERR_STATE, "b2pt_build_bvh before b2pt_set_scene");
   if (int rc = build_trace_structures(
-        ctx, flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH)))
+        ctx, flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH | B2PT_FLAG_BINARY_BVH)))
     return rc;
   ctx->haveBvh = true;
   return B2PT_OK;
@@ -1244,7 +1289,7 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     return fail(B2PT_ERR_BAD_VALUE, "REFERENCE_STREAM renders samples from 0 (one persistent stream per pixel)");
   // MapperPathTracer::RenderCellsImpl builds its acceleration structures on every call (:275-276); here
   // they are rebuilt only when the scene or the build-affecting flags changed.
-  const uint32_t buildFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH);
+  const uint32_t buildFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH | B2PT_FLAG_BINARY_BVH);
   if (!ctx->haveBvh || ctx->builtFlags != buildFlags)
   {
     if (int rc = build_trace_structures(ctx, buildFlags))
@@ -1275,7 +1320,7 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
   // k_shade per bounce with a ray queue in between.
   const bool fused = !ctx->useBvh && !(flags & B2PT_FLAG_SPLIT_BOUNCE);
   const int blocksPerSM = fused ? std::min(ctx->cfg.traceBlocksPerSM[1][0], ctx->cfg.bounceBlocksPerSM)
-                                : std::min(ctx->cfg.traceBlocksPerSM[0][ctx->useBvh ? 1 : 0],
+                                : std::min(ctx->cfg.traceBlocksPerSM[0][ctx->useBvh ? (ctx->bvh.wide ? 2 : 1) : 0],
                                            ctx->cfg.shadeBlocksPerSM[0][ctx->useBvh ? 1 : 0]);
   const int wpb = b2pt::warps_per_block();
   auto make_plan = [&](int64_t target, int64_t setsMax) {
@@ -1586,6 +1631,57 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
   ctx->pendingCounters = nBatches * maxDepth;
   ctx->pendingMaxDepth = maxDepth;
   ctx->pendingPathsPerBatch = pathsPerBatch;
+  return B2PT_OK;
+}
+
+// Host-only self-check of the tree builders on the configs[3]-style scene (no GPU): binary binned-SAH tree, collapse
+// into 8-wide compressed nodes, structural validation of both.
+int b2pt_bvh_selfcheck(int64_t nSpheres, int64_t* stats4)
+{
+  if (nSpheres < 1 || nSpheres > 4000000 || !stats4)
+    return fail(B2PT_ERR_BAD_VALUE, "b2pt_bvh_selfcheck: bad argument");
+  const size_t n = (size_t)nSpheres;
+  std::vector<float> pts(3 * (n + 8)), sphR(n), tex(12);
+  std::vector<int64_t> quadIds(10), sphPt(n), mq(2), tq(2), ms(n), ts(n);
+  std::vector<int> matType(5), texType(5);
+  if (int rc = b2pt_scene_spheres(nSpheres, pts.data(), quadIds.data(), sphPt.data(), sphR.data(), mq.data(), tq.data(),
+                                  ms.data(), ts.data(), matType.data(), texType.data(), tex.data()))
+    return fail(rc, "b2pt_scene_spheres failed");
+  std::vector<B2Quad> quads(2);
+  std::vector<B2Sphere> sph(n);
+  auto P = [&](int64_t i) -> H3 { return { pts[3 * (size_t)i], pts[3 * (size_t)i + 1], pts[3 * (size_t)i + 2] }; };
+  float sceneAbs = 0.f;
+  for (int q = 0; q < 2; ++q)
+  {
+    std::memset(&quads[(size_t)q], 0, sizeof(B2Quad));
+    const int64_t* id = quadIds.data() + 5 * q;
+    precompute_quad(quads[(size_t)q], P(id[1]), P(id[2]), P(id[3]), P(id[4]));
+    quads[(size_t)q].prim = q;
+  }
+  for (size_t k = 0; k < n; ++k)
+  {
+    std::memset(&sph[k], 0, sizeof(B2Sphere));
+    hst(sph[k].c, P((int64_t)k));
+    sph[k].r = sphR[k];
+    for (int c = 0; c < 3; ++c)
+      sceneAbs = std::fmax(sceneAbs, std::fabs(sph[k].c[c]) + sph[k].r);
+  }
+  std::vector<B2BvhNode> nodes;
+  std::vector<int32_t> slots;
+  const std::vector<int32_t> treeQuads = { 0, 1 };
+  int binDepth = 0;
+  if (!b2pt::build_bvh(quads, treeQuads, sph, nodes, slots, &binDepth))
+    return fail(B2PT_ERR_UNSUPPORTED, "binary tree does not fit the index packing");
+  b2pt::WideBuildResult wr;
+  if (!b2pt::collapse_to_wide(nodes, slots, quads, sph, sceneAbs, wr) || wr.slots.size() != n + 2)
+    return fail(B2PT_ERR_STATE, "collapse failed");
+  std::string why;
+  if (!b2pt::validate_wide(wr, quads, sph, why))
+    return fail(B2PT_ERR_STATE, "8-wide BVH validation failed: %s", why.c_str());
+  stats4[0] = (int64_t)nodes.size();
+  stats4[1] = binDepth;
+  stats4[2] = (int64_t)wr.nodes.size();
+  stats4[3] = wr.maxDepth;
   return B2PT_OK;
 }
 

@@ -259,7 +259,8 @@ struct BvhBuilder
 };
 
 inline bool build_bvh(const std::vector<B2Quad>& quads, const std::vector<int32_t>& keptQuads,
-                      const std::vector<B2Sphere>& sph, std::vector<B2BvhNode>& nodes, std::vector<int32_t>& slots)
+                      const std::vector<B2Sphere>& sph, std::vector<B2BvhNode>& nodes, std::vector<int32_t>& slots,
+                      int* depthOut = nullptr)
 {
   BvhBuilder B(nodes, slots);
   std::vector<BvhItem>& items = B.items;
@@ -293,6 +294,8 @@ inline bool build_bvh(const std::vector<B2Quad>& quads, const std::vector<int32_
 #pragma omp single nowait
   B.build(0, items.size(), 0);
   nodes.resize((size_t)B.nodeCount.load());
+  if (depthOut)
+    *depthOut = B.maxDepth.load() + 1;
   return nodes.size() < ((size_t)1 << 24) && slots.size() < ((size_t)1 << 24);
 }
 

@@ -836,6 +836,232 @@ __device__ __forceinline__ void fill_bvh(const B2BvhScene& S, int best, f3 o, f3
   }
 }
 
+// ------------------------------------------------------------------------------ 8-wide compressed BVH (b2pt_wide.h)
+// Traversal state of one ray over the wide tree.  A GROUP is a set of children of one node that still have to be
+// visited: x = base index (childBase: inner children; primBase: primitive children), y = hit bits in visiting order
+// (bit b = slot b XOR octant, ascending b = approximately front to back) | the node's inner / primitive slot mask << 8
+// | kWidePrimGroup for a primitive group.  The stack holds groups of either kind.
+constexpr uint32_t kWidePrimGroup = 0x10000u;
+constexpr int kWideStack = B2PT_WIDE_STACK; // groups: at most one per level (build_trace_structures checks the depth)
+struct WideTrav
+{
+  uint32_t nx, ny; // current node group (ny & 0xff == 0: none)
+  uint32_t px, py; // current primitive group
+  int sp;
+};
+// bit index b = s ^ oct within each byte of the low 16 bits
+__device__ __forceinline__ uint32_t wide_perm(uint32_t m, uint32_t oct)
+{
+  if (oct & 1u)
+    m = ((m & 0x5555u) << 1) | ((m >> 1) & 0x5555u);
+  if (oct & 2u)
+    m = ((m & 0x3333u) << 2) | ((m >> 2) & 0x3333u);
+  if (oct & 4u)
+    m = ((m & 0x0f0fu) << 4) | ((m >> 4) & 0x0f0fu);
+  return m;
+}
+// Slab test of a node's eight quantised child boxes against the ray (culling arithmetic: FMA, conservative boxes).
+// Dequantisation: PRMT drops byte q into the mantissa of 2^23, giving the float 2^23 + q exactly, and one FMA evaluates
+// (2^23 + q) * (scale * inv) + (b - 2^23 * scale * inv): the constant's rounding error is at most half a quantisation
+// step in t, which the builder's extra step of widening covers (b2pt_wide.h).  Returns the hit bits by SLOT.
+__device__ __forceinline__ uint32_t wide_node_hits(const uint4* __restrict__ node, f3 inv, f3 od, float tmin, float closest,
+                                                   uint32_t& childBase, uint32_t& primBase, uint32_t& innerMask,
+                                                   uint32_t& primMask)
+{
+  const uint4 h0 = __ldg(node), h1 = __ldg(node + 1), qa = __ldg(node + 2), qb = __ldg(node + 3), qc = __ldg(node + 4);
+  const uint32_t e = h0.w;
+  childBase = h1.x;
+  primBase = h1.y;
+  innerMask = e >> 24;
+  primMask = h1.z & 0xffu;
+  const float six = __uint_as_float((e & 0xffu) << 23) * inv.x, siy = __uint_as_float(((e >> 8) & 0xffu) << 23) * inv.y,
+              siz = __uint_as_float(((e >> 16) & 0xffu) << 23) * inv.z;
+  const float bx = __fmaf_rn(-8388608.f, six, __fmaf_rn(__uint_as_float(h0.x), inv.x, -od.x));
+  const float by = __fmaf_rn(-8388608.f, siy, __fmaf_rn(__uint_as_float(h0.y), inv.y, -od.y));
+  const float bz = __fmaf_rn(-8388608.f, siz, __fmaf_rn(__uint_as_float(h0.z), inv.z, -od.z));
+  // near / far plane bytes by the direction's sign: qlo = (qa.x qa.y | qa.z qa.w | qb.x qb.y), qhi = (qb.z qb.w | qc.x
+  // qc.y | qc.z qc.w) for x | y | z
+  const bool ngx = inv.x < 0.f, ngy = inv.y < 0.f, ngz = inv.z < 0.f;
+  const uint32_t nx[2] = { ngx ? qb.z : qa.x, ngx ? qb.w : qa.y }, fx[2] = { ngx ? qa.x : qb.z, ngx ? qa.y : qb.w };
+  const uint32_t ny[2] = { ngy ? qc.x : qa.z, ngy ? qc.y : qa.w }, fy[2] = { ngy ? qa.z : qc.x, ngy ? qa.w : qc.y };
+  const uint32_t nz[2] = { ngz ? qc.z : qb.x, ngz ? qc.w : qb.y }, fz[2] = { ngz ? qb.x : qc.z, ngz ? qb.y : qc.w };
+  uint32_t hits = 0u;
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+  {
+    const int w = s >> 2;
+    const uint32_t sel = 0x7540u | (uint32_t)(s & 3);
+    const float tnx = __fmaf_rn(__uint_as_float(__byte_perm(nx[w], 0x4B000000u, sel)), six, bx);
+    const float tny = __fmaf_rn(__uint_as_float(__byte_perm(ny[w], 0x4B000000u, sel)), siy, by);
+    const float tnz = __fmaf_rn(__uint_as_float(__byte_perm(nz[w], 0x4B000000u, sel)), siz, bz);
+    const float tfx = __fmaf_rn(__uint_as_float(__byte_perm(fx[w], 0x4B000000u, sel)), six, bx);
+    const float tfy = __fmaf_rn(__uint_as_float(__byte_perm(fy[w], 0x4B000000u, sel)), siy, by);
+    const float tfz = __fmaf_rn(__uint_as_float(__byte_perm(fz[w], 0x4B000000u, sel)), siz, bz);
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, closest));
+    if (tn <= tf)
+      hits |= 1u << s;
+  }
+  return hits;
+}
+// Exact test of the primitive in leaf-order slot `slot` (the reference's arithmetic; spheres behind their own leaf box,
+// sphere_gate).  Winner rule = brute force in index order: smallest t, an exact tie to the lower primitive id -- so the
+// result does not depend on the order in which the tree presents the primitives.
+__device__ __forceinline__ void wide_test_prim(const B2BvhScene& S, uint32_t slot, f3 o, f3 d, f3 inv, f3 od, float tmin,
+                                               float tmax, float& closest, int& best, int& bestId)
+{
+  const int enc = __ldg(S.primSlots + slot);
+  float t = 0.f;
+  bool h = false;
+  if (enc >= 0)
+    h = quad_hit(S.quads[enc], o, d, t) && t > tmin && t <= closest;
+  else
+  {
+    const float4 g = __ldg(S.leafSph + slot);
+    const f3 c = mk3(g.x, g.y, g.z);
+    if (sphere_gate(c, g.w, inv, od, tmin, tmax))
+    { // Surface.h:319-367 with the upper bound made inclusive (the tie rule below decides equality)
+      const f3 oc = o - c;
+      const float a = dot3(d, d), b = dot3(oc, d), cc = dot3(oc, oc) - g.w * g.w;
+      const float disc = b * b - a * cc;
+      if (disc > 0.f)
+      {
+        const float sq = sqrtf(b * b - a * cc);
+        float temp = (-b - sq) / a;
+        if (temp <= closest && temp > tmin)
+          t = temp, h = true;
+        else
+        {
+          temp = (-b + sq) / a;
+          if (temp <= closest && temp > tmin)
+            t = temp, h = true;
+        }
+      }
+    }
+  }
+  const int id = enc >= 0 ? enc : S.nQuads + (~enc);
+  if (h && (t < closest || id < bestId))
+  {
+    closest = t;
+    best = enc;
+    bestId = id;
+  }
+}
+// One traversal step of a lane: if it holds a node group, visit that group's next child node (A); the caller then runs
+// wide_step_prim for lanes holding a primitive group (B).  Returns false when the ray has nothing left.
+__device__ __forceinline__ void wide_push(uint32_t* stackX, uint32_t* stackY, int& sp, uint32_t x, uint32_t y)
+{
+  if (sp < kWideStack)
+  {
+    stackX[sp] = x;
+    stackY[sp] = y;
+    ++sp;
+  }
+}
+__device__ __forceinline__ void wide_start(WideTrav& R, uint32_t oct, bool any)
+{
+  // the root is "inner child 0 of a virtual node": one hit bit at the position slot 0 has for this octant
+  R.nx = 0u;
+  R.ny = any ? ((1u << 8) | (1u << oct)) : 0u;
+  R.px = R.py = 0u;
+  R.sp = 0;
+}
+// (A) visit the next child of the node group; new groups replace / are stacked as described in WideTrav
+__device__ __forceinline__ void wide_step_node(const B2BvhScene& S, WideTrav& R, uint32_t* stackX, uint32_t* stackY, f3 inv,
+                                               f3 od, uint32_t oct, float tmin, float closest)
+{
+  const uint32_t hb = R.ny & 0xffu;
+  const uint32_t b = (uint32_t)__ffs((int)hb) - 1u;
+  const uint32_t s = b ^ oct;
+  const uint32_t child = R.nx + (uint32_t)__popc((R.ny >> 8) & 0xffu & ((1u << s) - 1u));
+  R.ny &= ~(1u << b);
+  if (R.ny & 0xffu)
+    wide_push(stackX, stackY, R.sp, R.nx, R.ny);
+  uint32_t childBase, primBase, innerMask, primMask;
+  const uint32_t hits = wide_node_hits(S.wide + 5 * (size_t)child, inv, od, tmin, closest, childBase, primBase, innerMask,
+                                       primMask);
+  const uint32_t pm = wide_perm((hits & innerMask) | ((hits & primMask) << 8), oct);
+  R.nx = childBase;
+  R.ny = (innerMask << 8) | (pm & 0xffu);
+  const uint32_t ph = pm >> 8;
+  if (ph)
+  {
+    if (R.py & 0xffu) // (cannot happen: a lane holding a primitive group does not take step A)
+      wide_push(stackX, stackY, R.sp, R.px, R.py);
+    R.px = primBase;
+    R.py = kWidePrimGroup | (primMask << 8) | ph;
+  }
+}
+// (B) exact test of the next primitive of the primitive group
+__device__ __forceinline__ void wide_step_prim(const B2BvhScene& S, WideTrav& R, f3 o, f3 d, f3 inv, f3 od, uint32_t oct,
+                                               float tmin, float tmax, float& closest, int& best, int& bestId)
+{
+  const uint32_t hb = R.py & 0xffu;
+  const uint32_t b = (uint32_t)__ffs((int)hb) - 1u;
+  const uint32_t s = b ^ oct;
+  const uint32_t slot = R.px + (uint32_t)__popc((R.py >> 8) & 0xffu & ((1u << s) - 1u));
+  R.py &= ~(1u << b);
+  wide_test_prim(S, slot, o, d, inv, od, tmin, tmax, closest, best, bestId);
+}
+// both groups empty: take the next group from the stack; returns false when the traversal is over
+__device__ __forceinline__ bool wide_next(WideTrav& R, const uint32_t* stackX, const uint32_t* stackY)
+{
+  if ((R.ny & 0xffu) || (R.py & 0xffu))
+    return true;
+  if (R.sp == 0)
+    return false;
+  --R.sp;
+  const uint32_t x = stackX[R.sp], y = stackY[R.sp];
+  if (y & kWidePrimGroup)
+    R.px = x, R.py = y;
+  else
+    R.nx = x, R.ny = y;
+  return true;
+}
+__device__ __forceinline__ uint32_t wide_octant(f3 inv)
+{
+  return (inv.x < 0.f ? 1u : 0u) | (inv.y < 0.f ? 2u : 0u) | (inv.z < 0.f ? 4u : 0u);
+}
+// Closest hit of one ray (stage-level kernels; the bounce kernels use the persistent-lane form, trace_body_wide)
+__device__ __forceinline__ int closest_wide(const B2BvhScene& S, f3 o, f3 d, float tmin, float tmax, float& tHit)
+{
+  const f3 inv = mk3(rcp_safe(d.x), rcp_safe(d.y), rcp_safe(d.z));
+  const f3 od = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+  const uint32_t oct = wide_octant(inv);
+  float closest = tmax;
+  int best = 0, bestId = 0x7fffffff;
+  uint32_t stackX[kWideStack], stackY[kWideStack];
+  WideTrav R;
+  wide_start(R, oct, S.nWide > 0);
+  while (wide_next(R, stackX, stackY))
+  {
+    if (R.py & 0xffu)
+      wide_step_prim(S, R, o, d, inv, od, oct, tmin, tmax, closest, best, bestId);
+    else
+      wide_step_node(S, R, stackX, stackY, inv, od, oct, tmin, closest);
+  }
+  bool found = bestId != 0x7fffffff;
+  for (int g = 0; g < S.nGate; ++g)
+  { // non-planar quads: after the traversal, each behind its own leaf box (DESIGN.md "leaf-box gate")
+    float tn, t;
+    if (!slab_hit(S.gate[g].bmin, S.gate[g].bmax, inv, od, tmin, closest, tn))
+      continue;
+    const int q = S.gate[g].quad;
+    if (quad_accept(S.quads[q], o, d, tmin, closest, t))
+    {
+      closest = t;
+      best = q;
+      found = true;
+    }
+  }
+  tHit = closest;
+  return found ? best : B2PT_MISS;
+}
+__device__ __forceinline__ int closest_hit(const B2WideScene& S, f3 o, f3 d, float tmin, float tmax, float& t)
+{
+  return closest_wide(S, o, d, tmin, tmax, t);
+}
+
 __device__ __forceinline__ int closest_hit(const B2SmallScene& S, f3 o, f3 d, float tmin, float tmax, float& t)
 {
   return closest_small(S, o, d, tmin, tmax, t);

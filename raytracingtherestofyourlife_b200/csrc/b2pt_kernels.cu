@@ -97,6 +97,10 @@ __device__ __forceinline__ const B2BvhScene& stage_scene(const B2BvhScene& scene
 {
   return scene;
 }
+__device__ __forceinline__ const B2WideScene& stage_scene(const B2WideScene& scene, StageArea<B2WideScene>&)
+{
+  return scene;
+}
 template <class SceneT>
 __device__ __forceinline__ const B2Lights& stage_lights(const B2Lights& lights, StageArea<SceneT>& a)
 {
@@ -412,11 +416,198 @@ __device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhS
   }
 }
 
+// ---- BVH scenes, 8-wide compressed tree (B2WideScene; b2pt_wide.h, b2pt_device.cuh "8-wide compressed BVH").
+// The same persistent-lane scheme: a lane that finishes its ray takes the next ray of the warp's own region.  Every
+// iteration a lane with a node group visits ONE child node (eight quantised boxes in one 80-byte fetch: identical
+// straight-line work for every lane, whether the children are subtrees or primitives), then the lanes whose node had
+// primitive children that passed their box run ONE exact primitive test.  The ray's throughput, path id and RNG state
+// are not carried through the traversal: the finished lane reads them back from its queue entry (primary rays keep the
+// RNG state, the rest is implied).
+#ifndef B2PT_WIDE_REFILL
+#define B2PT_WIDE_REFILL 22
+#endif
+constexpr int kWideRefillLanes = B2PT_WIDE_REFILL;
+
+template <bool PRIMARY, bool TAIL>
+__device__ __forceinline__ void trace_body_wide(const B2Camera& cam, const B2BvhScene& S, const B2RenderArgs& A, int depth,
+                                                int w, int lane, int64_t nIn, int64_t tailWarps)
+{
+  const int64_t base = TAIL ? 0 : (int64_t)w * A.regionCap;
+  const bool refStream = (A.flags & B2PT_FLAG_REFERENCE_STREAM_DEV) != 0;
+  const unsigned lt = (1u << lane) - 1u;
+  int64_t nLocal = nIn;
+  if (TAIL)
+  {
+    const int64_t tiles = (nIn + 31) >> 5;
+    nLocal = tiles > w ? ((tiles - 1 - w) / tailWarps + 1) * 32 : 0;
+  }
+  const int64_t stride = TAIL ? tailWarps : (int64_t)A.numWarps;
+  auto ray_index = [&](int64_t r) -> int64_t {
+    return PRIMARY ? (primary_tile(r >> 5, w, A.numWarps) << 5) + (r & 31)
+                   : (TAIL ? ((((r >> 5) * stride + w) << 5) + (r & 31)) : base + r);
+  };
+  uint32_t cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
+  int64_t next = 0;
+  bool has = false, live = false;
+  f3 o = mk3(0.f, 0.f, 0.f), d = o, inv = o, od = o;
+  uint32_t rngP = 0, oct = 0, myRay = 0;
+  float closest = FLT_MAX;
+  int best = 0, bestId = 0x7fffffff;
+  WideTrav R;
+  R.nx = R.ny = R.px = R.py = 0u;
+  R.sp = 0;
+  uint32_t stackX[kWideStack], stackY[kWideStack];
+  for (;;)
+  {
+    // ---- refill: lanes without a ray take the next local ray numbers
+    const unsigned need = __ballot_sync(0xffffffffu, !has);
+    if (need)
+    {
+      const int64_t r = next + __popc(need & lt);
+      if (!has && r < nLocal)
+      {
+        const int64_t idx = ray_index(r);
+        if (PRIMARY ? idx < A.nPaths : (TAIL ? idx < nIn : true))
+        {
+          f3 T;
+          uint32_t pid;
+          load_ray<PRIMARY>(cam, A, idx, o, d, T, pid, rngP);
+          inv = mk3(rcp_safe(d.x), rcp_safe(d.y), rcp_safe(d.z));
+          od = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+          oct = wide_octant(inv);
+          closest = FLT_MAX;
+          best = 0;
+          bestId = 0x7fffffff;
+          myRay = (uint32_t)r;
+          wide_start(R, oct, S.nWide > 0);
+          has = true;
+          live = wide_next(R, stackX, stackY);
+        }
+      }
+      next += __popc(need);
+    }
+    if (!__any_sync(0xffffffffu, has))
+      break;
+    // ---- traverse until too few lanes are still busy (or, with nothing left to refill, until all are done)
+    for (;;)
+    {
+      const bool doA = live && !(R.py & 0xffu);
+      if (__any_sync(0xffffffffu, doA))
+      {
+        if (doA)
+          wide_step_node(S, R, stackX, stackY, inv, od, oct, 0.001f, closest);
+      }
+      const bool doB = live && (R.py & 0xffu);
+      if (__any_sync(0xffffffffu, doB))
+      {
+        if (doB)
+          wide_step_prim(S, R, o, d, inv, od, oct, 0.001f, FLT_MAX, closest, best, bestId);
+      }
+      if (live)
+        live = wide_next(R, stackX, stackY);
+      const unsigned act = __ballot_sync(0xffffffffu, live);
+      if (act == 0u || (next < nLocal && __popc(act) < kWideRefillLanes))
+        break;
+    }
+    // ---- resolve the finished rays: gated quads, then miss / emitter / bin (as in the generic body)
+    const bool resolve = has && !live;
+    int bin = -1;
+    int code = B2PT_MISS;
+    f3 T = mk3(1.f, 1.f, 1.f);
+    uint32_t pid = 0, rng = rngP;
+    if (resolve)
+    {
+      const int64_t idx = ray_index((int64_t)myRay);
+      if (PRIMARY)
+        pid = (uint32_t)idx;
+      else
+      {
+        const uint4 b = __ldcg(A.q.p1 + idx), c = __ldcg(A.q.p2 + idx);
+        T = mk3(__uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(c.x));
+        pid = c.y;
+        rng = c.z;
+      }
+      bool found = bestId != 0x7fffffff;
+      for (int g = 0; g < S.nGate; ++g)
+      {
+        float tn, t;
+        if (!slab_hit(S.gate[g].bmin, S.gate[g].bmax, inv, od, 0.001f, closest, tn))
+          continue;
+        const int q = S.gate[g].quad;
+        if (quad_accept(S.quads[q], o, d, 0.001f, closest, t))
+        {
+          closest = t;
+          best = q;
+          found = true;
+        }
+      }
+      code = found ? best : B2PT_MISS;
+      if (code == B2PT_MISS)
+        finish_path(A, pid, T * 0.f, rng, refStream, A.maxDepth - depth);
+      else
+      {
+        const int kind = hit_kind(S, code);
+        if (kind == 1)
+        {
+          Hit hit;
+          fill_hit(S, code, o, d, closest, hit);
+          const f3 em = (dot3(hit.n, d) < 0.0f) ? hit.alb : mk3(0.f, 0.f, 0.f);
+          finish_path(A, pid, mul3(T, em), rng, refStream, A.maxDepth - depth);
+        }
+        else
+        {
+          uint32_t peek = rng;
+          bin = (kind == 2) ? 0 : draw_which(peek);
+        }
+      }
+      has = false;
+    }
+    const unsigned b0 = __ballot_sync(0xffffffffu, bin == 0), b1 = __ballot_sync(0xffffffffu, bin == 1);
+    const unsigned b2 = __ballot_sync(0xffffffffu, bin == 2), b3 = __ballot_sync(0xffffffffu, bin == 3);
+    if (TAIL)
+    {
+      uint32_t got = 0;
+      if (lane < 4)
+      {
+        const unsigned bk = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
+        if (bk)
+          got = atomicAdd(&A.binTotals[depth * 4 + lane], (uint32_t)__popc(bk));
+      }
+      cnt0 = __shfl_sync(0xffffffffu, got, 0), cnt1 = __shfl_sync(0xffffffffu, got, 1);
+      cnt2 = __shfl_sync(0xffffffffu, got, 2), cnt3 = __shfl_sync(0xffffffffu, got, 3);
+    }
+    if (bin >= 0)
+    {
+      const unsigned mine = bin == 0 ? b0 : (bin == 1 ? b1 : (bin == 2 ? b2 : b3));
+      const uint32_t cnt = bin == 0 ? cnt0 : (bin == 1 ? cnt1 : (bin == 2 ? cnt2 : cnt3));
+      const int64_t j = (int64_t)bin * A.binStride + base + cnt + __popc(mine & lt);
+      A.bins[0].p0[j] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
+      A.bins[0].p1[j] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
+      A.bins[0].p2[j] = make_uint4(__float_as_uint(T.z), pid, rng, __float_as_uint(closest));
+      A.bins[0].code[j] = (uint32_t)code;
+    }
+    if (!TAIL)
+      cnt0 += __popc(b0), cnt1 += __popc(b1), cnt2 += __popc(b2), cnt3 += __popc(b3);
+  }
+  if (!TAIL && lane == 0)
+  {
+    A.bins[0].count[0 * A.numWarps + w] = cnt0;
+    A.bins[0].count[1 * A.numWarps + w] = cnt1;
+    A.bins[0].count[2 * A.numWarps + w] = cnt2;
+    A.bins[0].count[3 * A.numWarps + w] = cnt3;
+  }
+}
+
 // Work of one warp in k_trace: rays [.., nIn) of its region (TAIL: tiles w, w+tailWarps, ... of the flat queue).
 template <bool PRIMARY, class SceneT, bool TAIL>
 __device__ __forceinline__ void trace_body(const B2Camera& cam, const SceneT& S, const B2RenderArgs& A, int depth,
                                            int w, int lane, int64_t nIn, int64_t tailWarps)
 {
+  if constexpr (std::is_same<SceneT, B2WideScene>::value)
+  {
+    trace_body_wide<PRIMARY, TAIL>(cam, S, A, depth, w, lane, nIn, tailWarps);
+    return;
+  }
   if constexpr (std::is_same<SceneT, B2BvhScene>::value)
   {
     trace_body_bvh<PRIMARY, TAIL>(cam, S, A, depth, w, lane, nIn, tailWarps);
@@ -1253,6 +1444,8 @@ cudaError_t query_launch_cfg(LaunchCfg* cfg)
       (e = occ((const void*)k_trace<false, B2SmallScene, false>, cfg->traceBlocksPerSM[0][0])) != cudaSuccess ||
       (e = occ((const void*)k_trace<true, B2BvhScene, false>, cfg->traceBlocksPerSM[1][1])) != cudaSuccess ||
       (e = occ((const void*)k_trace<false, B2BvhScene, false>, cfg->traceBlocksPerSM[0][1])) != cudaSuccess ||
+      (e = occ((const void*)k_trace<true, B2WideScene, false>, cfg->traceBlocksPerSM[1][2])) != cudaSuccess ||
+      (e = occ((const void*)k_trace<false, B2WideScene, false>, cfg->traceBlocksPerSM[0][2])) != cudaSuccess ||
       (e = occ((const void*)k_shade<B2SmallScene, false, false>, cfg->shadeBlocksPerSM[0][0])) != cudaSuccess ||
       (e = occ((const void*)k_shade<B2BvhScene, false, false>, cfg->shadeBlocksPerSM[0][1])) != cudaSuccess ||
       (e = occ((const void*)k_bounce<B2SmallScene, false, false>, cfg->bounceBlocksPerSM)) != cudaSuccess)
@@ -1282,12 +1475,15 @@ static cudaError_t launch_bounce_t(const LaunchCfg& cfg, bool primary, int mode,
     k_trace<false, SceneT, false><<<grid, kBlock, 0, stream>>>(cam, S, args);
   if (betweenStages)
     cudaEventRecord(betweenStages, stream);
+  // (the shade stage never traverses: the wide scene shades through the kernels of its base type)
+  using ShadeT = typename std::conditional<std::is_same<SceneT, B2WideScene>::value, B2BvhScene, SceneT>::type;
+  const ShadeT& SS = S;
   if (mode == B2PT_BOUNCE_TAIL)
-    k_shade<SceneT, true, true><<<tailGrid, kBlock, 0, stream>>>(S, lights, args);
+    k_shade<ShadeT, true, true><<<tailGrid, kBlock, 0, stream>>>(SS, lights, args);
   else if (mode == B2PT_BOUNCE_TO_GLOBAL)
-    k_shade<SceneT, false, true><<<grid, kBlock, 0, stream>>>(S, lights, args);
+    k_shade<ShadeT, false, true><<<grid, kBlock, 0, stream>>>(SS, lights, args);
   else
-    k_shade<SceneT, false, false><<<grid, kBlock, 0, stream>>>(S, lights, args);
+    k_shade<ShadeT, false, false><<<grid, kBlock, 0, stream>>>(SS, lights, args);
   return cudaGetLastError();
 }
 
@@ -1331,7 +1527,13 @@ cudaError_t launch_tail_loop(const B2Camera& cam, const B2SmallScene* small, con
 {
   if (args.depth < 1)
     return cudaErrorInvalidValue;
-  if (bvh)
+  if (bvh && bvh->wide)
+  {
+    B2WideScene ws;
+    static_cast<B2BvhScene&>(ws) = *bvh;
+    k_tail_loop<B2WideScene><<<kTailCluster, kTailBlock, 0, stream>>>(cam, ws, lights, args);
+  }
+  else if (bvh)
     k_tail_loop<B2BvhScene><<<kTailCluster, kTailBlock, 0, stream>>>(cam, *bvh, lights, args);
   else
     k_tail_loop<B2SmallScene><<<kTailCluster, kTailBlock, 0, stream>>>(cam, *small, lights, args);
@@ -1342,6 +1544,12 @@ cudaError_t launch_bounce(const LaunchCfg& cfg, bool primary, int mode, const B2
                           const B2BvhScene* bvh, const B2Lights& lights, const B2RenderArgs& args,
                           cudaStream_t stream, cudaEvent_t betweenStages)
 {
+  if (bvh && bvh->wide)
+  {
+    B2WideScene ws;
+    static_cast<B2BvhScene&>(ws) = *bvh;
+    return launch_bounce_t(cfg, primary, mode, cam, ws, lights, args, stream, betweenStages);
+  }
   if (bvh)
     return launch_bounce_t(cfg, primary, mode, cam, *bvh, lights, args, stream, betweenStages);
   return launch_bounce_t(cfg, primary, mode, cam, *small, lights, args, stream, betweenStages);
@@ -1387,7 +1595,13 @@ cudaError_t launch_primary_hits(const B2Camera& cam, const B2SmallScene* small, 
                                 uint32_t seedOffset, int32_t* primOut, float* tOut, cudaStream_t stream)
 {
   const int n = cam.W * cam.H;
-  if (bvh)
+  if (bvh && bvh->wide)
+  {
+    B2WideScene ws;
+    static_cast<B2BvhScene&>(ws) = *bvh;
+    k_primary_hits<B2WideScene><<<(n + 255) / 256, 256, 0, stream>>>(cam, ws, seedOffset, primOut, tOut);
+  }
+  else if (bvh)
     k_primary_hits<B2BvhScene><<<(n + 255) / 256, 256, 0, stream>>>(cam, *bvh, seedOffset, primOut, tOut);
   else
     k_primary_hits<B2SmallScene><<<(n + 255) / 256, 256, 0, stream>>>(cam, *small, seedOffset, primOut, tOut);
@@ -1410,7 +1624,14 @@ cudaError_t launch_intersect(const B2SmallScene* small, const B2BvhScene* bvh, i
   const unsigned grid = (unsigned)((n + 255) / 256);
   if (grid == 0)
     return cudaSuccess;
-  if (bvh)
+  if (bvh && bvh->wide)
+  {
+    B2WideScene ws;
+    static_cast<B2BvhScene&>(ws) = *bvh;
+    k_intersect<B2WideScene>
+      <<<grid, 256, 0, stream>>>(ws, n, ox, oy, oz, dx, dy, dz, tmin, tmax, primId, hrec9, matId, texId);
+  }
+  else if (bvh)
     k_intersect<B2BvhScene>
       <<<grid, 256, 0, stream>>>(*bvh, n, ox, oy, oz, dx, dy, dz, tmin, tmax, primId, hrec9, matId, texId);
   else

@@ -12,7 +12,7 @@ namespace b2pt
 struct LaunchCfg
 {
   int numSMs;
-  int traceBlocksPerSM[2][2]; // [primary][bvh]
+  int traceBlocksPerSM[2][3]; // [primary][0 small scene, 1 binary BVH, 2 8-wide BVH]
   int shadeBlocksPerSM[2][2];
   int bounceBlocksPerSM; // k_bounce (one-kernel pipeline of small scenes)
 };

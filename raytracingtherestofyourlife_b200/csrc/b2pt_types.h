@@ -201,6 +201,21 @@ struct B2BvhNode // 32 B, two 16-byte loads
   int32_t count; // 0 = inner node, >0 = leaf with `count` primitive slots
 };
 
+#define B2PT_WIDE_STACK 32 // traversal stack entries per ray (groups); the tree may be at most this deep
+// 8-wide compressed BVH node (b2pt_wide.h builds it, wide_node_hits in b2pt_device.cuh tests it): 80 B = five 16-byte
+// loads.  Child s has the box  org + 2^(e-127) * [qlo[.][s], qhi[.][s]]  per axis; an empty slot has qlo > qhi.
+// Inner children are nodes childBase + rank of s in innerMask; primitive children are the leaf-order slots
+// primBase + rank of s in primMask.
+struct alignas(16) B2WideNode
+{
+  float org[3];
+  uint8_t ex, ey, ez, innerMask;
+  uint32_t childBase, primBase;
+  uint8_t primMask, pad8[7];
+  uint8_t qlo[3][8];
+  uint8_t qhi[3][8];
+};
+
 struct B2BvhScene
 {
   const B2BvhNode* nodes;
@@ -211,6 +226,16 @@ struct B2BvhScene
   const B2Sphere* sph;
   const B2GateBox* gate;
   int32_t nNodes, nQuads, nSph, nGate;
+  // the 8-wide tree the traversal walks (nodes / the binary tree above are what it was collapsed from; primSlots and
+  // leafSph are in the wide tree's leaf order)
+  const uint4* wide; // B2WideNode[nWide] as 5 x uint4 each
+  int32_t nWide, wideDepth;
+};
+
+// Same scene, traversed through the 8-wide tree (a distinct type selects the wide traversal kernels at compile time;
+// the binary-tree kernels stay available for A/B runs, B2PT_FLAG_BINARY_BVH).
+struct B2WideScene : B2BvhScene
+{
 };
 
 // One ray queue = three planes of uint4.

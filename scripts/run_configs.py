@@ -11,13 +11,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import raytracingtherestofyourlife_b200 as B
 
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
+FLAGS = int(os.environ.get("B2PT_FLAGS", "0"))  # e.g. 4096 = B2PT_FLAG_BINARY_BVH, 2048 = B2PT_FLAG_SPLIT_BOUNCE
 spp = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 
 
 def measure(ctx, spp, depth, reps=2):
     best = None
     for _ in range(reps + 1):  # first repetition is the warm-up
-        ctx.render(spp, depth, 0)
+        ctx.render(spp, depth, FLAGS)
         st = ctx.stats()
         best = st if best is None or st.renderMs < best.renderMs else best
     return best
@@ -28,7 +29,7 @@ if what in ("spheres", "all"):
     with B.Context(0) as ctx:
         t0 = time.time()
         ctx.set_scene(B.Scene.spheres(n))
-        ctx.build_bvh()
+        ctx.build_bvh(FLAGS)
         ctx.synchronize()
         build_s = time.time() - t0
         ctx.set_camera(B.Camera(1920, 1080))
@@ -36,7 +37,7 @@ if what in ("spheres", "all"):
         print(json.dumps({"config": "1M random spheres + BVH, 1920x1080, %d spp, depth 50" % spp,
                           "path_samples_per_s": st.paths / st.renderMs * 1e3, "segments_per_s": st.segments / st.renderMs * 1e3,
                           "ms": st.renderMs, "segments_per_path": st.segments / st.paths, "bvh_nodes": st.bvhNodes,
-                          "scene_upload_plus_bvh_build_s": build_s, "launches": st.launches}), flush=True)
+                          "scene_upload_plus_bvh_build_s": build_s, "launches": st.launches, "flags": FLAGS}), flush=True)
 if what in ("sweep", "all"):
     with B.Context(0) as ctx:
         ctx.set_scene(B.Scene.cornell())

@@ -36,3 +36,16 @@ def test_plan_batches_rules(b2pt):
         plan(4, 0)
     with pytest.raises(b2pt.B2ptError):
         plan(4, N, sets=0)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 9, 300, 5000, 200000])
+def test_bvh_builders_selfcheck(b2pt, n):
+    """Binned-SAH tree + collapse into 8-wide compressed nodes on the many-sphere scene, validated on the host: every
+    primitive reachable exactly once, child boxes nested, quantised boxes conservative with a step to spare."""
+    bin_nodes, bin_depth, wide_nodes, wide_depth = b2pt.bvh_selfcheck(n)
+    assert bin_nodes >= 1 and wide_nodes >= 1
+    assert wide_depth <= max(1, (bin_depth + 1) // 2 + 1) and wide_depth <= 32
+    assert wide_nodes <= max(1, bin_nodes // 2 + 1)
+    # 8-wide: about n / 6 leaf-level nodes
+    if n >= 300:
+        assert wide_nodes < 0.45 * n
