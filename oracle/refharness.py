@@ -24,7 +24,7 @@ def build(force=False):
     have_src = os.path.isdir(os.path.join(REF_ROOT, "pathtracing"))
     if have_src:
         O.build()
-        args = ["make", "-C", _HERE, "-s", "ref", "REF_ROOT=" + REF_ROOT]
+        args = ["make", "-C", _HERE, "-s", "ref", "reftime", "REF_ROOT=" + REF_ROOT]
         if force:
             args.insert(1, "-B")
         subprocess.check_call(args)
@@ -36,6 +36,21 @@ def available():
 
 
 _lib = None
+_TIMING_LIB_PATH = os.path.join(_HERE, "_ref", "libb2pt_refharness_o3.so")
+_tlib = None
+
+
+def timing_lib():
+    """The -O3 -march=x86-64-v3 build of the same harness (bench.py's CPU arm); None when it was not built."""
+    global _tlib
+    if _tlib is None and build() is not None and os.path.exists(_TIMING_LIB_PATH):
+        O.lib()
+        L = C.CDLL(_TIMING_LIB_PATH)
+        L.b2ref_render.restype = C.c_int
+        L.b2ref_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64),
+                                   C.c_void_p, C.c_void_p]
+        _tlib = L
+    return _tlib
 
 
 def lib():
@@ -119,6 +134,23 @@ def cornell_scene():
     npt, nq, ns = (int(v) for v in n)
     return dict(pts=pts[:npt], quadIds=quadIds[:nq], sphPt=sphPt[:ns], sphR=sphR[:ns], matIdxQ=matQ[:nq],
                 texIdxQ=texQ[:nq], matIdxS=matS[:ns], texIdxS=texS[:ns], matType=matType, texType=texType, tex=tex)
+
+
+def render_timed(scene, cam, spp, max_depth):
+    """render() through the timing build when it exists; returns (rgba_sum, segments, build description)."""
+    L = timing_lib()
+    if L is None:
+        rgba, seg, _, _ = render(scene, cam, spp, max_depth)
+        return rgba, seg, "-O2 -ffp-contract=off (parity build)"
+    n = cam.W * cam.H
+    rgba, t0, hit0 = np.zeros((n, 4), np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    seg = C.c_int64(0)
+    ss, cs = scene.c_struct(), cam.c_struct()
+    L.b2ref_set_tree_variant(0)
+    rc = L.b2ref_render(C.byref(ss), C.byref(cs), spp, max_depth, _p(rgba), C.byref(seg), _p(t0), _p(hit0))
+    if rc != 0:
+        raise RuntimeError("b2ref_render failed: %d" % rc)
+    return rgba, int(seg.value), "-O3 -march=x86-64-v3 -ffp-contract=off (timing build)"
 
 
 def render(scene, cam, spp, max_depth, tree_variant=0):

@@ -28,7 +28,7 @@ FLAG_GPU_LBVH = 0x80
 FLAG_VIEWS_NORMALIZE = 0x100
 FLAG_VIEWS_PNM16 = 0x200
 FLAG_NO_PRIMARY_MASKS = 0x400
-FLAG_SPLIT_BOUNCE = 0x800
+FLAG_ONE_KERNEL_BOUNCE = 0x800
 FLAG_BINARY_BVH = 0x1000
 
 ERR_BAD_VALUE, ERR_CUDA, ERR_STATE, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5

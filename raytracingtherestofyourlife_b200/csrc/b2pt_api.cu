@@ -1316,9 +1316,10 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     int64_t per = 1, viewsPerBatch = 0, B = 1, nBatches = 0, pathsPerBatch = 0, numWarps = 0, regionCap = 0, queueCap = 0;
     int nSets = 1;
   };
-  // Small scenes: one kernel per bounce (k_bounce); BVH scenes (and B2PT_FLAG_SPLIT_BOUNCE, for A/B runs): k_trace +
-  // k_shade per bounce with a ray queue in between.
-  const bool fused = !ctx->useBvh && !(flags & B2PT_FLAG_SPLIT_BOUNCE);
+  // Two kernels per bounce (k_trace + k_shade with a ray queue in between) by default; small scenes can run the
+  // one-kernel pipeline (k_bounce, B2PT_FLAG_ONE_KERNEL_BOUNCE): half the HBM traffic per survivor, but measured 25 %
+  // slower per ray on B200, so it is the opt-in.
+  const bool fused = !ctx->useBvh && (flags & B2PT_FLAG_ONE_KERNEL_BOUNCE);
   const int blocksPerSM = fused ? std::min(ctx->cfg.traceBlocksPerSM[1][0], ctx->cfg.bounceBlocksPerSM)
                                 : std::min(ctx->cfg.traceBlocksPerSM[0][ctx->useBvh ? (ctx->bvh.wide ? 2 : 1) : 0],
                                            ctx->cfg.shadeBlocksPerSM[0][ctx->useBvh ? 1 : 0]);

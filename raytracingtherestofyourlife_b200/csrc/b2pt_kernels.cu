@@ -911,6 +911,7 @@ __device__ __forceinline__ void bounce_body(const SceneT& S, const B2Lights& LT,
       uint32_t pid = 0, rng = 0;
       float t = 0.f;
       int code = B2PT_MISS;
+      bool traced = false; // this lane's path entered bounce `depth` (statistics)
       if (!IN_GLOBAL && i + 32 < nk)
       {
         prefetch_l2(Bi.p0 + binBase + i + 32);
@@ -938,6 +939,7 @@ __device__ __forceinline__ void bounce_body(const SceneT& S, const B2Lights& LT,
           finish_path(A, pid, T * 0.f, rng, refStream, 0);
         else
         {
+          traced = true;
           code = closest_hit(S, o, d, 0.001f, FLT_MAX, t);
           if (code == B2PT_MISS)
             finish_path(A, pid, T * 0.f, rng, refStream, A.maxDepth - depth); // a[d]=1, e[d]=0
@@ -961,6 +963,7 @@ __device__ __forceinline__ void bounce_body(const SceneT& S, const B2Lights& LT,
       }
       if (closing)
         continue; // (warp-uniform) nothing is binned by the closing launch
+      processed += (uint32_t)__popc(__ballot_sync(0xffffffffu, traced));
       const unsigned b0 = __ballot_sync(0xffffffffu, bin == 0), b1 = __ballot_sync(0xffffffffu, bin == 1);
       const unsigned b2 = __ballot_sync(0xffffffffu, bin == 2), b3 = __ballot_sync(0xffffffffu, bin == 3);
       if (OUT_GLOBAL)
@@ -987,7 +990,6 @@ __device__ __forceinline__ void bounce_body(const SceneT& S, const B2Lights& LT,
       }
       if (!OUT_GLOBAL)
         cnt0 += __popc(b0), cnt1 += __popc(b1), cnt2 += __popc(b2), cnt3 += __popc(b3);
-      processed += (uint32_t)min((int64_t)32, nk - i0);
     }
   }
   if (lane == 0)

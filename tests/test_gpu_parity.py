@@ -209,9 +209,9 @@ def test_axis_aligned_specialisation_is_bit_identical(gpu_ctx, b2pt):
 def test_tail_mode_is_bit_identical(gpu_ctx, b2pt, oracle, monkeypatch, pipeline):
     """Deep bounces switch to flat global bins with atomically appended records (k_bounce / k_trace / k_shade TAIL
     instantiations); the processing order changes, the paths and the sample-order accumulation do not.  Both
-    pipelines: one kernel per bounce (default for small scenes) and k_trace + k_shade (B2PT_FLAG_SPLIT_BOUNCE)."""
+    pipelines: k_trace + k_shade (default) and one kernel per bounce (B2PT_FLAG_ONE_KERNEL_BOUNCE)."""
     W, spp, depth = 256, 16, 50
-    pf = 0 if pipeline == "one_kernel" else b2pt.FLAG_SPLIT_BOUNCE
+    pf = b2pt.FLAG_ONE_KERNEL_BOUNCE if pipeline == "one_kernel" else 0
     first = 2 if pipeline == "one_kernel" else 1  # the one-kernel pipeline always bins bounce 0 per region
     monkeypatch.setenv("B2PT_BATCH_PATHS", str(W * W * 4))  # 4 batches: the tail depth is chosen after the first
     gpu_ctx.set_camera(b2pt.Camera(W, W))
@@ -271,7 +271,7 @@ def test_stage_profile_reports_both_launches(gpu_ctx, b2pt):
     consistent with b2pt_get_bounce_profile and with the segment count.  Two-kernel pipeline: the k_trace and the
     k_shade launch; one-kernel pipeline: the whole bounce is the first figure, the second is the empty event gap."""
     gpu_ctx.set_camera(b2pt.Camera(256, 256))
-    for flags, split in ((b2pt.FLAG_NO_OVERLAP, False), (b2pt.FLAG_NO_OVERLAP | b2pt.FLAG_SPLIT_BOUNCE, True)):
+    for flags, split in ((b2pt.FLAG_NO_OVERLAP, True), (b2pt.FLAG_NO_OVERLAP | b2pt.FLAG_ONE_KERNEL_BOUNCE, False)):
         gpu_ctx.render(8, 12, flags)
         st = gpu_ctx.stats()
         prof = gpu_ctx.stage_profile(16)

@@ -1,6 +1,6 @@
-"""The one-kernel-per-bounce pipeline of small scenes (k_bounce: shade the hits of bounce d-1, trace bounce d, bin the
-new hits; no ray queue) against the two-kernel pipeline (k_trace + k_shade, B2PT_FLAG_SPLIT_BOUNCE), which round 1
-pinned to the oracle: the same paths, the same per-path arithmetic, the same sample-order sums -- images must agree
+"""The one-kernel-per-bounce pipeline of small scenes (B2PT_FLAG_ONE_KERNEL_BOUNCE; k_bounce: shade the hits of bounce
+d-1, trace bounce d, bin the new hits; no ray queue) against the default two-kernel pipeline (k_trace + k_shade), which
+the parity tests pin to the oracle: the same paths, the same per-path arithmetic, the same sample-order sums -- images must agree
 bit for bit, in every mode that changes how records are laid out."""
 import numpy as np
 import pytest
@@ -21,8 +21,8 @@ def render(ctx, spp, depth, flags):
                                            (33, 7, 40, 3), (256, 256, 32, 16)])
 def test_one_kernel_pipeline_equals_two_kernel_pipeline(gpu_ctx, b2pt, W, H, spp, depth):
     gpu_ctx.set_camera(b2pt.Camera(W, H))
-    a, sa = render(gpu_ctx, spp, depth, 0)
-    b, sb = render(gpu_ctx, spp, depth, b2pt.FLAG_SPLIT_BOUNCE)
+    a, sa = render(gpu_ctx, spp, depth, b2pt.FLAG_ONE_KERNEL_BOUNCE)
+    b, sb = render(gpu_ctx, spp, depth, 0)
     assert sa.segments == sb.segments and sa.nanSamples == sb.nanSamples and sa.paths == sb.paths
     assert same(a, b)
     # one launch per bounce + the closing pass (+ candidate-mask prep when the canvas allows it + accumulate)
@@ -38,7 +38,7 @@ def test_one_kernel_pipeline_modes(gpu_ctx, b2pt, monkeypatch):
     for flags in (0, b2pt.FLAG_NO_TAIL, b2pt.FLAG_NO_OVERLAP, b2pt.FLAG_KILL_ZERO_THROUGHPUT, b2pt.FLAG_NO_AA,
                   b2pt.FLAG_NO_DEDUP, b2pt.FLAG_NO_PRIMARY_MASKS):
         a, sa = render(gpu_ctx, 24, 50, flags)
-        b, sb = render(gpu_ctx, 24, 50, flags | b2pt.FLAG_SPLIT_BOUNCE)
+        b, sb = render(gpu_ctx, 24, 50, flags | b2pt.FLAG_ONE_KERNEL_BOUNCE)
         assert sa.batches == sb.batches == 6 and sa.segments == sb.segments, flags
         assert same(a, b), flags
     for per_warp, loop_rays in (("100000", "24576"), ("100000", "100000000"), ("256", "0")):
@@ -46,7 +46,7 @@ def test_one_kernel_pipeline_modes(gpu_ctx, b2pt, monkeypatch):
         monkeypatch.setenv("B2PT_TAIL_LOOP_RAYS", loop_rays)
         for depth in (50, 3, 2):
             a, sa = render(gpu_ctx, 24, depth, 0)
-            b, sb = render(gpu_ctx, 24, depth, b2pt.FLAG_SPLIT_BOUNCE)
+            b, sb = render(gpu_ctx, 24, depth, b2pt.FLAG_ONE_KERNEL_BOUNCE)
             assert sa.segments == sb.segments and same(a, b), (per_warp, loop_rays, depth)
     monkeypatch.delenv("B2PT_TAIL_RAYS_PER_WARP")
     monkeypatch.delenv("B2PT_TAIL_LOOP_RAYS")
@@ -54,7 +54,7 @@ def test_one_kernel_pipeline_modes(gpu_ctx, b2pt, monkeypatch):
     gpu_ctx.set_camera(b2pt.Camera(64, 48))
     for depth in (1, 2, 5, 30):
         a, sa = render(gpu_ctx, 5, depth, b2pt.FLAG_REFERENCE_STREAM)
-        b, sb = render(gpu_ctx, 5, depth, b2pt.FLAG_REFERENCE_STREAM | b2pt.FLAG_SPLIT_BOUNCE)
+        b, sb = render(gpu_ctx, 5, depth, b2pt.FLAG_REFERENCE_STREAM | b2pt.FLAG_ONE_KERNEL_BOUNCE)
         assert sa.segments == sb.segments and same(a, b), depth
 
 
@@ -63,12 +63,12 @@ def test_one_kernel_pipeline_views_and_memory_budget(gpu_ctx, b2pt):
     views = np.array([[c + 2.2 * np.cos(t), c, c + 2.2 * np.sin(t), c, c, c, 0, 1, 0, 40.0]
                       for t in np.linspace(0.2, 6.0, 9)], np.float32)
     a = gpu_ctx.render_views(views, 64, 64, 10, 5)
-    b = gpu_ctx.render_views(views, 64, 64, 10, 5, flags=b2pt.FLAG_SPLIT_BOUNCE)
+    b = gpu_ctx.render_views(views, 64, 64, 10, 5, flags=b2pt.FLAG_ONE_KERNEL_BOUNCE)
     assert same(a, b)
     # a memory budget only changes the batch split
     gpu_ctx.set_camera(b2pt.Camera(512, 512))
     want, s0 = render(gpu_ctx, 64, 8, 0)
-    gpu_ctx.set_memory_budget(3 << 30)  # 3 GiB for the records in flight: 512*512*64 paths x 432 B = 7.2 GB do not fit
+    gpu_ctx.set_memory_budget(3 << 30)  # 3 GiB for the records in flight: 512*512*64 paths x 272 B = 4.6 GB do not fit
     try:
         got, s1 = render(gpu_ctx, 64, 8, 0)
     finally:
