@@ -147,6 +147,7 @@ struct b2pt_ctx
   DevBuf<B2Sphere> dSph;
   DevBuf<B2GateBox> dGates;
   int32_t tracedQuads = 0, tracedSph = 0, bvhNodes = 0;
+  float sortLo[3] = { 0.f, 0.f, 0.f }, sortHi[3] = { 1.f, 1.f, 1.f }; // scene box (cells of the ray sort)
   uint32_t builtFlags = 0;
 
   // camera
@@ -168,6 +169,8 @@ struct b2pt_ctx
     DevBuf<uint32_t> binCode[2];
     DevBuf<uint32_t> regionCounts; // qCount[numWarps] + two sets of bin counts [4*numWarps]
     DevBuf<float4> rad;
+    DevBuf<uint32_t> sortKeys, sortPerm, sortHist; // BVH scenes: spatial sort of the ray queue (b2pt_kernels.cu)
+    DevBuf<unsigned char> sortTemp;
     void release_all()
     {
       for (auto& q : queue)
@@ -179,6 +182,7 @@ struct b2pt_ctx
         c.release();
       regionCounts.release();
       rad.release();
+      sortKeys.release(), sortPerm.release(), sortHist.release(), sortTemp.release();
     }
   } bufs[kMaxSets];
   cudaStream_t extra[kMaxSets] = {}; // own non-blocking streams of sets 1.. (set 0 runs on `stream`)
@@ -872,6 +876,18 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
     }
     return B2PT_OK;
   }
+  for (int c = 0; c < 3; ++c)
+    ctx->sortLo[c] = FLT_MAX, ctx->sortHi[c] = -FLT_MAX;
+  for (int32_t k : keptQuads)
+  {
+    float a[3], b[3];
+    b2pt::quad_aabb(ctx->quads[(size_t)k], a, b);
+    for (int c = 0; c < 3; ++c)
+      ctx->sortLo[c] = std::fmin(ctx->sortLo[c], a[c]), ctx->sortHi[c] = std::fmax(ctx->sortHi[c], b[c]);
+  }
+  for (const B2Sphere& sp : ctx->sph)
+    for (int c = 0; c < 3; ++c)
+      ctx->sortLo[c] = std::fmin(ctx->sortLo[c], sp.c[c] - sp.r), ctx->sortHi[c] = std::fmax(ctx->sortHi[c], sp.c[c] + sp.r);
   std::vector<B2BvhNode> nodes;
   std::vector<int32_t> slots;
   std::vector<int32_t> treeQuads; // gated quads stay out of the tree (tested after the traversal)
@@ -1323,6 +1339,8 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
   const int blocksPerSM = fused ? std::min(ctx->cfg.traceBlocksPerSM[1][0], ctx->cfg.bounceBlocksPerSM)
                                 : std::min(ctx->cfg.traceBlocksPerSM[0][ctx->useBvh ? (ctx->bvh.wide ? 2 : 1) : 0],
                                            ctx->cfg.shadeBlocksPerSM[0][ctx->useBvh ? 1 : 0]);
+  // BVH scenes: the ray queue is sorted spatially before every region-mode bounce (B2PT_FLAG_NO_RAY_SORT: queue order)
+  const bool raySort = ctx->useBvh && !(flags & B2PT_FLAG_NO_RAY_SORT) && !refStream;
   const int wpb = b2pt::warps_per_block();
   auto make_plan = [&](int64_t target, int64_t setsMax) {
     Plan P;
@@ -1373,6 +1391,13 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
         e = bb.regionCounts.reserve((size_t)P.numWarps * 9);
       if (e == cudaSuccess)
         e = bb.rad.reserve((size_t)P.pathsPerBatch);
+      if (e == cudaSuccess && raySort)
+      {
+        if ((e = bb.sortKeys.reserve((size_t)P.queueCap)) == cudaSuccess &&
+            (e = bb.sortPerm.reserve((size_t)P.queueCap)) == cudaSuccess &&
+            (e = bb.sortHist.reserve((size_t)b2pt::sort_buckets())) == cudaSuccess)
+          e = bb.sortTemp.reserve(b2pt::sort_temp_bytes());
+      }
       if (e != cudaSuccess)
         return e;
     }
@@ -1562,6 +1587,14 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
                                   ctx->lights, A, bs));
         ++launches;
         break;
+      }
+      A.perm = nullptr;
+      if (raySort && depth >= 1 && mode != b2pt::B2PT_BOUNCE_TAIL)
+      { // queue regions of k_shade(depth - 1) -> permutation by origin cell and direction octant
+        CU(b2pt::launch_sort_rays(A, ctx->sortLo, ctx->sortHi, bb.sortHist.p, bb.sortKeys.p, bb.sortPerm.p,
+                                  bb.sortTemp.p, bb.sortTemp.cap, bs));
+        A.perm = bb.sortPerm.p;
+        launches += 3;
       }
       CU(b2pt::launch_bounce(ctx->cfg, depth == 0, mode, ctx->cam, ctx->useBvh ? nullptr : &ctx->small,
                              ctx->useBvh ? &ctx->bvh : nullptr, ctx->lights, A, bs, mid));

@@ -26,6 +26,7 @@
 
 #include <algorithm>
 #include <cooperative_groups.h>
+#include <cub/device/device_scan.cuh>
 #include <type_traits>
 
 namespace b2pt
@@ -172,6 +173,71 @@ __device__ __forceinline__ void finish_path(const B2RenderArgs& A, uint32_t pid,
   }
 }
 
+// ---- spatial sorting of the ray queue (BVH scenes).  Incoherent secondary rays make every lane of a warp walk its
+// own root-to-leaf path: dependent node fetches that miss L1, lanes that drift apart.  Between k_shade and k_trace the
+// queue is therefore bucketed by the ray origin's cell (64^3 Morton cells of the scene box) and direction octant --
+// a counting sort: k_sort_keys (keys + histogram), an exclusive scan, k_sort_scatter (permutation) -- and k_trace deals
+// each warp a contiguous chunk of the sorted order, so the rays a warp traces together start in one neighbourhood and
+// share most of their descent.  The rays themselves stay where k_shade put them (one 4-byte index per ray moves).
+// Which rays share a warp never changes a result: every path's arithmetic and its radiance slot are its own.
+constexpr int kSortCellBits = 6;                                   // cells per axis = 64
+constexpr int kSortBuckets = 1 << (3 * kSortCellBits + 3);         // x octants = 2 Mi buckets
+__device__ __forceinline__ int64_t sorted_chunk(const B2RenderArgs& A, int depth)
+{
+  if (!A.perm || depth < 1)
+    return 0;
+  const int64_t total = (int64_t)A.depthTotals[depth - 1];
+  return (((total + A.numWarps - 1) / A.numWarps) + 31) & ~(int64_t)31;
+}
+__device__ __forceinline__ uint32_t spread3(uint32_t v)
+{ // 6 bits -> every third bit
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+struct SortBox
+{
+  float lo[3], cellsPerUnit[3];
+};
+template <bool SCATTER>
+__global__ void __launch_bounds__(kBlock)
+  k_sort_rays(const __grid_constant__ B2RenderArgs A, const __grid_constant__ SortBox box, uint32_t* __restrict__ hist,
+              uint32_t* __restrict__ keys, uint32_t* __restrict__ perm)
+{
+  const int w = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= A.numWarps)
+    return;
+  const int64_t base = (int64_t)w * A.regionCap;
+  const uint32_t n = A.qCount[w];
+  for (uint32_t i = lane; i < n; i += 32)
+  {
+    if (SCATTER)
+    { // hist holds the exclusive scan: bucket start offsets, bumped per ray
+      const uint32_t key = keys[base + i];
+      perm[atomicAdd(&hist[key], 1u)] = (uint32_t)(base + i);
+    }
+    else
+    {
+      const uint4 a = __ldcg(A.q.p0 + base + i), b = __ldcg(A.q.p1 + base + i);
+      const float o[3] = { __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z) };
+      const float d[3] = { __uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y) };
+      uint32_t key = 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+      {
+        const float f = (o[c] - box.lo[c]) * box.cellsPerUnit[c];
+        const int cell = f > 0.f ? (f < (float)((1 << kSortCellBits) - 1) ? (int)f : (1 << kSortCellBits) - 1) : 0;
+        key |= spread3((uint32_t)cell) << c;
+      }
+      key = (key << 3) | (d[0] < 0.f ? 1u : 0u) | (d[1] < 0.f ? 2u : 0u) | (d[2] < 0.f ? 4u : 0u);
+      keys[base + i] = key;
+      atomicAdd(&hist[key], 1u);
+    }
+  }
+}
+
 // K1+K2 (+ the sorting half of K5): closest hit of every ray of the warp's queue region (PRIMARY: of freshly
 // generated camera rays).  Paths that miss or land on an emitter finish here (their radiance is final); every
 // other hit is binned by what the shade stage will do with it -- bin 0: specular (dielectric) hit, bins 1..3:
@@ -217,6 +283,7 @@ __device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhS
     nLocal = tiles > w ? ((tiles - 1 - w) / tailWarps + 1) * 32 : 0;
   }
   const int64_t stride = TAIL ? tailWarps : (int64_t)A.numWarps;
+  const int64_t permBase = sorted_chunk(A, depth) * w; // (sorted input: this warp's chunk of the permutation)
   uint32_t cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
   int64_t next = 0;
   bool has = false, done = false;
@@ -237,7 +304,8 @@ __device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhS
       if (!has && r < nLocal)
       {
         const int64_t idx = PRIMARY ? (primary_tile(r >> 5, w, A.numWarps) << 5) + (r & 31)
-                                    : (TAIL ? ((((r >> 5) * stride + w) << 5) + (r & 31)) : base + r);
+                                    : (TAIL ? ((((r >> 5) * stride + w) << 5) + (r & 31))
+                                            : (A.perm ? (int64_t)__ldg(A.perm + permBase + r) : base + r));
         if (PRIMARY ? idx < A.nPaths : (TAIL ? idx < nIn : true))
         {
           load_ray<PRIMARY>(cam, A, idx, o, d, T, pid, rng);
@@ -442,9 +510,11 @@ __device__ __forceinline__ void trace_body_wide(const B2Camera& cam, const B2Bvh
     nLocal = tiles > w ? ((tiles - 1 - w) / tailWarps + 1) * 32 : 0;
   }
   const int64_t stride = TAIL ? tailWarps : (int64_t)A.numWarps;
+  const int64_t permBase = sorted_chunk(A, depth) * w; // (sorted input: this warp's chunk of the permutation)
   auto ray_index = [&](int64_t r) -> int64_t {
     return PRIMARY ? (primary_tile(r >> 5, w, A.numWarps) << 5) + (r & 31)
-                   : (TAIL ? ((((r >> 5) * stride + w) << 5) + (r & 31)) : base + r);
+                   : (TAIL ? ((((r >> 5) * stride + w) << 5) + (r & 31))
+                           : (A.perm ? (int64_t)__ldg(A.perm + permBase + r) : base + r));
   };
   uint32_t cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
   int64_t next = 0;
@@ -737,6 +807,11 @@ __global__ void __launch_bounds__(kBlock, kTraceMinBlocksPerSM)
   }
   else if (PRIMARY)
     nIn = w < A.numWarps ? ((tilesTotal + A.numWarps - 1) / A.numWarps) * 32 : 0; // rounds; the last may be partial
+  else if (A.perm)
+  { // sorted input: chunk w of the permutation (the last chunks may be short or empty)
+    const int64_t total = (int64_t)A.depthTotals[A.depth - 1], chunk = sorted_chunk(A, A.depth);
+    nIn = w < A.numWarps ? max((int64_t)0, min(chunk, total - chunk * w)) : 0;
+  }
   else
     nIn = w < A.numWarps ? (int64_t)A.qCount[w] : 0;
   // CTAs whose eight regions are all empty (deep bounces) leave before staging the scene.
@@ -1521,6 +1596,36 @@ cudaError_t launch_bounce_tail_loop(const B2SmallScene& S, const B2Lights& light
   if (args.depth < 2)
     return cudaErrorInvalidValue;
   k_bounce_tail_loop<B2SmallScene><<<kTailCluster, kTailBlock, 0, stream>>>(S, lights, args);
+  return cudaGetLastError();
+}
+
+size_t sort_temp_bytes()
+{
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, kSortBuckets);
+  return bytes;
+}
+int sort_buckets() { return kSortBuckets; }
+
+cudaError_t launch_sort_rays(const B2RenderArgs& args, const float lo[3], const float hi[3], uint32_t* hist,
+                             uint32_t* keys, uint32_t* perm, void* temp, size_t tempBytes, cudaStream_t stream)
+{
+  SortBox box;
+  for (int c = 0; c < 3; ++c)
+  {
+    box.lo[c] = lo[c];
+    const float ext = hi[c] - lo[c];
+    box.cellsPerUnit[c] = ext > 0.f ? (float)(1 << kSortCellBits) / ext : 0.f;
+  }
+  const int grid = (args.numWarps + kWarps - 1) / kWarps;
+  cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(uint32_t) * kSortBuckets, stream);
+  if (e != cudaSuccess)
+    return e;
+  k_sort_rays<false><<<grid, kBlock, 0, stream>>>(args, box, hist, keys, perm);
+  e = cub::DeviceScan::ExclusiveSum(temp, tempBytes, hist, hist, kSortBuckets, stream);
+  if (e != cudaSuccess)
+    return e;
+  k_sort_rays<true><<<grid, kBlock, 0, stream>>>(args, box, hist, keys, perm);
   return cudaGetLastError();
 }
 

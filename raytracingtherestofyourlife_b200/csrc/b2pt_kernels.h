@@ -43,6 +43,13 @@ cudaError_t launch_bounce_fused(const LaunchCfg& cfg, int mode, const B2SmallSce
                                 const B2RenderArgs& args, cudaStream_t stream);
 cudaError_t launch_bounce_tail_loop(const B2SmallScene& S, const B2Lights& lights, const B2RenderArgs& args,
                                     cudaStream_t stream);
+// Spatial sort of the ray queue of a BVH scene (region mode, after k_shade of bounce args.depth - 1): fills perm[] with
+// the queue entries ordered by origin cell (64^3 cells of [lo, hi]) and direction octant.  hist: sort_buckets()
+// counters, keys / perm: one uint32 per queue entry, temp: sort_temp_bytes() of scan scratch.
+size_t sort_temp_bytes();
+int sort_buckets();
+cudaError_t launch_sort_rays(const B2RenderArgs& args, const float lo[3], const float hi[3], uint32_t* hist,
+                             uint32_t* keys, uint32_t* perm, void* temp, size_t tempBytes, cudaStream_t stream);
 // Every bounce from args.depth (>= 1, global-queue mode) to args.maxDepth-1 in one launch of a single thread-block
 // cluster; stops early when the queue runs empty.
 cudaError_t launch_tail_loop(const B2Camera& cam, const B2SmallScene* small, const B2BvhScene* bvh,

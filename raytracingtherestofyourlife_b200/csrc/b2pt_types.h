@@ -283,6 +283,10 @@ struct B2RenderArgs
   // candidate masks and B2PT_SMALL_MAX_QUADS per-quad constants
   const uint2* primMask;
   const B2PrimQuad* primQuads;
+  // BVH pipeline, bounces >= 1 in region mode: the rays of the queue in spatially sorted order (k_sort_keys /
+  // k_sort_scatter: perm[j] = queue entry of the j-th ray by origin cell and direction octant); warp w traces the
+  // chunk [w*chunk, (w+1)*chunk) of it, chunk = total / numWarps rounded up to whole tiles.  nullptr = queue order.
+  const uint32_t* perm;
   int64_t binStride;    // numWarps * regionCap
   int64_t nPaths;       // paths in this batch (N * samplesInBatch)
   int32_t numWarps;

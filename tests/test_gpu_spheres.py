@@ -141,3 +141,32 @@ def test_gpu_lbvh_equals_host_sah_on_the_million_sphere_scene(b2pt):
     assert eq.mean() > 0.9999
     assert sb.bvhNodes == 2 * (n + 2)
     print("host SAH build %.3f s, device LBVH build %.3f s" % (host_s, gpu_s))
+
+
+@pytest.mark.parametrize("n,W,H,spp,depth", [(9, 64, 36, 8, 6), (300, 64, 36, 8, 6), (20000, 192, 108, 8, 12)])
+def test_wide_tree_and_ray_sort_change_nothing(b2pt, n, W, H, spp, depth, monkeypatch):
+    """The 8-wide compressed tree against the binary tree it was collapsed from, and the spatially sorted ray order
+    against queue order: different node visits, different warps -- the same closest hits, the same paths, the same
+    image, bit for bit (several batches in flight so that the tail modes take part)."""
+    s = b2pt.Scene.spheres(n)
+    monkeypatch.setenv("B2PT_BATCH_PATHS", str(W * H * 2))
+    monkeypatch.setenv("B2PT_VALIDATE_BVH", "1")
+    ref = None
+    F = b2pt.FLAG_FORCE_BVH
+    for flags in (F, F | b2pt.FLAG_BINARY_BVH, F | b2pt.FLAG_NO_RAY_SORT, F | b2pt.FLAG_BINARY_BVH | b2pt.FLAG_NO_RAY_SORT,
+                  F | b2pt.FLAG_NO_TAIL, F | b2pt.FLAG_GPU_LBVH):
+        with b2pt.Context(0) as ctx:
+            ctx.set_scene(s)
+            ctx.build_bvh(flags)
+            ctx.set_camera(b2pt.Camera(W, H))
+            prim, t = ctx.primary_hits()
+            ctx.render(spp, depth, flags)
+            img, st = ctx.read_color().copy(), ctx.stats()
+        assert st.tracePath == 1 and st.batches == 4
+        cur = (prim, t.view(np.uint32), img.view(np.uint32), st.segments)
+        if ref is None:
+            ref = cur
+        else:
+            assert np.array_equal(ref[0], cur[0]) and np.array_equal(ref[1], cur[1]), flags
+            assert ref[3] == cur[3], flags
+            assert np.array_equal(ref[2], cur[2]), flags
