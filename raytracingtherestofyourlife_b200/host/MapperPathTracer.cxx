@@ -8,6 +8,8 @@
 #include <vector>
 
 #include "b2pt_facade.h"
+
+#include <algorithm>
 #include "pathtracing/Camera.h"
 #include "pathtracing/PathTracer.h"
 
@@ -119,19 +121,26 @@ void MapperPathTracer::UploadScene(const vtkm::cont::CoordinateSystem& coord,
   for (vtkm::Id l = 0; l < light_sphere_pointids.GetNumberOfValues(); ++l)
     lightR.push_back(l < nS ? SphereRadii.ReadPortal().Get(l) : 0.f); // radii.Get(i), PdfWorklet.h:205
   const int nLightSph = nS > 0 ? static_cast<int>(light_sphere_pointids.GetNumberOfValues()) : 0;
-  b2pt_facade::Check(b2pt_set_scene(
-    b2pt_facade::Context(), reinterpret_cast<const float*>(pts.GetStorage()), nPts,
-    reinterpret_cast<const int64_t*>(QuadIds.GetStorage()), nQ, reinterpret_cast<const int64_t*>(SphereIds.GetStorage()),
-    SphereRadii.GetStorage(), nS, reinterpret_cast<const int64_t*>(matIdx[0].GetStorage()),
-    reinterpret_cast<const int64_t*>(texIdx[0].GetStorage()), reinterpret_cast<const int64_t*>(matIdx[1].GetStorage()),
-    reinterpret_cast<const int64_t*>(texIdx[1].GetStorage()), MatType.GetStorage(),
-    static_cast<int>(MatType.GetNumberOfValues()), TexType.GetStorage(), static_cast<int>(TexType.GetNumberOfValues()),
-    reinterpret_cast<const float*>(Tex.GetStorage()), static_cast<int>(Tex.GetNumberOfValues()),
-    reinterpret_cast<const int64_t*>(light_box_pointids.GetStorage()),
-    static_cast<int>(light_box_pointids.GetNumberOfValues()),
-    reinterpret_cast<const int64_t*>(light_sphere_pointids.GetStorage()), lightR.data(), nLightSph, /*lightables*/ 2,
-    /*ref_idx, MapperPathTracer.cxx:467*/ 1.5f));
-  b2pt_facade::Check(b2pt_build_bvh(b2pt_facade::Context()));
+  // every device of SetDevices gets the scene (replicated: a few KB for the Cornell box, < 100 MB for a million spheres)
+  std::vector<int> devs = Devices;
+  if (devs.empty())
+    devs.push_back(-1);
+  for (int dev : devs)
+  {
+    b2pt_ctx* ctx = b2pt_facade::Context(dev);
+    b2pt_facade::Check(b2pt_set_scene(
+      ctx, reinterpret_cast<const float*>(pts.GetStorage()), nPts, reinterpret_cast<const int64_t*>(QuadIds.GetStorage()),
+      nQ, reinterpret_cast<const int64_t*>(SphereIds.GetStorage()), SphereRadii.GetStorage(), nS,
+      reinterpret_cast<const int64_t*>(matIdx[0].GetStorage()), reinterpret_cast<const int64_t*>(texIdx[0].GetStorage()),
+      reinterpret_cast<const int64_t*>(matIdx[1].GetStorage()), reinterpret_cast<const int64_t*>(texIdx[1].GetStorage()),
+      MatType.GetStorage(), static_cast<int>(MatType.GetNumberOfValues()), TexType.GetStorage(),
+      static_cast<int>(TexType.GetNumberOfValues()), reinterpret_cast<const float*>(Tex.GetStorage()),
+      static_cast<int>(Tex.GetNumberOfValues()), reinterpret_cast<const int64_t*>(light_box_pointids.GetStorage()),
+      static_cast<int>(light_box_pointids.GetNumberOfValues()),
+      reinterpret_cast<const int64_t*>(light_sphere_pointids.GetStorage()), lightR.data(), nLightSph, /*lightables*/ 2,
+      /*ref_idx, MapperPathTracer.cxx:467*/ 1.5f));
+    b2pt_facade::Check(b2pt_build_bvh(ctx));
+  }
 }
 
 void MapperPathTracer::buildBVH(const vtkm::cont::CoordinateSystem& coord,
@@ -217,22 +226,45 @@ void MapperPathTracer::RenderCellsImpl(const vtkm::cont::DynamicCellSet& cellset
   texIdArray.Allocate(nx * ny);
   buildBVH(coords, QuadIds, SphereIds, SphereRadii, matIdArray, texIdArray, MatIdx, TexIdx);
 
-  b2pt_ctx* ctx = b2pt_facade::Context();
   const auto pos = camera.GetPosition(), at = camera.GetLookAt(), up = camera.GetViewUp();
   const float p[3] = { pos[0], pos[1], pos[2] }, a[3] = { at[0], at[1], at[2] }, u[3] = { up[0], up[1], up[2] };
-  b2pt_facade::Check(
-    b2pt_set_camera(ctx, p, a, u, camera.GetFieldOfView(), static_cast<int>(nx), static_cast<int>(ny)));
-  b2pt_facade::Check(b2pt_seed(ctx, 0)); // seeds[i] = i, MapperPathTracer.cxx:265-267
-  b2pt_facade::Check(b2pt_render(ctx, samplecount, depthcount, RenderFlags));
+  std::vector<int> devs = Devices;
+  if (devs.empty())
+    devs.push_back(-1);
+  const int G = static_cast<int>(devs.size());
+  std::vector<b2pt_ctx*> ctxs;
+  for (int dev : devs)
+    ctxs.push_back(b2pt_facade::Context(dev));
+  // Device g renders the global samples [g*S/G, (g+1)*S/G) of every pixel.  The calls return once the work is queued
+  // on the device's own stream, so the G GPUs render side by side; the sums are then added across the devices.
+  for (int g = 0; g < G; ++g)
+  {
+    b2pt_ctx* ctx = ctxs[static_cast<size_t>(g)];
+    b2pt_facade::Check(
+      b2pt_set_camera(ctx, p, a, u, camera.GetFieldOfView(), static_cast<int>(nx), static_cast<int>(ny)));
+    b2pt_facade::Check(b2pt_seed(ctx, 0)); // seeds[i] = i, MapperPathTracer.cxx:265-267
+    const int begin = static_cast<int>(static_cast<long long>(samplecount) * g / G);
+    const int end = static_cast<int>(static_cast<long long>(samplecount) * (g + 1) / G);
+    b2pt_facade::Check(b2pt_clear_color(ctx)); // MapperPathTracer.cxx:222-223
+    b2pt_facade::Check(b2pt_render_range(ctx, begin, end - begin, depthcount, RenderFlags));
+  }
+  if (G > 1)
+    b2pt_facade::Check(b2pt_allreduce(ctxs.data(), G));
+  b2pt_ctx* ctx = ctxs[0];
   auto& cols = canvas->GetColorBuffer();
   if (cols.GetNumberOfValues() != nx * ny)
     cols.Allocate(nx * ny);
   static_assert(sizeof(vtkm::Vec<vtkm::Float32, 4>) == 16, "packed Vec4");
   b2pt_facade::Check(b2pt_read_color(ctx, reinterpret_cast<float*>(cols.GetStorage())));
   b2pt_stats st;
-  b2pt_facade::Check(b2pt_get_stats(ctx, &st));
-  LastRenderMs = st.renderMs;
-  LastSegments = st.segments;
+  LastRenderMs = 0.0;
+  LastSegments = 0;
+  for (b2pt_ctx* c : ctxs)
+  {
+    b2pt_facade::Check(b2pt_get_stats(c, &st));
+    LastRenderMs = std::max(LastRenderMs, st.renderMs);
+    LastSegments += st.segments;
+  }
 }
 
 void MapperPathTracer::RenderCells(const vtkm::cont::DynamicCellSet& cellset, const vtkm::cont::CoordinateSystem& coords,

@@ -91,6 +91,12 @@ public:
 
   // B200 additions (not in the reference): render flags (B2PT_FLAG_*) and the statistics of the last render.
   void SetRenderFlags(unsigned int flags) { RenderFlags = flags; }
+  // The GPUs RenderCells uses (CUDA device ordinals; default: the one of B2PT_DEVICE).  With G > 1 devices the samples
+  // of every pixel are partitioned over them -- device g renders a contiguous range of the global sample indices with
+  // the same per-(pixel, sample) streams a single GPU would use -- and the radiance sums are added over NVLink
+  // (b2pt_allreduce) before the canvas is read back: the single-process form of the sample-sharded render.
+  void SetDevices(const std::vector<int>& devices) { Devices = devices; }
+  const std::vector<int>& GetDevices() const { return Devices; }
   // Many cameras, one call: what main.cc's generateHemisphere / fibonacciHemisphere loops do by calling RenderCells
   // per view point (main.cc:431-561).  Every camera renders onto a canvas of the size of the canvas set with
   // SetCanvas; image v lands in colors[v] exactly as RenderCells would leave it in canvas->GetColorBuffer()
@@ -130,6 +136,7 @@ private:
   [[noreturn]] static void FusedStage(const char* name);
 
   unsigned int RenderFlags = 0;
+  std::vector<int> Devices; // empty = the default device
   double LastRenderMs = 0.0;
   long long LastSegments = 0;
   vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Id, 5>> light_box_pointids;

@@ -1,35 +1,48 @@
 #include "b2pt_facade.h"
 
 #include <cstdlib>
+#include <map>
 #include <mutex>
 
 namespace b2pt_facade
 {
 namespace
 {
-b2pt_ctx* g_ctx = nullptr;
+std::map<int, b2pt_ctx*> g_ctx; // one libb2pt context per GPU, created on first use
 std::mutex g_mutex;
 }
 
-b2pt_ctx* Context()
+int DefaultDevice()
+{
+  const char* dev = std::getenv("B2PT_DEVICE");
+  return dev ? std::atoi(dev) : 0;
+}
+
+b2pt_ctx* Context(int device)
 {
   std::lock_guard<std::mutex> lock(g_mutex);
-  if (!g_ctx)
+  if (device < 0)
+    device = DefaultDevice();
+  b2pt_ctx*& ctx = g_ctx[device];
+  if (!ctx)
   {
-    const char* dev = std::getenv("B2PT_DEVICE");
     int err = 0;
-    g_ctx = b2pt_create(dev ? std::atoi(dev) : 0, &err);
-    if (!g_ctx)
+    ctx = b2pt_create(device, &err);
+    if (!ctx)
+    {
+      g_ctx.erase(device);
       Check(err);
+    }
   }
-  return g_ctx;
+  return ctx;
 }
 
 void ReleaseContext()
 {
   std::lock_guard<std::mutex> lock(g_mutex);
-  if (g_ctx)
-    b2pt_destroy(g_ctx);
-  g_ctx = nullptr;
+  for (auto& kv : g_ctx)
+    if (kv.second)
+      b2pt_destroy(kv.second);
+  g_ctx.clear();
 }
 } // namespace b2pt_facade

@@ -1,4 +1,4 @@
-// b2pt_facade.h -- glue shared by the facade classes: the process-wide libb2pt context (one per GPU, created
+// b2pt_facade.h -- glue shared by the facade classes: the process-wide libb2pt contexts (one per GPU, created
 // on first use) and the status -> exception mapping.  The facade calls ONLY the C-ABI of include/b2pt.h.
 #ifndef b2pt_facade_h
 #define b2pt_facade_h
@@ -24,9 +24,10 @@ inline void Check(int rc)
   throw vtkm::cont::ErrorExecution("libb2pt: " + msg);
 }
 
-// Device selected with B2PT_DEVICE (default 0).
-b2pt_ctx* Context();
-void ReleaseContext();
+// The context of one GPU; device < 0 = the default device, selected with B2PT_DEVICE (default 0).
+int DefaultDevice();
+b2pt_ctx* Context(int device = -1);
+void ReleaseContext(); // destroys every context
 
 } // namespace b2pt_facade
 #endif

@@ -1,5 +1,6 @@
 // test_facade.cc -- C++ tests of the drop-in facade, written against the reference's class surface.
 //   test_facade --cpu            host-only behaviour (containers, validation, error messages); no GPU needed
+//   test_facade --multigpu G     MapperPathTracer::SetDevices on G GPUs of this box against the one-GPU render
 //   test_facade --gpu <prefix>   renders through MapperPathTracer / Camera::CreateRays / intersect on cuda:0 and
 //                                writes <prefix>_*.bin for tests/test_facade.py to compare with the oracle
 #include <cmath>
@@ -286,6 +287,63 @@ static void testGpu(const std::string& prefix)
   b2pt_facade::ReleaseContext();
 }
 
+// MapperPathTracer::SetDevices: G GPUs driven from this one process, samples partitioned, sums added by
+// b2pt_allreduce (reduce-scatter by k_sum_peers over NVLink peer access + all-gather).  The G-GPU image must equal the
+// one-GPU image up to the order of the float additions (identical per-sample radiance, NaN-poisoned pixels included).
+static void testMultiGpu(int G)
+{
+  CornellBox cb;
+  cb.buildDataSet();
+  const int W = 256, H = 192, spp = 24, depth = 12;
+  vtkm::rendering::Camera cam;
+  cam.SetPosition(vec3(278 / 555.0, 278 / 555.0, -800 / 555.0));
+  cam.SetFieldOfView(40.);
+  cam.SetViewUp(vec3(0, 1, 0));
+  cam.SetLookAt(vec3(278 / 555.0, 278 / 555.0, 278 / 555.0));
+  vtkm::cont::Field field;
+  vtkm::cont::ColorTable ct;
+  vtkm::Range sr;
+  std::vector<float> one, many;
+  long long segOne = 0, segMany = 0;
+  for (int pass = 0; pass < 2; ++pass)
+  {
+    vtkm::rendering::CanvasRayTracer canvas(W, H);
+    vtkm::rendering::MapperPathTracer mapper(spp, depth, cb.matIdx, cb.texIdx, cb.matType, cb.texType, cb.tex);
+    mapper.SetCanvas(&canvas);
+    std::vector<int> devs;
+    for (int g = 0; g < (pass == 0 ? 1 : G); ++g)
+      devs.push_back(g);
+    mapper.SetDevices(devs);
+    mapper.RenderCells(cb.ds.GetCellSet(), cb.coord, field, ct, cam, sr);
+    const float* c = reinterpret_cast<const float*>(canvas.GetColorBuffer().GetStorage());
+    (pass == 0 ? one : many).assign(c, c + size_t(W) * H * 4);
+    (pass == 0 ? segOne : segMany) = mapper.GetLastSegments();
+  }
+  CHECK(segOne == segMany && segOne > (long long)W * H * spp);
+  size_t bad = 0, nan = 0;
+  double maxRel = 0.0;
+  for (size_t i = 0; i < one.size(); ++i)
+  {
+    if ((i & 3) == 3)
+      continue; // alpha lane
+    const bool n0 = one[i] != one[i], n1 = many[i] != many[i];
+    nan += n0;
+    if (n0 != n1)
+      ++bad;
+    else if (!n0)
+    {
+      const double rel = std::fabs((double)one[i] - (double)many[i]) / std::max(1e-3, std::fabs((double)one[i]));
+      maxRel = std::max(maxRel, rel);
+      if (rel > 1e-5)
+        ++bad;
+    }
+  }
+  std::printf("multi-GPU facade: %d devices, %lld segments, max rel diff %.3g, %zu NaN channels, %zu mismatches\n", G,
+              segMany, maxRel, nan, bad);
+  CHECK(bad == 0);
+  b2pt_facade::ReleaseContext();
+}
+
 int main(int argc, char** argv)
 {
   if (argc >= 2 && !std::strcmp(argv[1], "--cpu"))
@@ -307,9 +365,21 @@ int main(int argc, char** argv)
       ++g_fail;
     }
   }
+  else if (argc >= 3 && !std::strcmp(argv[1], "--multigpu"))
+  {
+    try
+    {
+      testMultiGpu(std::atoi(argv[2]));
+    }
+    catch (const vtkm::cont::Error& e)
+    {
+      std::printf("FAIL exception: %s\n", e.GetMessage().c_str());
+      ++g_fail;
+    }
+  }
   else
   {
-    std::printf("usage: test_facade --cpu | --gpu <prefix>\n");
+    std::printf("usage: test_facade --cpu | --gpu <prefix> | --multigpu <G>\n");
     return 2;
   }
   std::printf(g_fail ? "%d check(s) FAILED\n" : "all facade checks passed\n", g_fail);

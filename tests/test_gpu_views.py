@@ -105,7 +105,7 @@ def test_views_stats_and_empty(gpu_ctx, b2pt):
     st = gpu_ctx.stats()
     assert st.paths == 4 * W * H * spp
     assert st.batches == 1  # all four views shared every launch
-    assert st.launches <= 2 * depth + 1
+    assert st.launches <= 2 * depth + 2  # k_primary_prep + two per bounce + k_accumulate
     assert gpu_ctx.render_views(np.zeros((0, 10), np.float32), W, H, spp, depth).shape == (0, W * H, 4)
     z = gpu_ctx.render_views(views, W, H, 0, depth)
     assert not z.any()
