@@ -223,7 +223,7 @@ def image_check(img_sum, total_spp, size, depth):
     if size % 256 != 0 or depth != 50 or not os.path.exists(fix):
         return None
     z = np.load(fix)
-    parts = z["parts"].astype(np.float64)  # [8, 256*256, 3] partial means of 512 spp each
+    parts = z["parts"].astype(np.float64)  # [2, 256*256, 3]: two independent halves of 2048 spp each
     f = size // 256
     ref = parts.mean(0).reshape(256, 256, 3)  # NaN wherever a part is NaN
     g_full = (img_sum[:, :3].astype(np.float64) / total_spp).reshape(256, f, 256, f, 3)
@@ -242,7 +242,7 @@ def image_check(img_sum, total_spp, size, depth):
     mo, mg = ref[ok].mean(0), g[ok].mean(0)
     mean_err = (np.abs(mg - mo) / mo).tolist()
     # the fixture's own Monte-Carlo noise at the same block size: half the RMSE between its two halves
-    h0, h1 = blocks(parts[:4].mean(0).reshape(256, 256, 3)), blocks(parts[4:].mean(0).reshape(256, 256, 3))
+    h0, h1 = blocks(parts[0].reshape(256, 256, 3)), blocks(parts[1].reshape(256, 256, 3))
     noise = float(0.5 * np.sqrt(((h0 - h1) ** 2).mean()) / bo.mean())
     return {"rel_rmse_8x8_blocks_vs_reference_stream_256x256_4096spp": rel_rmse, "per_channel_mean_rel_err": mean_err,
             "tolerance": {"rel_rmse": RMSE_TOLERANCE, "per_channel_mean": MEAN_TOLERANCE},

@@ -315,6 +315,9 @@ __device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhS
           found = false;
           best = 0;
           sp = 0;
+#ifdef B2PT_DEBUG_HIST
+          atomicAdd(&g_debugHist[51], 1ull); // binary: rays
+#endif
           done = S.nNodes <= 0;
           cur = done ? 0u : bvh_pack(__ldg(nodes4).w, __ldg(nodes4 + 1).w);
           has = true;
@@ -336,6 +339,9 @@ __device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhS
           break;
         if (!inner)
           continue;
+#ifdef B2PT_DEBUG_HIST
+        atomicAdd(&g_debugHist[48], 1ull); // binary: inner steps (child pairs)
+#endif
         // one 64-byte fetch of the child pair, nearer child first (BVHTraverser.h:189-201)
         const float4* lp = nodes4 + 2 * (size_t)(cur & 0xffffffu);
         const float4 l0 = __ldg(lp), l1 = __ldg(lp + 1), r0 = __ldg(lp + 2), r1 = __ldg(lp + 3);
@@ -364,6 +370,10 @@ __device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhS
       if (has && !done && (cur >> 24))
       { // leaf: primitives in ascending original index
         const uint32_t count = cur >> 24, left = cur & 0xffffffu;
+#ifdef B2PT_DEBUG_HIST
+        atomicAdd(&g_debugHist[49], 1ull);                        // binary: leaves visited
+        atomicAdd(&g_debugHist[50], (unsigned long long)count);   // binary: primitives offered by them
+#endif
         for (uint32_t k0 = 0; k0 < count; k0 += kLeafChunk)
         { // the slots and the leaf-ordered sphere geometry of a chunk are fetched together (independent loads)
           int enc[kLeafChunk];
@@ -389,7 +399,8 @@ __device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhS
                   found = true;
                 }
               }
-              else if (sphere_gate(mk3(geo[j].x, geo[j].y, geo[j].z), geo[j].w, inv, od, 0.001f, FLT_MAX) &&
+              else if (sphere_may_hit(mk3(geo[j].x, geo[j].y, geo[j].z), geo[j].w, o, d) &&
+                       sphere_gate(mk3(geo[j].x, geo[j].y, geo[j].z), geo[j].w, inv, od, 0.001f, FLT_MAX) &&
                        sphere_accept(mk3(geo[j].x, geo[j].y, geo[j].z), geo[j].w, o, d, 0.001f, closest, t))
               {
                 closest = t;
@@ -549,6 +560,9 @@ __device__ __forceinline__ void trace_body_wide(const B2Camera& cam, const B2Bvh
           best = 0;
           bestId = 0x7fffffff;
           myRay = (uint32_t)r;
+#ifdef B2PT_DEBUG_HIST
+          atomicAdd(&g_debugHist[42], 1ull); // wide: rays
+#endif
           wide_start(R, oct, S.nWide > 0);
           has = true;
           live = wide_next(R, stackX, stackY);
@@ -565,13 +579,25 @@ __device__ __forceinline__ void trace_body_wide(const B2Camera& cam, const B2Bvh
       if (__any_sync(0xffffffffu, doA))
       {
         if (doA)
+        {
           wide_step_node(S, R, stackX, stackY, inv, od, oct, 0.001f, closest);
+#ifdef B2PT_DEBUG_HIST
+          atomicAdd(&g_debugHist[40], 1ull); // wide: node visits
+          atomicAdd(&g_debugHist[43], (unsigned long long)__popc(R.ny & 0xffu)); // inner children hit
+          atomicAdd(&g_debugHist[44], (unsigned long long)__popc(R.py & 0xffu)); // primitive children hit (boxes)
+#endif
+        }
       }
       const bool doB = live && (R.py & 0xffu);
       if (__any_sync(0xffffffffu, doB))
       {
         if (doB)
+        {
           wide_step_prim(S, R, o, d, inv, od, oct, 0.001f, FLT_MAX, closest, best, bestId);
+#ifdef B2PT_DEBUG_HIST
+          atomicAdd(&g_debugHist[41], 1ull); // wide: exact primitive tests
+#endif
+        }
       }
       if (live)
         live = wide_next(R, stackX, stackY);
