@@ -54,7 +54,7 @@ typedef enum b2pt_status
 #define B2PT_FLAG_VIEWS_PNM16 0x200u         /* b2pt_render_views: rgbaOut receives uint16_t[nViews*W*H*3], the integers of b2pt_read_pnm16 */
 #define B2PT_FLAG_NO_PRIMARY_MASKS 0x400u    /* trace primary rays with the generic per-ray candidate filter instead of the per-tile candidate masks (A/B parity checks) */
 #define B2PT_FLAG_ONE_KERNEL_BOUNCE 0x800u   /* small scenes: ONE kernel per bounce (k_bounce: shade the hits of bounce d-1, trace bounce d, bin; no ray queue) instead of k_trace + k_shade; bit-identical images, half the HBM traffic, measured slower on B200 */
-#define B2PT_FLAG_BINARY_BVH 0x1000u         /* BVH scenes: traverse the binary tree (32-byte nodes) instead of the 8-wide compressed tree collapsed from it (A/B runs) */
+#define B2PT_FLAG_WIDE_BVH 0x1000u           /* BVH scenes: traverse the 8-wide compressed tree (80-byte nodes, 8-bit quantised child boxes) collapsed from the binary tree instead of the binary tree itself; identical hits, fewer dependent fetches, more instructions -- measured slower on B200, hence opt-in */
 #define B2PT_FLAG_NO_RAY_SORT 0x2000u        /* BVH scenes: trace the ray queue in the order k_shade left it instead of sorted by origin cell and direction octant (A/B runs) */
 #define B2PT_FLAG_NO_AA 0x10u               /* do not use the axis-aligned quad specialisation (A/B parity checks) */
 

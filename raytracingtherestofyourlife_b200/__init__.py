@@ -29,7 +29,7 @@ FLAG_VIEWS_NORMALIZE = 0x100
 FLAG_VIEWS_PNM16 = 0x200
 FLAG_NO_PRIMARY_MASKS = 0x400
 FLAG_ONE_KERNEL_BOUNCE = 0x800
-FLAG_BINARY_BVH = 0x1000
+FLAG_WIDE_BVH = 0x1000
 FLAG_NO_RAY_SORT = 0x2000
 
 ERR_BAD_VALUE, ERR_CUDA, ERR_STATE, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5

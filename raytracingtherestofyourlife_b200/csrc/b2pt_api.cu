@@ -621,7 +621,7 @@ int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t*
 
 static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
 {
-  ctx->builtFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH | B2PT_FLAG_BINARY_BVH);
+  ctx->builtFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH | B2PT_FLAG_WIDE_BVH);
   // Drop bit-identical duplicate quads: a later copy computes the same t and loses the strict t<tmax
   // comparison (Surface.h:178-179), so removing it cannot change any result.
   std::vector<int32_t> keptQuads;
@@ -940,8 +940,11 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
   }
   else
   {
-    if (!b2pt::build_bvh(ctx->quads, treeQuads, ctx->sph, nodes, slots))
+    int binDepth = 0;
+    if (!b2pt::build_bvh(ctx->quads, treeQuads, ctx->sph, nodes, slots, &binDepth))
       return fail(B2PT_ERR_UNSUPPORTED, "scene too large for the 24-bit BVH index packing");
+    if (binDepth > 62) // the traversal stack holds 64 entries (the builder's depth bound keeps real trees far below)
+      return fail(B2PT_ERR_UNSUPPORTED, "BVH is %d levels deep; the traversal stack holds 64 entries", binDepth);
     nNodes = nodes.size();
     CU(ctx->dNodes.reserve(std::max<size_t>(nodes.size(), 1)));
     CU(ctx->dSlots.reserve(std::max<size_t>(slots.size(), 1)));
@@ -1028,12 +1031,12 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
       return fail(B2PT_ERR_STATE, "BVH validation failed: %zu box violations, %zu of %zu slots reached once", bad, once,
                   nSlots);
   }
-  // The traversal kernels walk the 8-wide compressed tree collapsed from the binary one (b2pt_wide.h); primSlots and
-  // leafSph are rewritten in its leaf order.  B2PT_FLAG_BINARY_BVH keeps the binary tree (A/B runs).
+  // B2PT_FLAG_WIDE_BVH: the traversal kernels walk the 8-wide compressed tree collapsed from the binary one
+  // (b2pt_wide.h); primSlots and leafSph are rewritten in its leaf order.  Opt-in (B2PT_FLAG_WIDE_BVH): the binary tree measured faster.
   ctx->bvh.wide = nullptr;
   ctx->bvh.nWide = 0;
   ctx->bvh.wideDepth = 0;
-  if (!(flags & B2PT_FLAG_BINARY_BVH) && nNodes > 0)
+  if ((flags & B2PT_FLAG_WIDE_BVH) && nNodes > 0)
   {
     const size_t nSlots = treeQuads.size() + ctx->sph.size();
     if (nodes.empty())
@@ -1047,7 +1050,7 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
     if (!b2pt::collapse_to_wide(nodes, slots, ctx->quads, ctx->sph, sceneAbs, wr) || wr.slots.size() != nSlots)
       return fail(B2PT_ERR_STATE, "collapsing the BVH into 8-wide nodes failed");
     if (wr.maxDepth > B2PT_WIDE_STACK)
-      return fail(B2PT_ERR_UNSUPPORTED, "8-wide BVH is %d levels deep (limit %d); use B2PT_FLAG_BINARY_BVH", wr.maxDepth,
+      return fail(B2PT_ERR_UNSUPPORTED, "8-wide BVH is %d levels deep (limit %d); drop B2PT_FLAG_WIDE_BVH", wr.maxDepth,
                   B2PT_WIDE_STACK);
     if (getenv("B2PT_VALIDATE_BVH"))
     {
@@ -1092,7 +1095,7 @@ int b2pt_build_bvh_ex(b2pt_ctx* ctx, uint32_t flags)
   if (!ctx->haveScene)
     return fail(B2PT_ERR_STATE, "b2pt_build_bvh before b2pt_set_scene");
   if (int rc = build_trace_structures(
-        ctx, flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH | B2PT_FLAG_BINARY_BVH)))
+        ctx, flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH | B2PT_FLAG_WIDE_BVH)))
     return rc;
   ctx->haveBvh = true;
   return B2PT_OK;
@@ -1305,7 +1308,7 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     return fail(B2PT_ERR_BAD_VALUE, "REFERENCE_STREAM renders samples from 0 (one persistent stream per pixel)");
   // MapperPathTracer::RenderCellsImpl builds its acceleration structures on every call (:275-276); here
   // they are rebuilt only when the scene or the build-affecting flags changed.
-  const uint32_t buildFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH | B2PT_FLAG_BINARY_BVH);
+  const uint32_t buildFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH | B2PT_FLAG_WIDE_BVH);
   if (!ctx->haveBvh || ctx->builtFlags != buildFlags)
   {
     if (int rc = build_trace_structures(ctx, buildFlags))

@@ -233,7 +233,7 @@ struct B2BvhScene
 };
 
 // Same scene, traversed through the 8-wide tree (a distinct type selects the wide traversal kernels at compile time;
-// the binary-tree kernels stay available for A/B runs, B2PT_FLAG_BINARY_BVH).
+// B2PT_FLAG_WIDE_BVH; the binary tree is the default).
 struct B2WideScene : B2BvhScene
 {
 };

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import raytracingtherestofyourlife_b200 as B
 L = B.lib()
 buf = (C.c_ulonglong * 64)()
-for name, flags in (("8-wide tree", 0), ("binary tree", B.FLAG_BINARY_BVH)):
+for name, flags in (("8-wide tree", B.FLAG_WIDE_BVH), ("binary tree", 0)):
     ctx = B.Context(0)
     ctx.set_scene(B.Scene.spheres(1000000)); ctx.build_bvh(flags); ctx.set_camera(B.Camera(1920, 1080))
     L.b2pt_debug_hist(None, 1)
@@ -15,7 +15,7 @@ for name, flags in (("8-wide tree", 0), ("binary tree", B.FLAG_BINARY_BVH)):
     L.b2pt_debug_hist(buf, 0)
     h = list(buf)
     st = ctx.stats()
-    if flags == 0:
+    if flags:
         r = max(h[42], 1)
         print(json.dumps({"tree": name, "rays": h[42], "segments": st.segments, "node_visits_per_ray": h[40] / r,
                           "inner_children_hit_per_visit": h[43] / max(h[40], 1), "prim_boxes_hit_per_visit": h[44] / max(h[40], 1),

@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import raytracingtherestofyourlife_b200 as B
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
-FLAGS = int(os.environ.get("B2PT_FLAGS", "0"))  # 4096 = B2PT_FLAG_BINARY_BVH
+FLAGS = int(os.environ.get("B2PT_FLAGS", "0"))  # 4096 = B2PT_FLAG_WIDE_BVH
 ctx = B.Context(0)
 ctx.set_scene(B.Scene.spheres(n)); ctx.build_bvh(FLAGS); ctx.set_camera(B.Camera(1920, 1080))
 for rep in range(2):

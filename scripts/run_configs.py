@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import raytracingtherestofyourlife_b200 as B
 
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
-FLAGS = int(os.environ.get("B2PT_FLAGS", "0"))  # e.g. 4096 = B2PT_FLAG_BINARY_BVH, 2048 = B2PT_FLAG_ONE_KERNEL_BOUNCE
+FLAGS = int(os.environ.get("B2PT_FLAGS", "0"))  # e.g. 4096 = B2PT_FLAG_WIDE_BVH, 2048 = B2PT_FLAG_ONE_KERNEL_BOUNCE
 spp = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 
 

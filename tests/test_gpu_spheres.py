@@ -153,8 +153,8 @@ def test_wide_tree_and_ray_sort_change_nothing(b2pt, n, W, H, spp, depth, monkey
     monkeypatch.setenv("B2PT_VALIDATE_BVH", "1")
     ref = None
     F = b2pt.FLAG_FORCE_BVH
-    for flags in (F, F | b2pt.FLAG_BINARY_BVH, F | b2pt.FLAG_NO_RAY_SORT, F | b2pt.FLAG_BINARY_BVH | b2pt.FLAG_NO_RAY_SORT,
-                  F | b2pt.FLAG_NO_TAIL, F | b2pt.FLAG_GPU_LBVH):
+    for flags in (F, F | b2pt.FLAG_WIDE_BVH, F | b2pt.FLAG_NO_RAY_SORT, F | b2pt.FLAG_WIDE_BVH | b2pt.FLAG_NO_RAY_SORT,
+                  F | b2pt.FLAG_NO_TAIL, F | b2pt.FLAG_GPU_LBVH, F | b2pt.FLAG_GPU_LBVH | b2pt.FLAG_WIDE_BVH):
         with b2pt.Context(0) as ctx:
             ctx.set_scene(s)
             ctx.build_bvh(flags)
