@@ -351,17 +351,24 @@ __device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhS
         const bool hl = slab_hit_fma(l0, l1, inv, od, 0.001f, closest, tl);
         const bool hr = slab_hit_fma(r0, r1, inv, od, 0.001f, closest, tr);
         const uint32_t cl = bvh_pack(l0.w, l1.w), crr = bvh_pack(r0.w, r1.w);
-        // Branch-free update (the four outcomes -- both / left / right / none -- are selects, so the lanes of an inner
-        // step stay converged): the farther child goes to the slot above the stack top, which only becomes live when
-        // both children were hit; the stack top is read speculatively and only used when neither was.  The builders
-        // bound the tree depth below the 64 entries (build_trace_structures checks it).
-        const bool both = hl && hr, none = !(hl || hr);
-        const bool rightCloser = tl > tr;
-        const uint32_t top = stack[(sp - 1) & 63];
-        stack[sp & 63] = rightCloser ? cl : crr;
-        done = none && sp == 0;
-        cur = none ? top : (both ? (rightCloser ? crr : cl) : (hl ? cl : crr));
-        sp += (both ? 1 : 0) - ((none && sp > 0) ? 1 : 0);
+        // (a branch-free form of this update -- selects, speculative read of the stack top, unconditional store above
+        // it -- keeps the lanes converged but was measured 4.5 % SLOWER: every lane then touches the local-memory
+        // stack every step; profiles/r02_bvh_experiments.md)
+        if (hl && hr)
+        {
+          const bool rightCloser = tl > tr;
+          cur = rightCloser ? crr : cl;
+          if (sp < 64)
+            stack[sp++] = rightCloser ? cl : crr;
+        }
+        else if (hl)
+          cur = cl;
+        else if (hr)
+          cur = crr;
+        else if (sp == 0)
+          done = true;
+        else
+          cur = stack[--sp];
       }
       if (has && !done && (cur >> 24))
       { // leaf: primitives in ascending original index
