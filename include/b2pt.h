@@ -105,6 +105,17 @@ int b2pt_build_bvh(b2pt_ctx* ctx);
  * build flags rebuilds. */
 int b2pt_build_bvh_ex(b2pt_ctx* ctx, uint32_t flags);
 
+/* Moved spheres: new centres (3 floats per sphere, the order of b2pt_set_scene) and, optionally, radii; counts and
+ * materials stay.  The reference has no counterpart (its scene is static); this is the input side of
+ * b2pt_refit_bvh.  Waits for renders in flight. */
+int b2pt_update_spheres(b2pt_ctx* ctx, const float* centers, const float* radii);
+/* Refit instead of rebuild: the tree built by b2pt_build_bvh keeps its topology and every node box is recomputed
+ * bottom-up on the device from the primitives' current geometry (one kernel, atomic arrival counters as in the LBVH
+ * build).  The reference's equivalent is a full LinearBVH::Construct on every RenderCells (QuadIntersector.cxx:134,
+ * SphereIntersector.cxx:75).  Closest hits equal a fresh build's (they do not depend on the tree); traversal slows
+ * down as primitives drift away from the positions the tree was built for.  Binary tree only. */
+int b2pt_refit_bvh(b2pt_ctx* ctx);
+
 /* ---- camera -------------------------------------------------------------------------------- */
 /* Replaces pathtracing::Camera::SetParameters / CreateRaysImpl set-up (pathtracing/Camera.cxx:625-637,
  * 880-960) and the RayGen constructor (:438-476).  fovDeg in (0,180]; W,H > 0 else B2PT_ERR_BAD_VALUE. */
@@ -173,6 +184,17 @@ int b2pt_get_stage_profile(b2pt_ctx* ctx, int maxEntries, float* traceMs, float*
  * code: hit primitive id per pixel (quad q -> q, sphere s -> nQuads+s, miss -> -1) and hit t.
  * Either output may be NULL. */
 int b2pt_primary_hits(b2pt_ctx* ctx, int32_t* primId, float* t);
+/* Replaces the -direct G-buffer passes of main.cc:402-422 (runNorms / runAlbedo through MapperQuadNormals / MapperQuadAlbedo,
+ * raytracing/RayTracerNormals.cxx:47-143 and :234-281, RayTracerAlbedo.cxx:100-143, MapperQuad.cxx:86-150) and the
+ * depth image: one un-jittered ray per pixel (Camera::PerspectiveRayGen, pathtracing/Camera.cxx:394-423), the
+ * closest QUAD hit (the MapperQuad family extracts quads only), then per hit pixel
+ *   normals = (n.x, n.y, n.z, 1)   with n the geometric normal flipped to oppose the ray,
+ *   albedo  = (cosPhi R / (cosTheta L), 1) per channel, L / R / cosines as the reference's Shade computes them with the
+ *             light at camera + 2 up,
+ *   depth   = hit distance along the unit ray (VTK-m's canvas stores a projected depth; not restated),
+ * and (0,0,0,0) / 0 / -1 where nothing is hit.  Host outputs W*H*4, W*H*4, W*H floats and W*H ids; any may be NULL.
+ * Small scenes (kernel-parameter path) only; the Phong colour image of VTK-m's stock shader is out of scope. */
+int b2pt_render_direct(b2pt_ctx* ctx, float* normals, float* albedo, float* depth, int32_t* primId);
 /* Replaces pathtracing::Camera::CreateRays (pathtracing/Camera.cxx:880-960): one jittered primary ray
  * per pixel from the current per-pixel seeds; host outputs, any may be NULL. seedsInOut (W*H) is
  * read as the RNG state and updated (2 draws per pixel). */

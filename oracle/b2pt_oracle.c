@@ -1232,6 +1232,100 @@ int orc_primary_hits(const orc_scene* sc, const orc_camera* cam, uint32_t seedOf
   return 0;
 }
 
+/* ------------------------------------------------------------------------- direct G-buffers */
+/* main.cc:402-422 (-direct): the MapperQuad family casts ONE un-jittered ray per pixel and shades the hit.
+ *  * ray: Camera::PerspectiveRayGen (pathtracing/Camera.cxx:394-423, the reference's copy of VTK-m's generator):
+ *    through the pixel's lower-left corner, dir = nlook + dx*((2i - W)/2) + dy*((2j - H)/2), zero components
+ *    nudged, normalised by division;
+ *  * hit: quads only (MapperQuad.cxx:103-113 extracts quads, no vertices/spheres), closest hit beyond t = 0, the
+ *    normal flipped to oppose the ray (Surface.h:180-186, which restates VTK-m's quad intersector);
+ *  * normals buffer: RayTracerNormals.cxx:137-140 -- (n.x, n.y, n.z, 1) where a quad is hit, untouched elsewhere;
+ *  * albedo buffer: RayTracerAlbedo.cxx:100-143 -- with lightPosition = camera + 2*up (:154-155),
+ *    L = normalize(lightPosition - p), V = normalize(camera - lookAt), cosTheta = clamp(n.L, 0, 1),
+ *    R = normalize(2 (L.n) n - L), cosPhi = R.V: colour k = (cosPhi * R[k]) / (cosTheta * L[k]), alpha 1;
+ *  * depth: the hit distance t along the unit ray (VTK-m's canvas stores a projected depth instead; that conversion
+ *    lives inside VTK-m and is not restated), 0 where nothing is hit.
+ * The colour image of the stock Phong shader ("direct-*.pnm") needs VTK-m's colour table and is out of scope. */
+static inline v3 raygen_corner(const cam_basis* b, int64_t idx)
+{
+  int i = (int)((int32_t)idx % b->W);
+  int j = (int)((int32_t)idx / b->W);
+  v3 d = vadd(vadd(b->nlook, vscale(b->dx, (2.f * (float)i - (float)b->W) / 2.0f)),
+              vscale(b->dy, (2.f * (float)j - (float)b->H) / 2.0f));
+  if (d.x == 0.f)
+    d.x += 0.0000001f;
+  if (d.y == 0.f)
+    d.y += 0.0000001f;
+  if (d.z == 0.f)
+    d.z += 0.0000001f;
+  float m = sqrtf(vdot(d, d));
+  return V(d.x / m, d.y / m, d.z / m);
+}
+void orc_direct_shade(const float* n3, const float* p3, const float* camPos3, const float* lookAt3, const float* upN3,
+                      float* normals4, float* albedo4)
+{
+  const v3 n = ld3(n3), p = ld3(p3), cam = ld3(camPos3);
+  const v3 lightPosition = vadd(cam, V(2.f * upN3[0], 2.f * upN3[1], 2.f * upN3[2]));
+  const v3 L = vnormalize(vsub(lightPosition, p));
+  const v3 Vd = vnormalize(vsub(cam, ld3(lookAt3)));
+  float cosTheta = vdot(n, L);
+  cosTheta = fminf(fmaxf(cosTheta, 0.f), 1.f);
+  const float s = 2.f * vdot(L, n);
+  const v3 R = vnormalize(vsub(vscale(n, s), L));
+  const float cosPhi = vdot(R, Vd);
+  if (normals4)
+  {
+    normals4[0] = n.x, normals4[1] = n.y, normals4[2] = n.z, normals4[3] = 1.f;
+  }
+  if (albedo4)
+  {
+    albedo4[0] = (cosPhi * R.x) / (cosTheta * L.x);
+    albedo4[1] = (cosPhi * R.y) / (cosTheta * L.y);
+    albedo4[2] = (cosPhi * R.z) / (cosTheta * L.z);
+    albedo4[3] = 1.f;
+  }
+}
+int orc_direct(const orc_scene* sc, const orc_camera* cam, float* normals4, float* albedo4, float* depth,
+               int32_t* primId)
+{
+  if (cam->W <= 0 || cam->H <= 0)
+    return -1;
+  cam_basis cb = make_basis(cam);
+  orc_scene quadsOnly = *sc;
+  quadsOnly.nSph = 0;
+  v3 up = ld3(cam->up);
+  if (!(up.x == 0.f && up.y == 1.f && up.z == 0.f))
+    up = vnormalize(up); /* Camera::SetUp, Camera.cxx:803-811 */
+  const float upN[3] = { up.x, up.y, up.z };
+  const int64_t N = (int64_t)cam->W * cam->H;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < N; i++)
+  {
+    v3 d = raygen_corner(&cb, i);
+    float rec[9];
+    int hid[2];
+    rec[HR_T] = FLT_MAX;
+    int64_t prim = closest_hit(&quadsOnly, cb.pos, d, 0.f, FLT_MAX, 0, rec, hid);
+    if (primId)
+      primId[i] = (int32_t)prim;
+    if (depth)
+      depth[i] = prim >= 0 ? rec[HR_T] : 0.f;
+    if (normals4)
+      normals4[4 * i] = normals4[4 * i + 1] = normals4[4 * i + 2] = normals4[4 * i + 3] = 0.f;
+    if (albedo4)
+      albedo4[4 * i] = albedo4[4 * i + 1] = albedo4[4 * i + 2] = albedo4[4 * i + 3] = 0.f;
+    if (prim >= 0)
+      orc_direct_shade(rec + HR_NX, rec + HR_PX, cam->pos, cam->lookAt, upN, normals4 ? normals4 + 4 * i : NULL,
+                       albedo4 ? albedo4 + 4 * i : NULL);
+  }
+  return 0;
+}
+void orc_raygen_corner(const orc_camera* cam, int64_t idx, float* dir3)
+{
+  cam_basis b = make_basis(cam);
+  st3(dir3, raygen_corner(&b, idx));
+}
+
 static void merge_stats(orc_stats* dst, const LStats* s)
 {
   dst->segments += s->segments;

@@ -131,6 +131,16 @@ int64_t orc_closest_hit(const orc_scene* sc, const float* o3, const float* d3, f
 int orc_primary_hits(const orc_scene* sc, const orc_camera* cam, uint32_t seedOffset, int flags, int32_t* primId,
                      float* t);
 
+/* -direct G-buffers (main.cc:402-422; raytracing/RayTracerNormals.cxx:47-143, RayTracerAlbedo.cxx:100-143): one
+ * un-jittered ray per pixel (Camera::PerspectiveRayGen), closest QUAD hit, the two Shade rules; see b2pt_oracle.c.
+ * normals4 / albedo4: W*H*4 floats, depth: W*H hit distances (0 = nothing hit), primId: W*H; any may be NULL. */
+int orc_direct(const orc_scene* sc, const orc_camera* cam, float* normals4, float* albedo4, float* depth,
+               int32_t* primId);
+/* the per-pixel colour rules alone (for pinning against the reference's Shade worklets) and the pixel ray */
+void orc_direct_shade(const float* n3, const float* p3, const float* camPos3, const float* lookAt3, const float* upN3,
+                      float* normals4, float* albedo4);
+void orc_raygen_corner(const orc_camera* cam, int64_t idx, float* dir3);
+
 /* Render spp samples [sampleBegin, sampleBegin+spp) at maxDepth; rgba = un-normalised sum over samples
  * (MapperPathTracer.cxx:350), W*H*4 floats, alpha lane 0. In modes 0-2 sampleBegin must be 0. */
 int orc_render(const orc_scene* sc, const orc_camera* cam, int spp, int sampleBegin, int maxDepth, uint32_t seedOffset,

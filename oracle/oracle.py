@@ -233,6 +233,34 @@ def render(scene, cam, spp, max_depth, mode=MODE_FORWARD_FAST, sample_begin=0, s
     return rgba, st
 
 
+def direct(scene, cam):
+    """-direct G-buffers (orc_direct): (normals[N,4], albedo[N,4], depth[N], prim[N])."""
+    n = cam.W * cam.H
+    normals, albedo = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32)
+    depth, prim = np.zeros(n, np.float32), np.zeros(n, np.int32)
+    ss, cs = scene.c_struct(), cam.c_struct()
+    L = lib()
+    L.orc_direct.restype = C.c_int
+    rc = L.orc_direct(C.byref(ss), C.byref(cs), _p(normals), _p(albedo), _p(depth), _p(prim))
+    assert rc == 0
+    return normals, albedo, depth, prim
+
+
+def direct_shade(n, p, cam_pos, look_at, up_n):
+    """The two Shade rules for one hit (orc_direct_shade): (normals4, albedo4)."""
+    a = [np.ascontiguousarray(x, np.float32) for x in (n, p, cam_pos, look_at, up_n)]
+    o0, o1 = np.zeros(4, np.float32), np.zeros(4, np.float32)
+    lib().orc_direct_shade(*[_p(x) for x in a], _p(o0), _p(o1))
+    return o0, o1
+
+
+def raygen_corner(cam, idx):
+    d = np.zeros(3, np.float32)
+    cs = cam.c_struct()
+    lib().orc_raygen_corner(C.byref(cs), C.c_int64(idx), _p(d))
+    return d
+
+
 def normalize(rgba_sum, spp):
     out = np.zeros_like(rgba_sum)
     lib().orc_normalize(_p(np.ascontiguousarray(rgba_sum)), rgba_sum.shape[0], spp, _p(out))

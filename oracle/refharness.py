@@ -24,7 +24,7 @@ def build(force=False):
     have_src = os.path.isdir(os.path.join(REF_ROOT, "pathtracing"))
     if have_src:
         O.build()
-        args = ["make", "-C", _HERE, "-s", "ref", "reftime", "REF_ROOT=" + REF_ROOT]
+        args = ["make", "-C", _HERE, "-s", "ref", "reftime", "refdirect", "REF_ROOT=" + REF_ROOT]
         if force:
             args.insert(1, "-B")
         subprocess.check_call(args)
@@ -134,6 +134,40 @@ def cornell_scene():
     npt, nq, ns = (int(v) for v in n)
     return dict(pts=pts[:npt], quadIds=quadIds[:nq], sphPt=sphPt[:ns], sphR=sphR[:ns], matIdxQ=matQ[:nq],
                 texIdxQ=texQ[:nq], matIdxS=matS[:ns], texIdxS=texS[:ns], matType=matType, texType=texType, tex=tex)
+
+
+_DIRECT_LIB_PATH = os.path.join(_HERE, "_ref", "libb2pt_refdirect.so")
+_dlib = None
+
+
+def direct_lib():
+    """The reference's Shade worklets (RayTracerNormals.cxx / RayTracerAlbedo.cxx) and Camera::PerspectiveRayGen,
+    lifted and compiled by oracle/ref_direct.cxx."""
+    global _dlib
+    if _dlib is None:
+        build()
+        L = C.CDLL(_DIRECT_LIB_PATH)
+        L.b2ref_direct_shade.restype = None
+        L.b2ref_direct_shade.argtypes = [C.c_int] + [C.c_void_p] * 6
+        L.b2ref_raygen_corner.restype = None
+        L.b2ref_raygen_corner.argtypes = [C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        _dlib = L
+    return _dlib
+
+
+def direct_shade(which, n, p, light_pos, cam_pos, look_at):
+    """Shade::operator() of RayTracerNormals (which=0) / RayTracerAlbedo (which=1) for one hit; returns rgba[4]."""
+    a = [np.ascontiguousarray(x, np.float32) for x in (n, p, light_pos, cam_pos, look_at)]
+    out = np.zeros(4, np.float32)
+    direct_lib().b2ref_direct_shade(which, *[_p(x) for x in a], _p(out))
+    return out
+
+
+def raygen_corner(W, H, fov, look, up, idx):
+    a = [np.ascontiguousarray(x, np.float32) for x in (look, up)]
+    d = np.zeros(3, np.float32)
+    direct_lib().b2ref_raygen_corner(W, H, fov, _p(a[0]), _p(a[1]), idx, _p(d))
+    return d
 
 
 def render_timed(scene, cam, spp, max_depth):

@@ -24,6 +24,8 @@ inline Float32 Abs(Float32 a) { return std::fabs(a); }
 inline Float64 Abs(Float64 a) { return std::fabs(a); }
 inline Float32 Sqrt(Float32 a) { return std::sqrt(a); }
 inline Float64 Sqrt(Float64 a) { return std::sqrt(a); }
+inline Float32 Pow(Float32 a, Float32 b) { return std::pow(a, b); }
+inline Float64 Pow(Float64 a, Float64 b) { return std::pow(a, b); }
 inline Float32 RSqrt(Float32 a) { return 1.0f / std::sqrt(a); }
 inline Float64 RSqrt(Float64 a) { return 1.0 / std::sqrt(a); }
 } // namespace vtkm

@@ -62,6 +62,8 @@ SIGNATURES = {
     "b2pt_set_scene": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32,
                               _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _f]),
     "b2pt_build_bvh": (_i32, [_vp]),
+    "b2pt_update_spheres": (_i32, [_vp, _vp, _vp]),
+    "b2pt_refit_bvh": (_i32, [_vp]),
     "b2pt_set_camera": (_i32, [_vp, _vp, _vp, _vp, _f, _i32, _i32]),
     "b2pt_seed": (_i32, [_vp, C.c_uint32]),
     "b2pt_set_memory_budget": (_i32, [_vp, _i64]),
@@ -83,6 +85,7 @@ SIGNATURES = {
     "b2pt_get_bounce_profile": (_i32, [_vp, _i32, _vp, _vp]),
     "b2pt_get_stage_profile": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "b2pt_primary_hits": (_i32, [_vp, _vp, _vp]),
+    "b2pt_render_direct": (_i32, [_vp] * 5),
     "b2pt_create_rays": (_i32, [_vp] * 9),
     "b2pt_intersect": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
     "b2pt_allreduce": (_i32, [C.POINTER(_vp), _i32]),
@@ -240,6 +243,14 @@ class Context:
     def build_bvh(self, flags=0):
         _check(lib().b2pt_build_bvh_ex(self._h, flags))
 
+    def update_spheres(self, centers, radii=None):
+        c = np.ascontiguousarray(centers, np.float32).reshape(-1, 3)
+        r = None if radii is None else np.ascontiguousarray(radii, np.float32).reshape(-1)
+        _check(lib().b2pt_update_spheres(self._h, _p(c), _p(r)))
+
+    def refit_bvh(self):
+        _check(lib().b2pt_refit_bvh(self._h))
+
     def set_camera(self, cam):
         _check(lib().b2pt_set_camera(self._h, _p(cam.pos), _p(cam.lookAt), _p(cam.up), cam.fov, cam.W, cam.H))
         self.W, self.H = cam.W, cam.H
@@ -329,6 +340,14 @@ class Context:
         prim, t = np.zeros(n, np.int32), np.zeros(n, np.float32)
         _check(lib().b2pt_primary_hits(self._h, _p(prim), _p(t)))
         return prim, t
+
+    def render_direct(self):
+        """-direct G-buffers (b2pt_render_direct): (normals[N,4], albedo[N,4], depth[N], prim[N])."""
+        n = self.W * self.H
+        normals, albedo = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32)
+        depth, prim = np.zeros(n, np.float32), np.zeros(n, np.int32)
+        _check(lib().b2pt_render_direct(self._h, _p(normals), _p(albedo), _p(depth), _p(prim)))
+        return normals, albedo, depth, prim
 
     def create_rays(self, seeds):
         n = self.W * self.H

@@ -141,6 +141,9 @@ struct b2pt_ctx
   B2BvhScene bvh{};
   DevBuf<B2BvhNode> dNodes;
   DevBuf<uint4> dWide; // 8-wide compressed nodes, 5 x uint4 each
+  DevBuf<int32_t> dParent; // b2pt_refit_bvh: parent of every binary node (-1 root, -2 not in the tree)
+  DevBuf<int> dArrived;
+  bool haveParents = false;
   DevBuf<int32_t> dSlots;
   DevBuf<float4> dLeafSph;
   DevBuf<B2Quad> dQuads;
@@ -152,6 +155,7 @@ struct b2pt_ctx
 
   // camera
   B2Camera cam{};
+  float camLookAt[3] = { 0.f, 0.f, 0.f }, camUpN[3] = { 0.f, 1.f, 0.f }; // look-at point, up as Camera::SetUp stores it
   uint32_t seedOffset = 0;
 
   // buffers
@@ -443,7 +447,7 @@ void b2pt_destroy(b2pt_ctx* ctx)
   for (cudaStream_t st : ctx->extra)
     if (st)
       cudaStreamSynchronize(st);
-  ctx->dNodes.release(), ctx->dWide.release(), ctx->dSlots.release(), ctx->dLeafSph.release(), ctx->dQuads.release(), ctx->dSph.release(), ctx->dGates.release();
+  ctx->dNodes.release(), ctx->dWide.release(), ctx->dParent.release(), ctx->dArrived.release(), ctx->dSlots.release(), ctx->dLeafSph.release(), ctx->dQuads.release(), ctx->dSph.release(), ctx->dGates.release();
   ctx->colorOwn.release();
   for (auto& b : ctx->bufs)
     b.release_all();
@@ -621,6 +625,7 @@ int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t*
 
 static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
 {
+  ctx->haveParents = false;
   ctx->builtFlags = flags & (B2PT_FLAG_FORCE_BVH | B2PT_FLAG_NO_DEDUP | B2PT_FLAG_NO_AA | B2PT_FLAG_GPU_LBVH | B2PT_FLAG_WIDE_BVH);
   // Drop bit-identical duplicate quads: a later copy computes the same t and loses the strict t<tmax
   // comparison (Surface.h:178-179), so removing it cannot change any result.
@@ -1103,6 +1108,92 @@ int b2pt_build_bvh_ex(b2pt_ctx* ctx, uint32_t flags)
 
 int b2pt_build_bvh(b2pt_ctx* ctx) { return b2pt_build_bvh_ex(ctx, 0); }
 
+int b2pt_update_spheres(b2pt_ctx* ctx, const float* centers, const float* radii)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (!ctx->haveScene)
+    return fail(B2PT_ERR_STATE, "b2pt_update_spheres before b2pt_set_scene");
+  if (!centers)
+    return fail(B2PT_ERR_BAD_VALUE, "null sphere centres");
+  CU(cudaStreamSynchronize(ctx->stream)); // renders in flight still read the old geometry
+  for (size_t s = 0; s < ctx->sph.size(); ++s)
+  {
+    for (int c = 0; c < 3; ++c)
+      ctx->sph[s].c[c] = centers[3 * s + c];
+    if (radii)
+      ctx->sph[s].r = radii[s];
+  }
+  ++ctx->sceneVersion;
+  if (!ctx->haveBvh)
+    return B2PT_OK; // the structures are built from the new geometry anyway
+  if (!ctx->useBvh)
+  { // kernel-parameter path: the sphere table and the spheres' leaf boxes are the whole "structure"
+    for (size_t s = 0; s < ctx->sph.size(); ++s)
+    {
+      const B2Sphere& sp = ctx->sph[s];
+      ctx->small.sph[s] = sp;
+      B2GateBox& G = ctx->small.sphGate[s];
+      for (int c = 0; c < 3; ++c)
+      {
+        G.bmin[c] = std::fmin(sp.c[c] + sp.r, sp.c[c] - sp.r);
+        G.bmax[c] = std::fmax(sp.c[c] + sp.r, sp.c[c] - sp.r);
+      }
+    }
+    return B2PT_OK;
+  }
+  if (!ctx->sph.empty())
+    CU(cudaMemcpyAsync(ctx->dSph.p, ctx->sph.data(), ctx->sph.size() * sizeof(B2Sphere), cudaMemcpyHostToDevice,
+                       ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2PT_OK;
+}
+
+int b2pt_refit_bvh(b2pt_ctx* ctx)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (!ctx->haveScene || !ctx->haveBvh)
+    return fail(B2PT_ERR_STATE, "b2pt_refit_bvh before b2pt_build_bvh");
+  if (!ctx->useBvh)
+    return B2PT_OK; // no tree on the kernel-parameter path (b2pt_update_spheres refreshed its tables)
+  if (ctx->bvh.wide)
+    return fail(B2PT_ERR_UNSUPPORTED, "b2pt_refit_bvh refits the binary tree; rebuild when B2PT_FLAG_WIDE_BVH is in use");
+  const int nNodes = ctx->bvhNodes;
+  if (nNodes <= 0)
+    return B2PT_OK;
+  if (!ctx->haveParents)
+  { // one-time: parent links of the tree as it sits on the device (either builder's layout)
+    std::vector<B2BvhNode> hn((size_t)nNodes);
+    CU(cudaMemcpy(hn.data(), ctx->dNodes.p, (size_t)nNodes * sizeof(B2BvhNode), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> parent((size_t)nNodes, -2);
+    std::vector<int32_t> st(1, 0);
+    parent[0] = -1;
+    while (!st.empty())
+    {
+      const int32_t i = st.back();
+      st.pop_back();
+      if (hn[(size_t)i].count > 0)
+        continue;
+      for (int k = 0; k < 2; ++k)
+      {
+        const int32_t c = hn[(size_t)i].left + k;
+        if (c <= 0 || c >= nNodes || parent[(size_t)c] != -2)
+          return fail(B2PT_ERR_STATE, "b2pt_refit_bvh: malformed tree");
+        parent[(size_t)c] = i;
+        st.push_back(c);
+      }
+    }
+    CU(ctx->dParent.reserve((size_t)nNodes));
+    CU(ctx->dArrived.reserve((size_t)nNodes));
+    CU(cudaMemcpy(ctx->dParent.p, parent.data(), (size_t)nNodes * sizeof(int32_t), cudaMemcpyHostToDevice));
+    ctx->haveParents = true;
+  }
+  CU(b2pt::refit_bvh_device(ctx->dNodes.p, ctx->dParent.p, ctx->dArrived.p, nNodes, ctx->dSlots.p, ctx->dQuads.p,
+                            ctx->dSph.p, ctx->dLeafSph.p, ctx->stream));
+  return B2PT_OK;
+}
+
 // Camera.cxx:913-914 Look; :803-811 SetUp; RayGen ctor :438-476 with fovX = fovY (:936-938), zoom off.
 // Validation messages are the reference's (Camera.cxx:645, 667, 720-724).
 static int make_camera(const float pos[3], const float lookAt[3], const float up[3], float fovDeg, int W, int H,
@@ -1150,6 +1241,12 @@ int b2pt_set_camera(b2pt_ctx* ctx, const float pos[3], const float lookAt[3], co
   const bool resized = (W != ctx->cam.W || H != ctx->cam.H);
   ctx->cam = c;
   ctx->haveCamera = true;
+  H3 upv = { up[0], up[1], up[2] };
+  if (!(upv.x == 0.f && upv.y == 1.f && upv.z == 0.f))
+    upv = hnormalize(upv); // Camera::SetUp (Camera.cxx:803-811)
+  hst(ctx->camUpN, upv);
+  for (int k = 0; k < 3; ++k)
+    ctx->camLookAt[k] = lookAt[k];
   if (resized && !ctx->colorExt)
     ctx->colorPixels = 0; // force re-allocation + clear
   return B2PT_OK;
@@ -1995,6 +2092,45 @@ int b2pt_read_pnm16(b2pt_ctx* ctx, int spp, uint16_t* rgb)
   CU(ctx->pnm.reserve((size_t)N * 3));
   CU(b2pt::launch_pnm16(ctx->color(), N, spp, ctx->pnm.p, ctx->stream));
   CU(cudaMemcpyAsync(rgb, ctx->pnm.p, sizeof(uint16_t) * 3 * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2PT_OK;
+}
+
+static int ensure_trace(b2pt_ctx* ctx);
+
+int b2pt_render_direct(b2pt_ctx* ctx, float* normals, float* albedo, float* depth, int32_t* primId)
+{
+  if (int rc = bind(ctx))
+    return rc;
+  if (!ctx->haveCamera)
+    return fail(B2PT_ERR_STATE, "b2pt_render_direct before b2pt_set_camera");
+  if (int rc = ensure_trace(ctx))
+    return rc;
+  if (ctx->useBvh)
+    return fail(B2PT_ERR_UNSUPPORTED, "b2pt_render_direct serves scenes on the kernel-parameter path (<= %d quads)",
+                B2PT_SMALL_MAX_QUADS);
+  const size_t N = (size_t)ctx->cam.W * ctx->cam.H;
+  DevBuf<float4> dN, dA;
+  DevBuf<float> dD;
+  DevBuf<int32_t> dP;
+  if (normals)
+    CU(dN.reserve(N));
+  if (albedo)
+    CU(dA.reserve(N));
+  if (depth)
+    CU(dD.reserve(N));
+  if (primId)
+    CU(dP.reserve(N));
+  CU(b2pt::launch_direct(ctx->cam, ctx->small, ctx->cam.pos, ctx->camLookAt, ctx->camUpN, dN.p, dA.p, dD.p, dP.p,
+                         ctx->stream));
+  if (normals)
+    CU(cudaMemcpyAsync(normals, dN.p, N * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  if (albedo)
+    CU(cudaMemcpyAsync(albedo, dA.p, N * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  if (depth)
+    CU(cudaMemcpyAsync(depth, dD.p, N * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  if (primId)
+    CU(cudaMemcpyAsync(primId, dP.p, N * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return B2PT_OK;
 }

@@ -129,6 +129,40 @@ __device__ __forceinline__ f3 raygen(const B2Camera& cam, int pixel, uint32_t& s
   return mk3(d.x / m, d.y / m, d.z / m);
 }
 
+// pathtracing/Camera.cxx:394-423 (Camera::PerspectiveRayGen, the generator of the -direct modes): the un-jittered ray
+// through the pixel's lower-left corner.
+__device__ __forceinline__ f3 raygen_corner(const B2Camera& cam, int pixel)
+{
+  const int i = pixel % cam.W, j = pixel / cam.W;
+  f3 d = (ld3(cam.nlook) + ld3(cam.dx) * ((2.f * (float)i - (float)cam.W) / 2.0f)) +
+    ld3(cam.dy) * ((2.f * (float)j - (float)cam.H) / 2.0f);
+  if (d.x == 0.f)
+    d.x += 0.0000001f;
+  if (d.y == 0.f)
+    d.y += 0.0000001f;
+  if (d.z == 0.f)
+    d.z += 0.0000001f;
+  const float m = sqrtf(dot3(d, d));
+  return mk3(d.x / m, d.y / m, d.z / m);
+}
+// The per-pixel colour rules of the -direct G-buffers: raytracing/RayTracerNormals.cxx:137-140 (the hit normal) and
+// RayTracerAlbedo.cxx:100-143 (cosPhi * R / (cosTheta * L) per channel, with the light at camera + 2 up, :154-155).
+// Same float operations in the same order as the reference's worklets (pinned through the oracle, tests/).
+__device__ __forceinline__ void direct_shade(f3 n, f3 p, f3 camPos, f3 lookAt, f3 upN, float4& normals, float4& albedo)
+{
+  const f3 lightPosition = camPos + mk3(2.f * upN.x, 2.f * upN.y, 2.f * upN.z);
+  const f3 L = unit3(lightPosition - p);
+  const f3 V = unit3(camPos - lookAt);
+  float cosTheta = dot3(n, L);
+  cosTheta = fminf(fmaxf(cosTheta, 0.f), 1.f);
+  const float s = 2.f * dot3(L, n);
+  const f3 R = unit3(n * s - L);
+  const float cosPhi = dot3(R, V);
+  normals = make_float4(n.x, n.y, n.z, 1.f);
+  albedo = make_float4((cosPhi * R.x) / (cosTheta * L.x), (cosPhi * R.y) / (cosTheta * L.y),
+                       (cosPhi * R.z) / (cosTheta * L.z), 1.f);
+}
+
 // --------------------------------------------------------------------------------------- primitives
 // Surface.h:30-104 (Lagae-Dutre ray/quad test up to t; the bilinear u,v of :106-158 are never consumed
 // downstream and are not computed).  Returns true iff the reference's hit() returns true; t is valid then.
@@ -500,7 +534,8 @@ __device__ __forceinline__ void filt_frame(const B2SmallScene& S, int f, int& pB
 // experiment builds only (scripts/build_variant.sh hist -DB2PT_DEBUG_HIST): per-ray counts of the two-phase filter
 __device__ unsigned long long g_debugHist[64];
 #endif
-__device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, float tmin, float tmax, float& tHit)
+__device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, float tmin, float tmax, float& tHit,
+                                             bool withSpheres = true)
 {
   float closest = tmax;
   int slot = -1;
@@ -554,7 +589,8 @@ __device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, 
   }
   // ---- remaining quads behind the slab test of their own leaf box (BVHTraverser.h:35-79, 143-157), then the
   // spheres behind theirs (sphere_gate)
-  if (S.firstBoxed < S.nQuads || S.nSph > 0)
+  const int nSph = withSpheres ? S.nSph : 0;
+  if (S.firstBoxed < S.nQuads || nSph > 0)
   {
     const f3 inv = mk3(rcp_safe(d.x), rcp_safe(d.y), rcp_safe(d.z));
     const f3 od = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
@@ -573,7 +609,7 @@ __device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, 
         bestPrim = Q.prim;
       }
     }
-    for (int s = 0; s < S.nSph; ++s)
+    for (int s = 0; s < nSph; ++s)
     {
       float tn, t;
       if (slab_hit(S.sphGate[s].bmin, S.sphGate[s].bmax, inv, od, tmin, tmax, tn) &&

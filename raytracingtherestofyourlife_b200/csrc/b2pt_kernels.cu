@@ -1421,6 +1421,45 @@ __global__ void __launch_bounds__(256)
     tOut[p] = h ? hit.t : FLT_MAX;
 }
 
+// -direct G-buffers (main.cc:402-422: runNorms / runAlbedo + the depth buffer): one un-jittered ray per pixel
+// (Camera::PerspectiveRayGen), closest QUAD hit (MapperQuad.cxx:103-113 extracts quads only) beyond t = 0, the two
+// Shade rules.  Misses leave (0,0,0,0) / depth 0.  The Phong colour image of the stock VTK-m shader is out of scope.
+struct DirectView
+{
+  float pos[3], lookAt[3], upN[3];
+};
+__global__ void __launch_bounds__(256)
+  k_direct(const __grid_constant__ B2Camera cam, const __grid_constant__ B2SmallScene scene,
+           const __grid_constant__ DirectView view, float4* normals, float4* albedo, float* depth, int32_t* primOut)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= cam.W * cam.H)
+    return;
+  const f3 o = ld3(cam.pos);
+  const f3 d = raygen_corner(cam, p);
+  float t;
+  const int code = closest_small(scene, o, d, 0.f, FLT_MAX, t, /*withSpheres*/ false);
+  float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f), alb = nrm;
+  float dep = 0.f;
+  int prim = -1;
+  if (code != B2PT_MISS)
+  {
+    Hit hit;
+    fill_small(scene, code, o, d, t, hit);
+    direct_shade(hit.n, hit.p, ld3(view.pos), ld3(view.lookAt), ld3(view.upN), nrm, alb);
+    dep = t;
+    prim = hit.prim;
+  }
+  if (normals)
+    normals[p] = nrm;
+  if (albedo)
+    albedo[p] = alb;
+  if (depth)
+    depth[p] = dep;
+  if (primOut)
+    primOut[p] = prim;
+}
+
 // pathtracing/Camera.cxx:894-953: fills + RayGen + origin broadcast, fused.
 __global__ void __launch_bounds__(256)
   k_create_rays(const __grid_constant__ B2Camera cam, uint32_t* seeds, float* dx, float* dy, float* dz, float* ox,
@@ -1741,6 +1780,18 @@ cudaError_t launch_primary_hits(const B2Camera& cam, const B2SmallScene* small, 
     k_primary_hits<B2BvhScene><<<(n + 255) / 256, 256, 0, stream>>>(cam, *bvh, seedOffset, primOut, tOut);
   else
     k_primary_hits<B2SmallScene><<<(n + 255) / 256, 256, 0, stream>>>(cam, *small, seedOffset, primOut, tOut);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_direct(const B2Camera& cam, const B2SmallScene& S, const float pos[3], const float lookAt[3],
+                          const float upN[3], float4* normals, float4* albedo, float* depth, int32_t* primOut,
+                          cudaStream_t stream)
+{
+  DirectView v;
+  for (int c = 0; c < 3; ++c)
+    v.pos[c] = pos[c], v.lookAt[c] = lookAt[c], v.upN[c] = upN[c];
+  const int n = cam.W * cam.H;
+  k_direct<<<(n + 255) / 256, 256, 0, stream>>>(cam, S, v, normals, albedo, depth, primOut);
   return cudaGetLastError();
 }
 

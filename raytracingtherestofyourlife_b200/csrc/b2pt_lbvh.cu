@@ -9,6 +9,7 @@
 // The host binned-SAH builder (b2pt_bvh.h) stays the default: its trees trace faster; this one builds ~two orders of
 // magnitude faster (B2PT_FLAG_GPU_LBVH).  Closest hits do not depend on the tree (tests compare with brute force).
 #include <algorithm>
+#include <cfloat>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -226,6 +227,50 @@ __global__ void __launch_bounds__(256)
   out[2 * i + 3] = child_record(nodes[i].right, nodes, nlo, nhi, plo, phi);
 }
 
+// ---- refit: the tree keeps its topology, the boxes follow the primitives' current geometry.  One thread per node; a
+// reachable leaf recomputes its box from its primitives (the builders' padded boxes, prim_box) and climbs: the second
+// thread to arrive at an inner node merges the boxes of its two (adjacent) children -- the bottom-up pass of the LBVH
+// build, on the final 32-byte node layout of either builder.
+__global__ void __launch_bounds__(256)
+  k_bvh_refit(B2BvhNode* nodes, const int32_t* parent, int* arrived, int nNodes, const int32_t* slots,
+              const B2Quad* quads, const B2Sphere* sph, float4* leafSph)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nNodes)
+    return;
+  if (parent[i] == -2) // not part of the tree (layout holes)
+    return;
+  B2BvhNode nd = nodes[i];
+  if (nd.count <= 0)
+    return; // inner nodes are filled by their second child to arrive
+  float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+  for (int k = 0; k < nd.count; ++k)
+  {
+    const int enc = slots[nd.left + k];
+    float a[3], b[3];
+    prim_box(quads, sph, enc, a, b);
+    for (int c = 0; c < 3; ++c)
+      lo[c] = fminf(lo[c], a[c]), hi[c] = fmaxf(hi[c], b[c]);
+    if (enc < 0)
+      leafSph[nd.left + k] = make_float4(sph[~enc].c[0], sph[~enc].c[1], sph[~enc].c[2], sph[~enc].r);
+  }
+  for (int c = 0; c < 3; ++c)
+    nodes[i].bmin[c] = lo[c], nodes[i].bmax[c] = hi[c];
+  int node = parent[i];
+  while (node >= 0)
+  {
+    __threadfence();
+    if (atomicAdd(&arrived[node], 1) == 0)
+      return; // the sibling subtree is not finished yet
+    const int l = nodes[node].left;
+    const float4* c4 = reinterpret_cast<const float4*>(nodes + l);
+    const float4 al = __ldcg(c4), ah = __ldcg(c4 + 1), bl = __ldcg(c4 + 2), bh = __ldcg(c4 + 3);
+    nodes[node].bmin[0] = fminf(al.x, bl.x), nodes[node].bmin[1] = fminf(al.y, bl.y), nodes[node].bmin[2] = fminf(al.z, bl.z);
+    nodes[node].bmax[0] = fmaxf(ah.x, bh.x), nodes[node].bmax[1] = fmaxf(ah.y, bh.y), nodes[node].bmax[2] = fmaxf(ah.z, bh.z);
+    node = parent[node];
+  }
+}
+
 template <class T>
 cudaError_t grow(T*& p, size_t& cap, size_t n)
 {
@@ -303,6 +348,20 @@ cudaError_t build_lbvh_device(const B2Quad* dQuads, const B2Sphere* dSph, const 
 #undef LB
   cleanup();
   return cudaSuccess;
+}
+
+cudaError_t refit_bvh_device(B2BvhNode* dNodes, const int32_t* dParent, int* dArrived, int nNodes,
+                             const int32_t* dSlots, const B2Quad* dQuads, const B2Sphere* dSph, float4* dLeafSph,
+                             cudaStream_t stream)
+{
+  if (nNodes <= 0)
+    return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(dArrived, 0, sizeof(int) * (size_t)nNodes, stream);
+  if (e != cudaSuccess)
+    return e;
+  k_bvh_refit<<<(nNodes + 255) / 256, 256, 0, stream>>>(dNodes, dParent, dArrived, nNodes, dSlots, dQuads, dSph,
+                                                        dLeafSph);
+  return cudaGetLastError();
 }
 
 } // namespace b2pt

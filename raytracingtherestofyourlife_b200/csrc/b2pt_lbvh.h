@@ -19,5 +19,12 @@ cudaError_t build_lbvh_device(const B2Quad* dQuads, const B2Sphere* dSph, const 
                               int nSph, const float sceneLo[3], const float sceneHi[3], B2BvhNode* dNodesOut,
                               int32_t* dSlotsOut, float4* dLeafSphOut, cudaStream_t stream);
 
+// Bottom-up refit of an existing tree (either builder's B2BvhNode layout) to the primitives' current geometry.
+// dParent[i]: parent node of node i, -1 for the root, -2 for entries that are not part of the tree; dArrived: nNodes
+// scratch counters.  Also rewrites the leaf-ordered sphere geometry.  Asynchronous on `stream`.
+cudaError_t refit_bvh_device(B2BvhNode* dNodes, const int32_t* dParent, int* dArrived, int nNodes,
+                             const int32_t* dSlots, const B2Quad* dQuads, const B2Sphere* dSph, float4* dLeafSph,
+                             cudaStream_t stream);
+
 } // namespace b2pt
 #endif

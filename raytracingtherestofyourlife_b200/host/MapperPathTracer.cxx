@@ -277,6 +277,38 @@ void MapperPathTracer::RenderCells(const vtkm::cont::DynamicCellSet& cellset, co
   RenderCellsImpl(cellset, coords, scalarField, camera);
 }
 
+void MapperPathTracer::RenderDirectBuffers(const vtkm::cont::DynamicCellSet& cellset,
+                                           const vtkm::cont::CoordinateSystem& coords,
+                                           const vtkm::rendering::Camera& camera,
+                                           vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Float32, 4>>& normals,
+                                           vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Float32, 4>>& albedo,
+                                           vtkm::cont::ArrayHandle<vtkm::Float32>& depth)
+{
+  if (Internals->Canvas == nullptr)
+    throw vtkm::cont::ErrorBadValue("MapperPathTracer: no canvas set");
+  auto* canvas = Internals->Canvas;
+  const vtkm::Id nx = canvas->GetWidth(), ny = canvas->GetHeight();
+  Internals->RayCamera.SetParameters(camera, *canvas);
+  auto tup = extract(cellset);
+  auto SphereIds = std::get<0>(tup);
+  auto SphereRadii = std::get<1>(tup);
+  auto QuadIds = std::get<3>(tup);
+  vtkm::cont::ArrayHandle<vtkm::Int32> matIdArray, texIdArray;
+  matIdArray.Allocate(nx * ny);
+  texIdArray.Allocate(nx * ny);
+  buildBVH(coords, QuadIds, SphereIds, SphereRadii, matIdArray, texIdArray, MatIdx, TexIdx);
+  b2pt_ctx* ctx = b2pt_facade::Context(Devices.empty() ? -1 : Devices[0]);
+  const auto pos = camera.GetPosition(), at = camera.GetLookAt(), up = camera.GetViewUp();
+  const float p[3] = { pos[0], pos[1], pos[2] }, a[3] = { at[0], at[1], at[2] }, u[3] = { up[0], up[1], up[2] };
+  b2pt_facade::Check(
+    b2pt_set_camera(ctx, p, a, u, camera.GetFieldOfView(), static_cast<int>(nx), static_cast<int>(ny)));
+  normals.Allocate(nx * ny);
+  albedo.Allocate(nx * ny);
+  depth.Allocate(nx * ny);
+  b2pt_facade::Check(b2pt_render_direct(ctx, reinterpret_cast<float*>(normals.GetStorage()),
+                                        reinterpret_cast<float*>(albedo.GetStorage()), depth.GetStorage(), nullptr));
+}
+
 void MapperPathTracer::RenderViewsImpl(const vtkm::cont::DynamicCellSet& cellset,
                                        const vtkm::cont::CoordinateSystem& coords,
                                        const std::vector<vtkm::rendering::Camera>& cameras, unsigned int flags,

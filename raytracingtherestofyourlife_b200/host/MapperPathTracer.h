@@ -109,6 +109,15 @@ public:
   // Packed on the GPU, 6 bytes per pixel cross PCIe instead of 16.
   void RenderCellsViewsPnm(const vtkm::cont::DynamicCellSet& cellset, const vtkm::cont::CoordinateSystem& coords,
                            const std::vector<vtkm::rendering::Camera>& cameras, std::vector<unsigned short>& pnm);
+  // The -direct G-buffers of main.cc:402-422 (what MapperQuadNormals / MapperQuadAlbedo leave in the canvas colour
+  // buffer, raytracing/RayTracerNormals.cxx / RayTracerAlbedo.cxx, and a depth image) for the canvas set with
+  // SetCanvas: one un-jittered ray per pixel, closest quad hit, the reference's two Shade rules (b2pt_render_direct).
+  // depth holds the hit distance along the ray (VTK-m's projected canvas depth is not restated).
+  void RenderDirectBuffers(const vtkm::cont::DynamicCellSet& cellset, const vtkm::cont::CoordinateSystem& coords,
+                           const vtkm::rendering::Camera& camera,
+                           vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Float32, 4>>& normals,
+                           vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Float32, 4>>& albedo,
+                           vtkm::cont::ArrayHandle<vtkm::Float32>& depth);
   double GetLastRenderMilliseconds() const { return LastRenderMs; }
   long long GetLastSegments() const { return LastSegments; }
 

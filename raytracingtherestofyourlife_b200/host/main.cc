@@ -32,6 +32,7 @@ struct Options
   std::string out = "output";
   bool stats = false;
   bool hemi = false;
+  bool direct = false;
   int phiCount = 15, thetaCount = 15; // main.cc:59-60
 };
 
@@ -63,7 +64,7 @@ Options parse(int argc, char** argv)
     else if (!std::strcmp(argv[i], "-thetacount"))
       next(o.thetaCount);
     else if (!std::strcmp(argv[i], "-direct"))
-      std::cerr << "note: -direct is outside the path-tracing hot path and is ignored\n";
+      o.direct = true;
   }
   return o;
 }
@@ -121,6 +122,43 @@ void savePnm(const std::string& stem, int nx, int ny, const vtkm::cont::ArrayHan
       col = 0.0f;
     fs << int(255.99 * col[0]) << " " << int(255.99 * col[1]) << " " << int(255.99 * col[2]) << std::endl;
   }
+}
+
+// save() for a scalar image (main.cc:343-359, the depth buffer): de_nan, sqrt, one value on three channels
+void savePnmScalar(const std::string& stem, int nx, int ny, const vtkm::cont::ArrayHandle<vtkm::Float32>& values)
+{
+  std::ofstream fs(stem + ".pnm");
+  if (!fs)
+  {
+    std::cout << "Couldn't save pnm." << std::endl;
+    return;
+  }
+  fs << "P3\n" << nx << " " << ny << " 255" << std::endl;
+  auto v = values.ReadPortal();
+  for (vtkm::Id i = 0; i < v.GetNumberOfValues(); ++i)
+  {
+    float col = v.Get(i);
+    if (col != col)
+      col = 0.f;
+    col = std::sqrt(col);
+    const int g = int(255.99 * col);
+    fs << g << " " << g << " " << g << std::endl;
+  }
+}
+
+// the G-buffer half of generate() with direct = true (main.cc:402-422): "normals", "albedo" and "depth" images of the
+// view.  The "direct" colour image needs VTK-m's stock Phong shader and colour table and is not produced.
+void runDirect(CornellBox& cb, const Options& o, vtkm::rendering::Canvas& canvas, vtkm::rendering::Camera& cam)
+{
+  vtkm::rendering::MapperPathTracer mapper(o.samples, o.depth, cb.matIdx, cb.texIdx, cb.matType, cb.texType, cb.tex);
+  mapper.SetCanvas(&canvas);
+  vtkm::cont::ArrayHandle<vtkm::Vec<vtkm::Float32, 4>> normals, albedo;
+  vtkm::cont::ArrayHandle<vtkm::Float32> depth;
+  mapper.RenderDirectBuffers(cb.ds.GetCellSet(), cb.coord, cam, normals, albedo, depth);
+  savePnm("normals", o.x, o.y, normals);
+  savePnm("albedo", o.x, o.y, albedo);
+  savePnmScalar("depth", o.x, o.y, depth);
+  std::cout << " wrote normals.pnm albedo.pnm depth.pnm (direct.pnm, the stock Phong image, is out of scope)" << std::endl;
 }
 
 // The same file from the integers packed on the GPU (RenderCellsViewsPnm): "r g b\n" per pixel, formatted into one
@@ -227,8 +265,13 @@ int main(int argc, char* argv[])
     cam.SetFieldOfView(40.);
     cam.SetViewUp(vec3(0, 1, 0));
     cam.SetLookAt(vec3(278 / 555.0, 278 / 555.0, 278 / 555.0));
-    runPath(*cb, o.samples, o.depth, canvas, cam, o.stats);
-    savePnm(o.out, o.x, o.y, canvas.GetColorBuffer());
+    if (o.direct)
+      runDirect(*cb, o, canvas, cam);
+    else
+    {
+      runPath(*cb, o.samples, o.depth, canvas, cam, o.stats);
+      savePnm(o.out, o.x, o.y, canvas.GetColorBuffer());
+    }
   }
   catch (const vtkm::cont::Error& e)
   {
