@@ -380,6 +380,7 @@ def main():
         # bounce 0 generates its rays in registers (no queue read), so the 88 B figure applies from bounce 1 on
         cand = range(1, len(prof)) if len(prof) > 1 else range(len(prof))
         top = max(cand, key=lambda k: prof[k][0] + prof[k][1]) if prof else None
+        top_rays = 0
         if top is not None and prof[top][0] + prof[top][1] > 0:
             tr_ms, sh_ms, top_rays = prof[top]
             achieved = top_rays * ALGO_BYTES_PER_SEGMENT / ((tr_ms + sh_ms) * 1e-3) / 1e9
@@ -397,8 +398,9 @@ def main():
             "scaling": "weak" if (world > 1 and args.weak) else "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_label(W, total_spp, args.depth, world),
-                       "parallelism": "samples sharded across %d GPU(s) (%d spp each), one NCCL all-reduce of %d B" % (
-                           world, count, N * 16),
+                       "parallelism": ("one GPU, no exchange" if world == 1 else
+                                       "samples sharded across %d GPUs (%d spp each), one NCCL all-reduce of %d B" % (
+                                           world, count, N * 16)),
                        "scaling_note": ("N=1 runs BASELINE.json configs[1] (1024 spp); N>1 runs ONE fixed job, the "
                                         "north_star target 1024^2 x 4096 spp, its samples partitioned over the ranks "
                                         "(strong scaling).  What limits it: every rank still pays the per-render fixed "
@@ -412,7 +414,8 @@ def main():
             "segments_per_s": segments_per_step * args.steps / (ms * 1e-3),
             "render_ms_library_events_last_step": st.renderMs,  # cross-check of ms_per_step (same stream, own events)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                         "traffic": ((traffic or {}).get("dram_bytes_per_input_ray") or 0) * top_rays or None,
+                         "traffic_source": (traffic or {}).get("kernel"), "peak_source": peak_src,
                          "kernel": top_desc, "algorithmic_bytes_per_segment": ALGO_BYTES_PER_SEGMENT,
                          "whole_step_achieved": step_gbs, "stage_profile_trace_ms_shade_ms_rays": prof[:8],
                          "note": "per GPU; FP32-issue bound in practice, see DESIGN.md and profiles/"},

@@ -132,6 +132,7 @@ struct b2pt_ctx
   int64_t nQuads = 0, nSph = 0;
   std::vector<B2Quad> quads; // by original index
   std::vector<B2Sphere> sph;
+  std::vector<int64_t> sphPointIds, lightSphPointIds; // point id of every sphere / light sphere (b2pt_update_spheres)
   std::vector<B2GateBox> gates; // leaf boxes of non-planar quads (B2Quad::gate indexes this, 1-based)
   std::vector<B2GateBox> boxes; // leaf box of every quad (AABBSurface.h), by original index
   B2Lights lights{};
@@ -602,6 +603,8 @@ int b2pt_set_scene(b2pt_ctx* ctx, const float* pts, int64_t nPts, const int64_t*
     hst(L.ls[l].c, P(lightSpherePt[l]));
     L.ls[l].r = lightSphereR[l];
   }
+  ctx->sphPointIds.assign(spherePt, spherePt + (nSpheres ? nSpheres : 0));
+  ctx->lightSphPointIds.assign(lightSpherePt, lightSpherePt + (nLightSpheres ? nLightSpheres : 0));
   ctx->quads.swap(quads);
   ctx->sph.swap(sph);
   ctx->gates.swap(gates);
@@ -1123,6 +1126,15 @@ int b2pt_update_spheres(b2pt_ctx* ctx, const float* centers, const float* radii)
       ctx->sph[s].c[c] = centers[3 * s + c];
     if (radii)
       ctx->sph[s].r = radii[s];
+    // a light sphere is a scene sphere referenced by point id (SphereGenerateDir.h / SpherePdf.h): it moves along
+    for (size_t l = 0; l < ctx->lightSphPointIds.size(); ++l)
+      if (ctx->lightSphPointIds[l] == ctx->sphPointIds[s])
+      {
+        for (int c = 0; c < 3; ++c)
+          ctx->lights.ls[l].c[c] = ctx->sph[s].c[c];
+        if (radii)
+          ctx->lights.ls[l].r = radii[s];
+      }
   }
   ++ctx->sceneVersion;
   if (!ctx->haveBvh)
