@@ -255,3 +255,19 @@ def test_normalize(oracle):
     x = np.array([[4.0, np.nan, 16.0, 0.0], [1.0, 9.0, 0.0, 0.0]], np.float32)
     out = oracle.normalize(x, 4)
     assert np.allclose(out[:, :3], [[1.0, 0.0, 2.0], [0.5, 1.5, 0.0]])
+
+
+def test_forward_burn_equals_passes_with_several_lights(oracle):
+    """Two light quads: the generators loop over every light for dead pixels too (PdfWorklet.h:122, :203), so the
+    forward form must burn 3 draws per light quad / 2 per light sphere per remaining depth to stay on the
+    reference-faithful stream."""
+    base = oracle.cornell_scene()
+    lq = np.array([[0, 8, 9, 10, 11], [3, 12, 13, 14, 15]], np.int64)
+    sc = oracle.Scene(base.pts, base.quadIds, base.sphPt, base.sphR, base.matIdxQ, base.texIdxQ, base.matIdxS,
+                      base.texIdxS, base.matType, base.texType, base.tex, lq, base.lightSphPt, base.lightSphR, 2, 1.5)
+    cam = oracle.Camera(48, 32)
+    a, sa = oracle.render(sc, cam, 5, 6, mode=oracle.MODE_PASSES)
+    b, sb = oracle.render(sc, cam, 5, 6, mode=oracle.MODE_FORWARD_BURN)
+    assert sa.segments == sb.segments and sa.rngDraws == sb.rngDraws
+    ok = ~np.isnan(a)
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(a[ok], b[ok], rtol=2e-5, atol=1e-6)
