@@ -83,7 +83,8 @@ def parse():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """Samples SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): through NVML
+    (nvidia_ml_py, ~1 ms per sample) when it loads, else through the nvidia-smi command line of the recipe."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -92,18 +93,42 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.rows = index, threading.Event(), []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(index))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        nv, h = self.nvml
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        bit = lambda name: "Active" if (r & getattr(nv, name, 0)) else "Not Active"
+        return [str(sm), str(mx), "0", bit("nvmlClocksThrottleReasonHwSlowdown"),
+                bit("nvmlClocksThrottleReasonHwThermalSlowdown"), bit("nvmlClocksThrottleReasonSwThermalSlowdown"),
+                bit("nvmlClocksThrottleReasonSwPowerCap")]
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                if self.nvml:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                         timeout=5).stdout
+                    parts = [p.strip() for p in out.strip().split(",")]
+                    if len(parts) >= 7:
+                        self.rows.append(parts)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05 if self.nvml else 0.2)
 
     def summary(self):
         sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
@@ -111,7 +136,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "via": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def measured_peak():
@@ -205,7 +230,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 RMSE_TOLERANCE = 0.02  # stated tolerance of the image check: relative RMSE over 8x8-pixel blocks of the 256^2 image
@@ -253,8 +278,29 @@ def image_check(img_sum, total_spp, size, depth):
             "masked": "NaN-poisoned pixels excluded on both sides"}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (the NCCL version banner, torchrun's notices) write to file
+    descriptor 1 as well, so everything but the result line is sent to stderr: fd 1 is pointed at fd 2 for the
+    lifetime of the process and the result is written to a saved duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -439,7 +485,7 @@ def main():
                                     "sample": "%dx%d, depth %d, 2 of %d spp in %.1f s on %d threads and 1 spp in %.1f s "
                                               "on one thread; built %s; %s" % (W, H, args.depth, args.spp, dt, cores,
                                                                                 dt1, build[0], desc)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.barrier()

@@ -258,11 +258,11 @@ def test_normalize(oracle):
 
 
 def test_forward_burn_equals_passes_with_several_lights(oracle):
-    """Two light quads: the generators loop over every light for dead pixels too (PdfWorklet.h:122, :203), so the
-    forward form must burn 3 draws per light quad / 2 per light sphere per remaining depth to stay on the
-    reference-faithful stream."""
+    """Two light quads (the light listed twice): the generators loop over every light for dead pixels too
+    (PdfWorklet.h:122, :203), so the forward form must burn 3 draws per light quad / 2 per light sphere per remaining
+    depth to stay on the reference-faithful stream."""
     base = oracle.cornell_scene()
-    lq = np.array([[0, 8, 9, 10, 11], [3, 12, 13, 14, 15]], np.int64)
+    lq = np.array([[0, 8, 9, 10, 11], [0, 8, 9, 10, 11]], np.int64)
     sc = oracle.Scene(base.pts, base.quadIds, base.sphPt, base.sphR, base.matIdxQ, base.texIdxQ, base.matIdxS,
                       base.texIdxS, base.matType, base.texType, base.tex, lq, base.lightSphPt, base.lightSphR, 2, 1.5)
     cam = oracle.Camera(48, 32)
