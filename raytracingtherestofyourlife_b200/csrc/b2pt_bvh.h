@@ -207,7 +207,10 @@ struct BvhBuilder
       }
     }
     const float parentArea = half_area(bmin, bmax);
-    const float leafCost = (float)n;                                                 // intersection cost 1 per primitive
+#ifndef B2PT_LEAF_COST
+#define B2PT_LEAF_COST 1.0f
+#endif
+    const float leafCost = B2PT_LEAF_COST * (float)n; // intersection cost per primitive, in traversal steps
     const float splitCost = bestAxis >= 0 ? 1.5f + bestCost / parentArea : FLT_MAX; // traversal step ~1.5
     if (n <= (size_t)kLeafTarget && (splitCost >= leafCost || bestAxis < 0))
       return make_leaf(wlo, whi, wnode);
