@@ -194,3 +194,29 @@ def test_render_replans_when_memory_was_taken_after_planning(b2pt):
             del hog
             torch.cuda.empty_cache()
     assert same_bits(got, want)
+
+
+def test_destroy_releases_every_device_buffer(b2pt):
+    """b2pt_destroy gives back everything a context allocated -- the view canvases, the camera array and the PNM staging
+    buffer included (they used to leak; all buffers are owning DevBufs now)."""
+    torch = pytest.importorskip("torch")
+    torch.cuda.init()
+    torch.cuda.synchronize()
+    views = hemisphere_views(2, 3)
+
+    def cycle():
+        with b2pt.Context(0) as ctx:
+            ctx.set_scene(b2pt.Scene.cornell())
+            ctx.build_bvh()
+            ctx.set_camera(b2pt.Camera(256, 256))
+            ctx.render(8, 6)
+            ctx.read_pnm16(8)
+            ctx.render_views(views, 256, 256, 4, 5, flags=b2pt.FLAG_VIEWS_PNM16)
+            ctx.render_views(views, 256, 256, 4, 5)
+
+    cycle()  # first use loads the module and creates the primary context's pools
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(3):
+        cycle()
+    free1, _ = torch.cuda.mem_get_info()
+    assert abs(free0 - free1) < (64 << 20), (free0, free1)
