@@ -55,6 +55,7 @@ typedef enum b2pt_status
 #define B2PT_FLAG_NO_PRIMARY_MASKS 0x400u    /* trace primary rays with the generic per-ray candidate filter instead of the per-tile candidate masks (A/B parity checks) */
 #define B2PT_FLAG_ONE_KERNEL_BOUNCE 0x800u   /* small scenes: ONE kernel per bounce (k_bounce: shade the hits of bounce d-1, trace bounce d, bin; no ray queue) instead of k_trace + k_shade; bit-identical images, half the HBM traffic, measured slower on B200 */
 #define B2PT_FLAG_WIDE_BVH 0x1000u           /* BVH scenes: traverse the 8-wide compressed tree (80-byte nodes, 8-bit quantised child boxes) collapsed from the binary tree instead of the binary tree itself; identical hits, fewer dependent fetches, more instructions -- measured slower on B200, hence opt-in */
+#define B2PT_FLAG_SPLIT_TRACE 0x4000u        /* BVH scenes, binary tree, sorted rays: a lean traversal kernel (k_bvh_hits) followed by k_resolve_hits instead of one k_trace per bounce; bit-identical, measured 0.4 % slower on configs[3] (A/B runs) */
 #define B2PT_FLAG_NO_RAY_SORT 0x2000u        /* BVH scenes: trace the ray queue in the order k_shade left it instead of sorted by origin cell and direction octant (A/B runs) */
 #define B2PT_FLAG_NO_AA 0x10u               /* do not use the axis-aligned quad specialisation (A/B parity checks) */
 

@@ -31,6 +31,7 @@ FLAG_NO_PRIMARY_MASKS = 0x400
 FLAG_ONE_KERNEL_BOUNCE = 0x800
 FLAG_WIDE_BVH = 0x1000
 FLAG_NO_RAY_SORT = 0x2000
+FLAG_SPLIT_TRACE = 0x4000
 
 ERR_BAD_VALUE, ERR_CUDA, ERR_STATE, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 

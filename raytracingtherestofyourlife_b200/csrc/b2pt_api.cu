@@ -176,6 +176,7 @@ struct b2pt_ctx
     DevBuf<float4> rad;
     DevBuf<uint32_t> sortKeys, sortPerm, sortHist; // BVH scenes: spatial sort of the ray queue (b2pt_kernels.cu)
     DevBuf<unsigned char> sortTemp;
+    DevBuf<uint2> hits; // split BVH bounce: closest hit per queue entry (k_bvh_hits -> k_resolve_hits)
     void release_all()
     {
       for (auto& q : queue)
@@ -188,6 +189,7 @@ struct b2pt_ctx
       regionCounts.release();
       rad.release();
       sortKeys.release(), sortPerm.release(), sortHist.release(), sortTemp.release();
+      hits.release();
     }
   } bufs[kMaxSets];
   cudaStream_t extra[kMaxSets] = {}; // own non-blocking streams of sets 1.. (set 0 runs on `stream`)
@@ -1347,7 +1349,7 @@ static int64_t tail_loop_rays()
 
 // Bytes of batch buffers per path in flight: one-kernel pipeline = two sets of four bins (52 B records) + radiance
 // 16 B; two-kernel pipeline = ray queue 48 B + one set of bins + radiance.
-static double bytes_per_path(bool fused) { return fused ? 2 * 4 * 52.0 + 16.0 : 48.0 + 4 * 52.0 + 16.0; }
+static double bytes_per_path(bool fused) { return fused ? 2 * 4 * 52.0 + 16.0 : 48.0 + 4 * 52.0 + 16.0 + 16.0; } // (+ sort keys, permutation, hits of BVH scenes)
 
 static int64_t batch_target_paths(b2pt_ctx* ctx, bool fused)
 {
@@ -1453,6 +1455,8 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
                                            ctx->cfg.shadeBlocksPerSM[0][ctx->useBvh ? 1 : 0]);
   // BVH scenes: the ray queue is sorted spatially before every region-mode bounce (B2PT_FLAG_NO_RAY_SORT: queue order)
   const bool raySort = ctx->useBvh && !(flags & B2PT_FLAG_NO_RAY_SORT) && !refStream;
+  // ... and, on request, traced by the lean traversal kernel (k_bvh_hits) with the bookkeeping in a second one
+  const bool splitTrace = raySort && !ctx->bvh.wide && (flags & B2PT_FLAG_SPLIT_TRACE);
   const int wpb = b2pt::warps_per_block();
   auto make_plan = [&](int64_t target, int64_t setsMax) {
     Plan P;
@@ -1509,6 +1513,8 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
             (e = bb.sortPerm.reserve((size_t)P.queueCap)) == cudaSuccess &&
             (e = bb.sortHist.reserve((size_t)b2pt::sort_buckets())) == cudaSuccess)
           e = bb.sortTemp.reserve(b2pt::sort_temp_bytes());
+        if (e == cudaSuccess && splitTrace)
+          e = bb.hits.reserve((size_t)P.queueCap);
       }
       if (e != cudaSuccess)
         return e;
@@ -1701,12 +1707,14 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
         break;
       }
       A.perm = nullptr;
+      A.hits = nullptr;
       if (raySort && depth >= 1 && mode != b2pt::B2PT_BOUNCE_TAIL)
       { // queue regions of k_shade(depth - 1) -> permutation by origin cell and direction octant
         CU(b2pt::launch_sort_rays(A, ctx->sortLo, ctx->sortHi, bb.sortHist.p, bb.sortKeys.p, bb.sortPerm.p,
                                   bb.sortTemp.p, bb.sortTemp.cap, bs));
         A.perm = bb.sortPerm.p;
-        launches += 3;
+        A.hits = splitTrace ? bb.hits.p : nullptr;
+        launches += splitTrace ? 4 : 3;
       }
       CU(b2pt::launch_bounce(ctx->cfg, depth == 0, mode, ctx->cam, ctx->useBvh ? nullptr : &ctx->small,
                              ctx->useBvh ? &ctx->bvh : nullptr, ctx->lights, A, bs, mid));

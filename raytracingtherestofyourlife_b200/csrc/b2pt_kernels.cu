@@ -520,6 +520,271 @@ __device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhS
   }
 }
 
+// ---- BVH scenes, binary tree, sorted rays: the traversal on its own.  In trace_body_bvh a lane that finishes a ray
+// resolves it (gated quads, emitter / miss bookkeeping, strategy draw, a 52-byte bin record behind four ballots) while
+// the other lanes of the warp wait: with ~41 inner steps per ray and a few lanes finishing per round that part ran at
+// a quarter of the warp and, with the ray's throughput / path id / RNG state alive through the loop, pinned the kernel
+// at 64 registers.  k_bvh_hits keeps only what the descent needs (reciprocal direction, o/d products, closest, stack):
+// a finished lane stores 8 bytes (t, primitive) at its queue index and takes the next ray of the warp's chunk of the
+// sorted order at once; origin and direction are read again from the queue when a leaf needs the exact tests.
+// k_resolve_hits then does the per-ray bookkeeping in queue order with full warps and coalesced accesses.  Node visits,
+// their order and the leaf tests are those of closest_bvh, so every hit is bit-identical (tests/test_gpu_spheres.py).
+// Measured on configs[3]: 795 ms against 792 ms for the single kernel (4 or 5 CTAs per SM alike; refilling at 32 / 28 /
+// 20 busy lanes 857 / 831 / 807 ms; reading the ray again at every leaf instead of keeping it 992 ms): a warp's step
+// waits for the slowest of its 32 node fetches (27 % of them leave L1), and neither more warps nor cheaper
+// bookkeeping shortens that chain.  Opt-in (B2PT_FLAG_SPLIT_TRACE); profiles/r02_experiments.md.
+#ifndef B2PT_LEAN_BLOCKS
+#define B2PT_LEAN_BLOCKS 5
+#endif
+#ifndef B2PT_LEAN_REFILL
+#define B2PT_LEAN_REFILL 20 // refill as soon as fewer lanes than this are traversing
+#endif
+#ifndef B2PT_LEAN_INNER_STEPS
+#define B2PT_LEAN_INNER_STEPS 8
+#endif
+// Staged rays of one warp: the next 32 rays of its chunk, fetched by all 32 lanes at once (one coalesced read of the
+// permutation, one gathered read of the rays) so that a lane that needs a new ray takes it from shared memory instead
+// of waiting, alone, for three dependent global loads while the rest of the warp idles.
+struct LeanStage
+{
+  uint32_t r[32];
+  float o[3][32], d[3][32];
+};
+__global__ void __launch_bounds__(kBlock, B2PT_LEAN_BLOCKS)
+  k_bvh_hits(const __grid_constant__ B2BvhScene S, const __grid_constant__ B2RenderArgs A)
+{
+  __shared__ LeanStage sStage[kWarps];
+  const uint32_t w = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  LeanStage& st = sStage[threadIdx.x >> 5];
+  const unsigned lt = (1u << lane) - 1u;
+  const uint32_t total = A.depthTotals[A.depth - 1];
+  const uint32_t nW = gridDim.x * kWarps;
+  const uint32_t chunk = (((total + nW - 1) / nW) + 31u) & ~31u;
+  if ((uint64_t)chunk * w >= total)
+    return; // warp-uniform
+  uint32_t next = chunk * w; // first ray of the chunk that is not staged yet
+  const uint32_t end = (uint32_t)min((uint64_t)total, (uint64_t)next + chunk);
+  uint32_t staged = 0, taken = 0; // rays in the stage / handed out
+  bool has = false, done = false;
+  f3 o = mk3(0.f, 0.f, 0.f), d = o, inv = o, od = o;
+  uint32_t r = 0, cur = 0;
+  float closest = FLT_MAX;
+  int best = B2PT_MISS, sp = 0;
+  uint32_t stack[64];
+  const float4* nodes4 = reinterpret_cast<const float4*>(S.nodes);
+  const uint32_t rootCur = S.nNodes > 0 ? bvh_pack(__ldg(nodes4).w, __ldg(nodes4 + 1).w) : 0u;
+  for (;;)
+  {
+    // ---- refill: lanes without a ray take staged rays in order; an empty stage is refilled by the whole warp
+    unsigned need = __ballot_sync(0xffffffffu, !has);
+    while (need)
+    {
+      if (taken == staged)
+      {
+        if (next >= end)
+          break;
+        __syncwarp();
+        const uint32_t k = next + lane;
+        if (k < end)
+        {
+          const uint32_t q = __ldg(A.perm + k);
+          const uint4 a = __ldcg(A.q.p0 + q), b = __ldcg(A.q.p1 + q);
+          st.r[lane] = q;
+          st.o[0][lane] = __uint_as_float(a.x), st.o[1][lane] = __uint_as_float(a.y), st.o[2][lane] = __uint_as_float(a.z);
+          st.d[0][lane] = __uint_as_float(a.w), st.d[1][lane] = __uint_as_float(b.x), st.d[2][lane] = __uint_as_float(b.y);
+        }
+        staged = min(32u, end - next);
+        taken = 0;
+        next += staged;
+        __syncwarp();
+      }
+      const uint32_t slot = taken + __popc(need & lt);
+      const bool take = !has && slot < staged;
+      if (take)
+      {
+        r = st.r[slot];
+        o = mk3(st.o[0][slot], st.o[1][slot], st.o[2][slot]);
+        d = mk3(st.d[0][slot], st.d[1][slot], st.d[2][slot]);
+        inv = mk3(rcp_safe(d.x), rcp_safe(d.y), rcp_safe(d.z));
+        od = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+        closest = FLT_MAX;
+        best = B2PT_MISS;
+        sp = 0;
+        done = S.nNodes <= 0;
+        cur = rootCur;
+        has = true;
+      }
+      taken = min(staged, taken + (uint32_t)__popc(need));
+      need = __ballot_sync(0xffffffffu, !has);
+    }
+    if (!__any_sync(0xffffffffu, has))
+      break;
+    const bool more = taken < staged || next < end;
+    for (;;)
+    {
+#pragma unroll 1
+      for (int it = 0; it < B2PT_LEAN_INNER_STEPS; ++it)
+      {
+        const bool inner = has && !done && !(cur >> 24);
+        if (!__any_sync(0xffffffffu, inner))
+          break;
+        if (!inner)
+          continue;
+        const float4* lp = nodes4 + 2 * (size_t)(cur & 0xffffffu);
+        const float4 l0 = __ldg(lp), l1 = __ldg(lp + 1), r0 = __ldg(lp + 2), r1 = __ldg(lp + 3);
+        float tl, tr;
+        const bool hl = slab_hit_fma(l0, l1, inv, od, 0.001f, closest, tl);
+        const bool hr = slab_hit_fma(r0, r1, inv, od, 0.001f, closest, tr);
+        const uint32_t cl = bvh_pack(l0.w, l1.w), crr = bvh_pack(r0.w, r1.w);
+        if (hl && hr)
+        {
+          const bool rightCloser = tl > tr;
+          cur = rightCloser ? crr : cl;
+          if (sp < 64)
+            stack[sp++] = rightCloser ? cl : crr;
+        }
+        else if (hl)
+          cur = cl;
+        else if (hr)
+          cur = crr;
+        else if (sp == 0)
+          done = true;
+        else
+          cur = stack[--sp];
+      }
+      if (has && !done && (cur >> 24))
+      { // leaf: primitives in ascending original index
+        const uint32_t count = cur >> 24, left = cur & 0xffffffu;
+        for (uint32_t k0 = 0; k0 < count; ++k0)
+        {
+          const int enc = __ldg(S.primSlots + left + k0);
+          const float4 geo = __ldg(S.leafSph + left + k0);
+          float t;
+          if (enc >= 0)
+          {
+            if (quad_accept(S.quads[enc], o, d, 0.001f, closest, t))
+            {
+              closest = t;
+              best = enc;
+            }
+          }
+          else if (sphere_may_hit(mk3(geo.x, geo.y, geo.z), geo.w, o, d) &&
+                   sphere_gate(mk3(geo.x, geo.y, geo.z), geo.w, inv, od, 0.001f, FLT_MAX) &&
+                   sphere_accept(mk3(geo.x, geo.y, geo.z), geo.w, o, d, 0.001f, closest, t))
+          {
+            closest = t;
+            best = enc;
+          }
+        }
+        if (sp == 0)
+          done = true;
+        else
+          cur = stack[--sp];
+      }
+      if (has && done)
+      { // hand the hit over; the lane is free
+        A.hits[r] = make_uint2(__float_as_uint(closest), (uint32_t)best);
+        has = false;
+        done = false;
+      }
+      const unsigned act = __ballot_sync(0xffffffffu, has);
+      if (act == 0u || (more && __popc(act) < B2PT_LEAN_REFILL))
+        break;
+    }
+  }
+}
+
+// The bookkeeping half of a split BVH bounce: queue order, one ray per lane, hits read from A.hits.  Same rules as the
+// resolve part of trace_body_bvh (gated quads continue from the tree's closest hit; miss / emitter finish the path;
+// every other hit is binned by shading strategy).
+__global__ void __launch_bounds__(kBlock, kMinBlocksPerSM)
+  k_resolve_hits(const __grid_constant__ B2BvhScene S, const __grid_constant__ B2RenderArgs A)
+{
+  const int w = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= A.numWarps)
+    return;
+  const int depth = A.depth;
+  const int64_t base = (int64_t)w * A.regionCap;
+  const int64_t nIn = (int64_t)A.qCount[w];
+  const bool refStream = (A.flags & B2PT_FLAG_REFERENCE_STREAM_DEV) != 0;
+  const unsigned lt = (1u << lane) - 1u;
+  uint32_t cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
+  for (int64_t i0 = 0; i0 < nIn; i0 += 32)
+  {
+    const int64_t i = i0 + lane;
+    int bin = -1;
+    f3 o, d, T;
+    uint32_t pid = 0, rng = 0;
+    float closest = 0.f;
+    int code = B2PT_MISS;
+    if (i < nIn)
+    {
+      const int64_t idx = base + i;
+      load_ray<false>(B2Camera{}, A, idx, o, d, T, pid, rng);
+      const uint2 h = __ldcg(A.hits + idx);
+      closest = __uint_as_float(h.x);
+      code = (int)h.y;
+      if (S.nGate > 0)
+      {
+        const f3 inv = mk3(rcp_safe(d.x), rcp_safe(d.y), rcp_safe(d.z));
+        const f3 od = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+        for (int g = 0; g < S.nGate; ++g)
+        {
+          float tn, t;
+          if (!slab_hit(S.gate[g].bmin, S.gate[g].bmax, inv, od, 0.001f, closest, tn))
+            continue;
+          const int q = S.gate[g].quad;
+          if (quad_accept(S.quads[q], o, d, 0.001f, closest, t))
+          {
+            closest = t;
+            code = q;
+          }
+        }
+      }
+      if (code == B2PT_MISS)
+        finish_path(A, pid, T * 0.f, rng, refStream, A.maxDepth - depth);
+      else
+      {
+        const int kind = hit_kind(S, code);
+        if (kind == 1)
+        {
+          Hit hit;
+          fill_hit(S, code, o, d, closest, hit);
+          const f3 em = (dot3(hit.n, d) < 0.0f) ? hit.alb : mk3(0.f, 0.f, 0.f);
+          finish_path(A, pid, mul3(T, em), rng, refStream, A.maxDepth - depth);
+        }
+        else
+        {
+          uint32_t peek = rng;
+          bin = (kind == 2) ? 0 : draw_which(peek);
+        }
+      }
+    }
+    const unsigned b0 = __ballot_sync(0xffffffffu, bin == 0), b1 = __ballot_sync(0xffffffffu, bin == 1);
+    const unsigned b2 = __ballot_sync(0xffffffffu, bin == 2), b3 = __ballot_sync(0xffffffffu, bin == 3);
+    if (bin >= 0)
+    {
+      const unsigned mine = bin == 0 ? b0 : (bin == 1 ? b1 : (bin == 2 ? b2 : b3));
+      const uint32_t cnt = bin == 0 ? cnt0 : (bin == 1 ? cnt1 : (bin == 2 ? cnt2 : cnt3));
+      const int64_t j = (int64_t)bin * A.binStride + base + cnt + __popc(mine & lt);
+      A.bins[0].p0[j] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
+      A.bins[0].p1[j] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
+      A.bins[0].p2[j] = make_uint4(__float_as_uint(T.z), pid, rng, __float_as_uint(closest));
+      A.bins[0].code[j] = (uint32_t)code;
+    }
+    cnt0 += __popc(b0), cnt1 += __popc(b1), cnt2 += __popc(b2), cnt3 += __popc(b3);
+  }
+  if (lane == 0)
+  {
+    A.bins[0].count[0 * A.numWarps + w] = cnt0;
+    A.bins[0].count[1 * A.numWarps + w] = cnt1;
+    A.bins[0].count[2 * A.numWarps + w] = cnt2;
+    A.bins[0].count[3 * A.numWarps + w] = cnt3;
+  }
+}
+
 // ---- BVH scenes, 8-wide compressed tree (B2WideScene; b2pt_wide.h, b2pt_device.cuh "8-wide compressed BVH").
 // The same persistent-lane scheme: a lane that finishes its ray takes the next ray of the warp's own region.  Every
 // iteration a lane with a node group visits ONE child node (eight quantised boxes in one 80-byte fetch: identical
@@ -1615,7 +1880,8 @@ cudaError_t query_launch_cfg(LaunchCfg* cfg)
       (e = occ((const void*)k_trace<false, B2WideScene, false>, cfg->traceBlocksPerSM[0][2])) != cudaSuccess ||
       (e = occ((const void*)k_shade<B2SmallScene, false, false>, cfg->shadeBlocksPerSM[0][0])) != cudaSuccess ||
       (e = occ((const void*)k_shade<B2BvhScene, false, false>, cfg->shadeBlocksPerSM[0][1])) != cudaSuccess ||
-      (e = occ((const void*)k_bounce<B2SmallScene, false, false>, cfg->bounceBlocksPerSM)) != cudaSuccess)
+      (e = occ((const void*)k_bounce<B2SmallScene, false, false>, cfg->bounceBlocksPerSM)) != cudaSuccess ||
+      (e = occ((const void*)k_bvh_hits, cfg->leanBlocksPerSM)) != cudaSuccess)
     return e;
   return cudaSuccess;
 }
@@ -1638,6 +1904,12 @@ static cudaError_t launch_bounce_t(const LaunchCfg& cfg, bool primary, int mode,
   }
   else if (primary)
     k_trace<true, SceneT, false><<<grid, kBlock, 0, stream>>>(cam, S, args);
+  else if (std::is_same<SceneT, B2BvhScene>::value && args.perm && args.hits)
+  { // split bounce: lean traversal over the sorted order, then the bookkeeping in queue order
+    const B2BvhScene& BS = reinterpret_cast<const B2BvhScene&>(S);
+    k_bvh_hits<<<cfg.numSMs * cfg.leanBlocksPerSM, kBlock, 0, stream>>>(BS, args);
+    k_resolve_hits<<<grid, kBlock, 0, stream>>>(BS, args);
+  }
   else
     k_trace<false, SceneT, false><<<grid, kBlock, 0, stream>>>(cam, S, args);
   if (betweenStages)

@@ -14,7 +14,8 @@ struct LaunchCfg
   int numSMs;
   int traceBlocksPerSM[2][3]; // [primary][0 small scene, 1 binary BVH, 2 8-wide BVH]
   int shadeBlocksPerSM[2][2];
-  int bounceBlocksPerSM; // k_bounce (one-kernel pipeline of small scenes)
+  int bounceBlocksPerSM;
+  int leanBlocksPerSM; // k_bvh_hits // k_bounce (one-kernel pipeline of small scenes)
 };
 
 // Queries occupancy of the bounce kernels on the current device.

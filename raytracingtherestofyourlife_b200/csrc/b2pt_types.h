@@ -287,6 +287,9 @@ struct B2RenderArgs
   // k_sort_scatter: perm[j] = queue entry of the j-th ray by origin cell and direction octant); warp w traces the
   // chunk [w*chunk, (w+1)*chunk) of it, chunk = total / numWarps rounded up to whole tiles.  nullptr = queue order.
   const uint32_t* perm;
+  // BVH pipeline with a binary tree and sorted rays: the closest hit of queue entry r, written by k_bvh_hits
+  // (x = bits of t, y = primitive code or B2PT_MISS) and consumed by k_resolve_hits.  nullptr = k_trace does both.
+  uint2* hits;
   int64_t binStride;    // numWarps * regionCap
   int64_t nPaths;       // paths in this batch (N * samplesInBatch)
   int32_t numWarps;

@@ -14,7 +14,7 @@ with B.Context(0) as ctx:
                   B.FLAG_ONE_KERNEL_BOUNCE | B.FLAG_REFERENCE_STREAM, B.FLAG_FORCE_BVH, B.FLAG_FORCE_BVH | B.FLAG_WIDE_BVH):
         ctx.render(8, 12, flags)
         print("cornell flags", flags, "segments", ctx.stats().segments, flush=True)
-    ctx.primary_hits(); ctx.render_direct(); ctx.read_pnm16(8)
+    ctx.render(2, 6, 0); ctx.primary_hits(); ctx.render_direct(); ctx.read_pnm16(8)
     views = np.array([[0.5 + 2 * np.cos(t), 0.5, 0.5 + 2 * np.sin(t), 0.5, 0.5, 0.5, 0, 1, 0, 40.0] for t in (0.5, 2.0, 4.0)], np.float32)
     ctx.render_views(views, 32, 32, 4, 5)
     ctx.render_views(views, 32, 32, 4, 5, flags=B.FLAG_VIEWS_PNM16)

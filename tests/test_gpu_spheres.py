@@ -145,16 +145,19 @@ def test_gpu_lbvh_equals_host_sah_on_the_million_sphere_scene(b2pt):
 
 @pytest.mark.parametrize("n,W,H,spp,depth", [(9, 64, 36, 8, 6), (300, 64, 36, 8, 6), (20000, 192, 108, 8, 12)])
 def test_wide_tree_and_ray_sort_change_nothing(b2pt, n, W, H, spp, depth, monkeypatch):
-    """The 8-wide compressed tree against the binary tree it was collapsed from, and the spatially sorted ray order
-    against queue order: different node visits, different warps -- the same closest hits, the same paths, the same
-    image, bit for bit (several batches in flight so that the tail modes take part)."""
+    """The 8-wide compressed tree against the binary tree it was collapsed from, the spatially sorted ray order
+    against queue order, and the split bounce (k_bvh_hits + k_resolve_hits) against the single k_trace: different node
+    visits, different warps, different kernels -- the same closest hits, the same paths, the same image, bit for bit
+    (several batches in flight so that the tail modes take part)."""
     s = b2pt.Scene.spheres(n)
     monkeypatch.setenv("B2PT_BATCH_PATHS", str(W * H * 2))
     monkeypatch.setenv("B2PT_VALIDATE_BVH", "1")
     ref = None
     F = b2pt.FLAG_FORCE_BVH
     for flags in (F, F | b2pt.FLAG_WIDE_BVH, F | b2pt.FLAG_NO_RAY_SORT, F | b2pt.FLAG_WIDE_BVH | b2pt.FLAG_NO_RAY_SORT,
-                  F | b2pt.FLAG_NO_TAIL, F | b2pt.FLAG_GPU_LBVH, F | b2pt.FLAG_GPU_LBVH | b2pt.FLAG_WIDE_BVH):
+                  F | b2pt.FLAG_SPLIT_TRACE, F | b2pt.FLAG_NO_TAIL, F | b2pt.FLAG_NO_TAIL | b2pt.FLAG_SPLIT_TRACE,
+                  F | b2pt.FLAG_GPU_LBVH, F | b2pt.FLAG_GPU_LBVH | b2pt.FLAG_WIDE_BVH,
+                  F | b2pt.FLAG_GPU_LBVH | b2pt.FLAG_SPLIT_TRACE):
         with b2pt.Context(0) as ctx:
             ctx.set_scene(s)
             ctx.build_bvh(flags)
