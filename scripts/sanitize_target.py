@@ -1,4 +1,5 @@
-"""Small target for `compute-sanitizer --tool memcheck`: every kernel family of the library once, at sizes that finish
+"""Small target that runs every kernel family of the library once (written for `compute-sanitizer --tool memcheck`, which
+this pool has closed; it still serves as a quick all-paths run), at sizes that finish
 in seconds under the sanitizer (Cornell 64x48 and a 300-sphere BVH scene).  Not a test of results (tests/ do that)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,7 +19,7 @@ with B.Context(0) as ctx:
     views = np.array([[0.5 + 2 * np.cos(t), 0.5, 0.5 + 2 * np.sin(t), 0.5, 0.5, 0.5, 0, 1, 0, 40.0] for t in (0.5, 2.0, 4.0)], np.float32)
     ctx.render_views(views, 32, 32, 4, 5)
     ctx.render_views(views, 32, 32, 4, 5, flags=B.FLAG_VIEWS_PNM16)
-for flags in (0, B.FLAG_WIDE_BVH, B.FLAG_GPU_LBVH, B.FLAG_NO_RAY_SORT, B.FLAG_GPU_LBVH | B.FLAG_WIDE_BVH):
+for flags in (0, B.FLAG_WIDE_BVH, B.FLAG_GPU_LBVH, B.FLAG_NO_RAY_SORT, B.FLAG_SPLIT_TRACE, B.FLAG_GPU_LBVH | B.FLAG_WIDE_BVH):
     with B.Context(0) as ctx:
         s = B.Scene.spheres(300)
         ctx.set_scene(s); ctx.build_bvh(flags); ctx.set_camera(cam)
