@@ -1034,6 +1034,16 @@ __device__ __forceinline__ void trace_body(const B2Camera& cam, const SceneT& S,
         const uint32_t view = A.views ? slotB / (uint32_t)A.sppPerView : 0u;
         const uint32_t tileInView = (uint32_t)((tileBase - (int64_t)slotB * A.nPixels) >> 5);
         const uint2 mask = __ldg(A.primMask + (size_t)view * A.tilesPerView + tileInView);
+#ifdef B2PT_DEBUG_HIST
+        if (lane == 0)
+        { // [40..]: tiles, filter candidates, gate/sphere bits, tiles with any gate bit
+          atomicAdd(&g_debugHist[40], 1ull);
+          atomicAdd(&g_debugHist[41], (unsigned long long)__popc(mask.x));
+          atomicAdd(&g_debugHist[42], (unsigned long long)__popc(mask.y));
+          atomicAdd(&g_debugHist[43], mask.y ? 1ull : 0ull);
+          atomicAdd(&g_debugHist[44 + min(__popc(mask.x), 3)], 1ull); // tiles with 0 / 1 / 2 / >= 3 candidates
+        }
+#endif
         code = closest_small_masked(S, A.primQuads + (size_t)view * B2PT_SMALL_MAX_QUADS, mask, o, d, 0.001f, FLT_MAX, t);
       }
       if (!masked)

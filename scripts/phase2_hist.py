@@ -20,4 +20,13 @@ for name, depth, flags in (("primary rays (generic filter)", 1, B.FLAG_NO_PRIMAR
                       "mean_candidates": sum(i * x for i, x in enumerate(h[0:16])) / max(n, 1),
                       "mean_exact_tests": sum(i * x for i, x in enumerate(h[16:32])) / max(n, 1),
                       "filtered_quads_hit_fraction": h[33] / max(h[32] + h[33], 1)}))
+L.b2pt_debug_hist(None, 1)
+ctx.set_camera(B.Camera(1024, 1024))
+ctx.render(4, 1, B.FLAG_NO_OVERLAP)
+ctx.synchronize()
+L.b2pt_debug_hist(buf, 0)
+h = list(buf)
+print(json.dumps({"what": "primary tiles at 1024x1024 (masked path)", "tiles": h[40], "filter_candidates_per_tile": h[41] / max(h[40], 1),
+                  "gate_bits_per_tile": h[42] / max(h[40], 1), "tiles_with_gate_bits": h[43] / max(h[40], 1),
+                  "tiles_with_0_1_2_3plus_candidates": [round(x / max(h[40], 1), 4) for x in h[44:48]]}))
 ctx.close()
