@@ -6,6 +6,11 @@
 // (generateHemisphere, main.cc:504-561): one path-traced image per view, named output-<phi>-<theta>.pnm as the
 // reference's generate() names them (main.cc:386-429).  Every view is an independent render through the same mapper;
 // scene tables and trace structures stay resident on the GPU between views.
+// -fibonacci [-viewcount N -viewseed R] is the reference's other sweep, fibonacciHemisphere (main.cc:430-503; its call
+// at main.cc:612 is commented out, N = 10000 there): the points of an N-point Fibonacci lattice on the unit sphere
+// around the box centre that lie on the camera's side (z < 0), rotated by R steps (the reference draws R = rand() % N
+// from an unseeded rand(); here it is an option, default 0); images are named output-0.0000-<i>.0000.pnm like
+// generate(cam, ..., 0, i) names them.
 // The -direct G-buffer modes (MapperQuad*, RayTracerNormals/Albedo) are outside the hot path.
 #include <chrono>
 #include <cmath>
@@ -33,7 +38,9 @@ struct Options
   bool stats = false;
   bool hemi = false;
   bool direct = false;
-  int phiCount = 15, thetaCount = 15; // main.cc:59-60
+  bool fibonacci = false;
+  int viewCount = 10000, viewSeed = 0; // main.cc:612 / :468
+  int phiCount = 15, thetaCount = 15;  // main.cc:59-60
 };
 
 Options parse(int argc, char** argv)
@@ -65,6 +72,12 @@ Options parse(int argc, char** argv)
       next(o.thetaCount);
     else if (!std::strcmp(argv[i], "-direct"))
       o.direct = true;
+    else if (!std::strcmp(argv[i], "-fibonacci"))
+      o.fibonacci = true;
+    else if (!std::strcmp(argv[i], "-viewcount"))
+      next(o.viewCount);
+    else if (!std::strcmp(argv[i], "-viewseed"))
+      next(o.viewSeed);
   }
   return o;
 }
@@ -191,42 +204,17 @@ void savePnm16(const std::string& stem, int nx, int ny, const unsigned short* rg
   fs.write(buf.data(), static_cast<std::streamsize>(buf.size()));
 }
 
-// the reference's generateHemisphere (main.cc:504-561) for the path-traced output: view points on a sphere of
-// radius 1078/555 around the box centre, phi in [0,1) in phiCount steps, theta in [0,2pi) in thetaCount steps
-int generateHemisphere(CornellBox& cb, const Options& o)
+// generate() for a list of view points (main.cc:386-429, path-traced branch): the reference renders and saves one
+// view per call; here ONE call renders them all (small canvases share GPU launches across views), NormalizeFunctor and
+// the integer conversion of save() (main.cc:253-287, 325-384) run on the GPU.
+int renderViews(CornellBox& cb, const Options& o, const std::vector<vtkm::rendering::Camera>& cameras,
+                const std::vector<std::string>& names)
 {
+  if (cameras.empty())
+    return 0;
   vtkm::rendering::CanvasRayTracer canvas(o.x, o.y);
-  vtkm::rendering::Camera cam;
-  cam.SetClippingRange(01.f, 5.f);
-  cam.SetPosition(vec3(278 / 555.0, 278 / 555.0, -800 / 555.0));
-  cam.SetFieldOfView(40.f);
-  cam.SetViewUp(vec3(0, 1, 0));
-  cam.SetLookAt(vec3(278 / 555.0, 278 / 555.0, 278 / 555.0));
-  const float phiBegin = 0.0f, phiEnd = 1.0f, thetaBegin = 0.f;
-  const float thetaEnd = static_cast<float>(2 * 3.14159265358979323846);
-  const float rTheta = thetaEnd / static_cast<float>(o.thetaCount);
-  const float rPhi = (phiEnd - phiBegin) / float(o.phiCount);
-  const float r = static_cast<float>(-1078 / 555.0);
-  // the reference renders and saves inside the loop (generate(), main.cc:386-429); here the loop only collects the
-  // view points and ONE call renders them all (small canvases share GPU launches across views)
-  std::vector<vtkm::rendering::Camera> cameras;
-  std::vector<std::string> names;
-  for (float phi = phiBegin; phi < (phiEnd - 0.5 * rPhi); phi += rPhi)
-    for (float theta = thetaBegin; theta < thetaEnd; theta += rTheta)
-    {
-      const auto x = r * std::cos(theta) * std::sin(phi);
-      const auto y = r * std::sin(theta) * std::sin(phi);
-      const auto z = r * std::cos(phi);
-      cam.SetPosition(vec3(x + 278 / 555.0, y + 278 / 555.0, z + 278 / 555.0));
-      std::stringstream name; // generate(): "output-" << fixed << setw(4) << setprecision(4) << phi << "-" << theta
-      name << o.out << "-" << std::fixed << std::setw(4) << std::setprecision(4) << phi << "-";
-      name << std::fixed << std::setw(4) << std::setprecision(4) << theta;
-      cameras.push_back(cam);
-      names.push_back(name.str());
-    }
   vtkm::rendering::MapperPathTracer mapper(o.samples, o.depth, cb.matIdx, cb.texIdx, cb.matType, cb.texType, cb.tex);
   mapper.SetCanvas(&canvas);
-  // NormalizeFunctor and the integer conversion of save() (main.cc:253-287, 325-384) run on the GPU
   std::vector<unsigned short> pnm;
   mapper.RenderCellsViewsPnm(cb.ds.GetCellSet(), cb.coord, cameras, pnm);
   if (o.stats)
@@ -239,6 +227,81 @@ int generateHemisphere(CornellBox& cb, const Options& o)
   return static_cast<int>(cameras.size());
 }
 
+vtkm::rendering::Camera sweepCamera()
+{ // main.cc:463-467 / :516-521
+  vtkm::rendering::Camera cam;
+  cam.SetClippingRange(01.f, 5.f);
+  cam.SetPosition(vec3(278 / 555.0, 278 / 555.0, -800 / 555.0));
+  cam.SetFieldOfView(40.f);
+  cam.SetViewUp(vec3(0, 1, 0));
+  cam.SetLookAt(vec3(278 / 555.0, 278 / 555.0, 278 / 555.0));
+  return cam;
+}
+
+std::string viewName(const std::string& stem, float phi, float theta)
+{ // generate(): "output-" << fixed << setw(4) << setprecision(4) << phi << "-" << theta
+  std::stringstream name;
+  name << stem << "-" << std::fixed << std::setw(4) << std::setprecision(4) << phi << "-";
+  name << std::fixed << std::setw(4) << std::setprecision(4) << theta;
+  return name.str();
+}
+
+// the reference's generateHemisphere (main.cc:504-561) for the path-traced output: view points on a sphere of
+// radius 1078/555 around the box centre, phi in [0,1) in phiCount steps, theta in [0,2pi) in thetaCount steps
+int generateHemisphere(CornellBox& cb, const Options& o)
+{
+  vtkm::rendering::Camera cam = sweepCamera();
+  const float phiBegin = 0.0f, phiEnd = 1.0f, thetaBegin = 0.f;
+  const float thetaEnd = static_cast<float>(2 * 3.14159265358979323846);
+  const float rTheta = thetaEnd / static_cast<float>(o.thetaCount);
+  const float rPhi = (phiEnd - phiBegin) / float(o.phiCount);
+  const float r = static_cast<float>(-1078 / 555.0);
+  std::vector<vtkm::rendering::Camera> cameras;
+  std::vector<std::string> names;
+  for (float phi = phiBegin; phi < (phiEnd - 0.5 * rPhi); phi += rPhi)
+    for (float theta = thetaBegin; theta < thetaEnd; theta += rTheta)
+    {
+      const auto x = r * std::cos(theta) * std::sin(phi);
+      const auto y = r * std::sin(theta) * std::sin(phi);
+      const auto z = r * std::cos(phi);
+      cam.SetPosition(vec3(x + 278 / 555.0, y + 278 / 555.0, z + 278 / 555.0));
+      cameras.push_back(cam);
+      names.push_back(viewName(o.out, phi, theta));
+    }
+  return renderViews(cb, o, cameras, names);
+}
+
+// the reference's fibonacciHemisphere (main.cc:430-503): lattice point i of N has height z = (i + 1/2) 2/N - 1 (float),
+// radius sqrt(1 - z^2) and azimuth ((i + rnd) mod N) * pi (3 - sqrt 5) (double); points with z < 0 become camera
+// positions on the unit sphere around the box centre
+int fibonacciHemisphere(CornellBox& cb, const Options& o)
+{
+  vtkm::rendering::Camera cam = sweepCamera();
+  const int n = o.viewCount;
+  if (n <= 0)
+    return 0;
+  const int rnd = ((o.viewSeed % n) + n) % n;
+  const float offset = static_cast<float>(2. / n);
+  const double increment = 3.14159265358979323846 * (3. - std::sqrt(5.0));
+  std::vector<vtkm::rendering::Camera> cameras;
+  std::vector<std::string> names;
+  for (int i = 0; i < n; ++i)
+  {
+    const float z = ((i * offset) - 1) + (offset / 2);
+    const float r = static_cast<float>(std::sqrt(1 - std::pow(z, 2)));
+    const double phi = ((i + rnd) % n) * increment;
+    const float x = static_cast<float>(std::cos(phi) * r);
+    const float y = static_cast<float>(std::sin(phi) * r);
+    if (z < 0)
+    {
+      cam.SetPosition(vec3(x + 278 / 555.0, y + 278 / 555.0, z + 278 / 555.0));
+      cameras.push_back(cam);
+      names.push_back(viewName(o.out, 0.f, static_cast<float>(i)));
+    }
+  }
+  return renderViews(cb, o, cameras, names);
+}
+
 } // namespace
 
 int main(int argc, char* argv[])
@@ -249,9 +312,9 @@ int main(int argc, char* argv[])
   {
     auto cb = std::make_unique<CornellBox>();
     cb->buildDataSet();
-    if (o.hemi)
+    if (o.hemi || o.fibonacci)
     {
-      const int views = generateHemisphere(*cb, o);
+      const int views = o.fibonacci ? fibonacciHemisphere(*cb, o) : generateHemisphere(*cb, o);
       std::cout << " views rendered       = " << views << std::endl;
       b2pt_facade::ReleaseContext();
       const double dth = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -125,3 +125,33 @@ def test_cli_hemisphere_sweep_matches_oracle_views(host_build, tmp_path, oracle)
         o, _ = oracle.render(oracle.cornell_scene(), oracle.Camera(48, 48, pos=pos), 6, 5, mode=oracle.MODE_FORWARD_FAST)
         want = (255.99 * oracle.normalize(o, 6)[:, :3].astype(np.float64)).astype(np.int64)
         assert (np.abs(got - want) <= 1).mean() > 0.999, (name, (np.abs(got - want) <= 1).mean())
+
+
+@pytest.mark.gpu
+def test_cli_fibonacci_sweep_matches_oracle_views(host_build, tmp_path, oracle):
+    """-fibonacci (fibonacciHemisphere, main.cc:430-503): the lattice points with z < 0 become camera positions on the
+    unit sphere around the box centre, images named output-0.0000-<i>.0000 like generate(cam, ..., 0, i); two views are
+    checked against the oracle rendered from the same camera position (float z and radius, double azimuth)."""
+    out = str(tmp_path / "fib")
+    n, rnd = 12, 5
+    r = subprocess.run([os.path.join(host_build, "CornellBox_b2pt"), "-x", "48", "-y", "48", "-samplecount", "6",
+                        "-raydepth", "5", "-fibonacci", "-viewcount", str(n), "-viewseed", str(rnd), "-o", out],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "views rendered       = 6" in r.stdout  # the lower half of the lattice
+    files = sorted(f for f in os.listdir(tmp_path) if f.startswith("fib-") and f.endswith(".pnm"))
+    assert files == sorted("fib-0.0000-%d.0000.pnm" % i for i in range(6))
+    offset = np.float32(2.0 / n)
+    inc = np.pi * (3.0 - np.sqrt(5.0))
+    c = 278 / 555.0
+    for i in (0, 4):
+        z = np.float32(np.float32(np.float32(i * offset) - np.float32(1)) + np.float32(offset / np.float32(2)))
+        rad = np.float32(np.sqrt(1 - float(z) ** 2))
+        phi = ((i + rnd) % n) * inc
+        x, y = np.float32(np.cos(phi) * float(rad)), np.float32(np.sin(phi) * float(rad))
+        pos = [np.float32(float(x) + c), np.float32(float(y) + c), np.float32(float(z) + c)]
+        tok = open(os.path.join(tmp_path, "fib-0.0000-%d.0000.pnm" % i)).read().split()
+        got = np.array(tok[4:], np.int64).reshape(-1, 3)
+        o, _ = oracle.render(oracle.cornell_scene(), oracle.Camera(48, 48, pos=pos), 6, 5, mode=oracle.MODE_FORWARD_FAST)
+        want = (255.99 * oracle.normalize(o, 6)[:, :3].astype(np.float64)).astype(np.int64)
+        assert (np.abs(got - want) <= 1).mean() > 0.999, (i, (np.abs(got - want) <= 1).mean())
