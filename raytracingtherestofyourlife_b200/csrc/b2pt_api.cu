@@ -661,6 +661,7 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
     int frame, axis;
     FiltRec fq;
     int32_t quad;
+    bool exact; // world frame and all four vertices share the float plane coordinate (B2Frame::eaCoef)
   };
   std::vector<FiltEntry> filt;
   std::vector<B2Frame> frames;
@@ -719,6 +720,7 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
       // plane-offset spread, doubled
       const double mu = 2e-5 * (hi[u] - lo[u]) + 2e-6 * scale, mv = 2e-5 * (hi[vv] - lo[vv]) + 2e-6 * scale;
       E.axis = n;
+      E.exact = F.identity != 0 && hi[n] == lo[n];
       E.fq = FiltRec{};
       E.fq.c = (float)(0.5 * (lo[n] + hi[n]));
       E.fq.uc = (float)(0.5 * (lo[u] + hi[u]));
@@ -840,7 +842,13 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
         fm = S.nFrames++;
         S.frames[fm] = frames[(size_t)filt[k].frame];
         for (int a = 0; a < 3; ++a)
-          S.frames[fm].axisEnd[a] = nPairs;
+          S.frames[fm].axisEnd[a] = nPairs, S.frames[fm].eaCoef[a] = 4e-6f;
+      }
+      {
+        bool exact = true;
+        for (size_t i = k; i < e; ++i)
+          exact = exact && filt[i].exact;
+        S.frames[fm].eaCoef[filt[k].axis] = exact ? 4e-7f : 4e-6f;
       }
       for (size_t i = k; i < e; i += 2)
       {

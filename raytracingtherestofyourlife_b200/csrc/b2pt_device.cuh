@@ -448,9 +448,14 @@ __device__ __forceinline__ f2x sub2(f2x a, f2x b)
 // t*(4e-6*D) + 4e-6*S/|dn|  of the true plane distance (>= 20x the forward error of either evaluation, incl. the
 // rotation into the frame), and the hit point within  S*(2e-5 + 2e-5*D)  of the true one plus the exact test's
 // own edge tolerance (static part folded into hu/hv on the host).  A quad the exact test could accept therefore
-// always passes.
+// always passes.  The absolute part 4e-6*S/|dn| is dominated by the rotation into a frame and by quads whose plane
+// offsets differ by up to 1e-6*S; for a world-frame group of exactly planar quads it is eaCoef = 4e-7 (B2Frame): with
+// E01_n = E03_n = 0 and v00_n = c the exact test's t = (T_n A)/(d_n A') carries only relative rounding (<= 10 u), and
+// t' = fma(c, r, -(on r)) with r = rcp.approx(dn) (1 ulp) differs from the true distance by at most 3 u |t| +
+// u |on| |r| <= 1.8e-7 |t| + 6e-8 S/|dn|.
 __device__ __forceinline__ void filt_axis(const B2SmallScene& S, int pBegin, int pEnd, float on, float dn, float ou,
-                                          float du, float ov, float dv, float dabs, float Sr, float tmin, FiltState& F)
+                                          float du, float ov, float dv, float dabs, float Sr, float eaCoef, float tmin,
+                                          FiltState& F)
 {
   if (pEnd <= pBegin)
     return;
@@ -461,7 +466,7 @@ __device__ __forceinline__ void filt_axis(const B2SmallScene& S, int pBegin, int
   const float D = dabs * fabsf(rdn);
   const float marg = Sr * __fmaf_rn(2e-5f, D, 2e-5f);
   const float er = 4e-6f * D;               // relative error bound of t' (and of the exact t)
-  const float ea = 4e-6f * Sr * fabsf(rdn); // absolute part
+  const float ea = eaCoef * Sr * fabsf(rdn); // absolute part (B2Frame::eaCoef: 4e-6, exactly planar world-frame groups 4e-7)
   // candidate iff  t' + |t'|*er + ea > tmin  (upper bound of the true distance beyond tmin); as a threshold on t':
   const float bt = tmin - ea;
   // (bt > 0: t' > bt/(1+er), bounded below by bt*(1-2er); bt <= 0: t' > bt/(1-er), bounded below by bt*(1+2er) while
@@ -518,9 +523,9 @@ __device__ __forceinline__ void filt_frame(const B2SmallScene& S, int f, int& pB
     Sf = 4.0f * Sr; // frame coordinates are relative to org: |.| <= 2*sqrt(3)*Sr
   }
   const float dabs = fabsf(dl.x) + fabsf(dl.y) + fabsf(dl.z);
-  filt_axis(S, pBegin, Fr.axisEnd[0], ol.x, dl.x, ol.y, dl.y, ol.z, dl.z, dabs, Sf, tmin, F);
-  filt_axis(S, max(pBegin, Fr.axisEnd[0]), Fr.axisEnd[1], ol.y, dl.y, ol.z, dl.z, ol.x, dl.x, dabs, Sf, tmin, F);
-  filt_axis(S, max(pBegin, Fr.axisEnd[1]), Fr.axisEnd[2], ol.z, dl.z, ol.x, dl.x, ol.y, dl.y, dabs, Sf, tmin, F);
+  filt_axis(S, pBegin, Fr.axisEnd[0], ol.x, dl.x, ol.y, dl.y, ol.z, dl.z, dabs, Sf, Fr.eaCoef[0], tmin, F);
+  filt_axis(S, max(pBegin, Fr.axisEnd[0]), Fr.axisEnd[1], ol.y, dl.y, ol.z, dl.z, ol.x, dl.x, dabs, Sf, Fr.eaCoef[1], tmin, F);
+  filt_axis(S, max(pBegin, Fr.axisEnd[1]), Fr.axisEnd[2], ol.z, dl.z, ol.x, dl.x, ol.y, dl.y, dabs, Sf, Fr.eaCoef[2], tmin, F);
   pBegin = max(pBegin, Fr.axisEnd[2]);
 }
 
@@ -532,7 +537,7 @@ __device__ __forceinline__ void filt_frame(const B2SmallScene& S, int f, int& pB
 #define B2PT_MISS 0x7fffffff
 #ifdef B2PT_DEBUG_HIST
 // experiment builds only (scripts/build_variant.sh hist -DB2PT_DEBUG_HIST): per-ray counts of the two-phase filter
-__device__ unsigned long long g_debugHist[64];
+__device__ unsigned long long g_debugHist[256];
 #endif
 __device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, float tmin, float tmax, float& tHit,
                                              bool withSpheres = true)
@@ -574,8 +579,20 @@ __device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, 
     while (rest)
     {
       rest &= ~(1u << (top - v));
+#ifdef B2PT_DEBUG_HIST
+      const int slotBefore = slot;
+      // [64+v]: first exact test on visit index v; [96+v]: ... that failed; [128+v]: later tests on v; [160+v]: ... that
+      // won; [192+v]: first test on v hit, but another candidate's lower bound kept the loop going
+      atomicAdd(&g_debugHist[(iters == 0 ? 64 : 128) + v], 1ull);
+#endif
       test_quad(S.visitSlot[v]);
 #ifdef B2PT_DEBUG_HIST
+      if (iters == 0 && slot < 0)
+        atomicAdd(&g_debugHist[96 + v], 1ull);
+      if (iters > 0 && slot != slotBefore)
+        atomicAdd(&g_debugHist[160 + v], 1ull);
+      if (iters == 0 && slot >= 0 && rest && !(F.t2 > closest))
+        atomicAdd(&g_debugHist[192 + v], 1ull);
       ++iters;
 #endif
       if (slot >= 0 && F.t2 > closest) // valid from the first iteration on: F.vb is tested first

@@ -2043,7 +2043,7 @@ extern "C" int b2pt_debug_hist(unsigned long long* out, int reset)
     return -1;
   if (reset)
   {
-    unsigned long long z[64] = {};
+    unsigned long long z[256] = {};
     if (cudaMemcpyToSymbol(g_debugHist, z, sizeof(z)) != cudaSuccess)
       return -1;
   }

@@ -143,12 +143,20 @@ struct alignas(16) B2FiltPair // 48 B: two 16-byte chunks + one 8-byte chunk
   float hv[2];
   float pad[2];
 };
-struct alignas(16) B2Frame // 64 B
+struct alignas(16) B2Frame // 80 B
 {
   float R[9];         // rows = frame axes in world coordinates (world -> frame rotation)
   float org[3];       // frame origin (subtracted before the rotation)
   int32_t axisEnd[3]; // end index in pairs[] of the quads normal to frame axis 0,1,2 (cumulative over frames)
   int32_t identity;   // 1: world axes, no transform
+  // absolute error bound of the filter's plane distance, per axis group, in units of (coordinate scale) / |d_n|:
+  // 4e-6 in general (rotation into the frame, plane offsets within 1e-6 of the scale); 4e-7 for a group of the world
+  // frame whose quads are exactly planar (all four vertices share the float coordinate): there the filter's
+  // t' = c rcp(d_n) - o_n rcp(d_n) is off by at most 6e-8 |o_n| / |d_n| and the exact test's t by a relative 6e-7 only
+  // (filt_axis).  A tight bound matters for rays that graze their own plane -- every light-sampled ray that leaves the
+  // ceiling one unit above the light quad --: with the general bound the own plane passes the distance threshold.
+  float eaCoef[3];
+  float padf;
 };
 #define B2PT_MAX_FRAMES 4
 #define B2PT_MAX_PAIRS 16

@@ -5,7 +5,7 @@ import ctypes as C, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import raytracingtherestofyourlife_b200 as B
 L = B.lib()
-buf = (C.c_ulonglong * 64)()
+buf = (C.c_ulonglong * 256)()
 for name, flags in (("8-wide tree", B.FLAG_WIDE_BVH), ("binary tree", 0)):
     ctx = B.Context(0)
     ctx.set_scene(B.Scene.spheres(1000000)); ctx.build_bvh(flags); ctx.set_camera(B.Camera(1920, 1080))
