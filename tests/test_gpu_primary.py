@@ -76,3 +76,30 @@ def test_masked_primary_rays_on_a_small_sphere_scene(b2pt):
             assert sa.tracePath == 0
             assert sa.segments == sb.segments
             assert np.array_equal(bits(a), bits(b))
+
+
+@pytest.mark.parametrize("noise", [0.0, 6e-8, 2.5e-7, 2e-6])
+def test_candidate_filter_on_perturbed_scenes_equals_no_filter(b2pt, noise):
+    """The candidate filter against no filter at all (B2PT_FLAG_NO_AA: every quad behind its leaf box + the exact test) on
+    the Cornell box with every vertex coordinate jittered: 0 keeps the world-frame axis groups exactly planar (tight
+    distance bound, B2Frame::eaCoef = 4e-7), 6e-8 .. 2.5e-7 leaves the quads planar to the filter's tolerance but not
+    exactly (general bound 4e-6), 2e-6 pushes most of them out of the filter behind their leaf boxes.  Primary hits,
+    segments and the image must agree bit for bit in every case -- the light-sampled rays that leave the ceiling graze
+    their own plane and are the ones the distance threshold must get right."""
+    s = b2pt.Scene.cornell()
+    if noise:
+        rng = np.random.default_rng(7)
+        s.pts = (s.pts.astype(np.float64) + rng.uniform(-noise, noise, s.pts.shape)).astype(np.float32)
+    res = []
+    for flags in (0, b2pt.FLAG_NO_AA):
+        with b2pt.Context(0) as ctx:
+            ctx.set_scene(s)
+            ctx.build_bvh(flags)
+            ctx.set_camera(b2pt.Camera(160, 128))
+            prim, t = ctx.primary_hits()
+            ctx.render(32, 50, flags)
+            res.append((prim, t.view(np.uint32).copy(), ctx.read_color().view(np.uint32).copy(), ctx.stats().segments))
+    a, b = res
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert a[3] == b[3]
+    assert np.array_equal(a[2], b[2])
