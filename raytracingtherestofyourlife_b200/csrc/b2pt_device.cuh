@@ -471,7 +471,10 @@ __device__ __forceinline__ void filt_axis(const B2SmallScene& S, int pBegin, int
   const float bt = tmin - ea;
   // (bt > 0: t' > bt/(1+er), bounded below by bt*(1-2er); bt <= 0: t' > bt/(1-er), bounded below by bt*(1+2er) while
   // er < 0.5 -- one branch-free form, bt - 2er*|bt|, covers both signs)
-  const float tlo = !axisOk ? inf : (er < 0.5f ? __fmaf_rn(-2.0f * er, fabsf(bt), bt) : -inf);
+  // (two selects written as PTX: left to itself the compiler wraps the threshold arithmetic in a branch)
+  float tlo = __fmaf_rn(-2.0f * er, fabsf(bt), bt);
+  asm("{ .reg .pred p; setp.ne.s32 p, %2, 0; selp.f32 %0, %0, %1, p; }" : "+f"(tlo) : "f"(-inf), "r"((int)(er < 0.5f)));
+  asm("{ .reg .pred p; setp.ne.s32 p, %2, 0; selp.f32 %0, %0, %1, p; }" : "+f"(tlo) : "f"(inf), "r"((int)axisOk));
   // lower bound of the true distance used for ordering / pruning:  t'*(1-er) - 3*ea  (valid for either sign of t'
   // that passes the threshold); extreme grazing (er >= 0.5) gets -inf, i.e. is never pruned
   const float cLo = er < 0.5f ? 1.0f - er : 0.f;
