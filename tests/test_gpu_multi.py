@@ -29,11 +29,14 @@ def test_sharded_nccl_render_equals_single_gpu(b2pt, world):
                           os.path.join(ROOT, "scripts", "multi_rank_check.py")], capture_output=True, text=True, env=env,
                          timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
-    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    line = [l for l in lines if "segments_sharded" in l][-1]
     assert line["world"] == world
     assert line["segments_sharded"] == line["segments_single"]  # the same set of paths
     assert line["nan_masks_equal"]
     assert line["max_rel_diff"] <= 1e-5  # summation order only
+    vline = [l for l in lines if "view_stack_bit_identical" in l][-1]  # views dealt to the ranks: independent renders
+    assert vline["world"] == world and vline["view_stack_bit_identical"]
 
 
 def test_single_process_allreduce_over_peer_access(b2pt):
