@@ -505,7 +505,12 @@ __device__ __forceinline__ void filt_axis(const B2SmallScene& S, int pBegin, int
     if (l1 < F.tbl)
       F.vb = 2 * p + 1;
     F.tbl = fminf(F.tbl, l1);
-    F.mask = (F.mask << 2) | (pass0 ? 2u : 0u) | (pass1 ? 1u : 0u);
+    // (mask = mask*4 + 2*pass0 + pass1 as one shift and two predicated ORs; the compiler's own form is two selects,
+    // a multiply-add and an add)
+    asm("{ .reg .pred p0, p1; setp.ne.s32 p0, %1, 0; setp.ne.s32 p1, %2, 0; shl.b32 %0, %0, 2; @p0 or.b32 %0, %0, 2; "
+        "@p1 or.b32 %0, %0, 1; }"
+        : "+r"(F.mask)
+        : "r"((int)pass0), "r"((int)pass1));
   }
 }
 __device__ __forceinline__ void filt_frame(const B2SmallScene& S, int f, int& pBegin, f3 o, f3 d, float Sr, float tmin,
