@@ -858,6 +858,7 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
           const bool real = i + h < e;
           const FiltRec r = real ? filt[i + h].fq : FiltRec{ std::nanf(""), 0.f, -1.f, 0.f, -1.f };
           P.c[h] = r.c, P.uc[h] = r.uc, P.hu[h] = r.hu, P.vc[h] = r.vc, P.hv[h] = r.hv;
+          P.vis[h] = (uint32_t)(2 * nPairs + h);
           S.visitSlot[2 * nPairs + h] = real ? (int32_t)(i + h) : -1;
         }
         ++nPairs;

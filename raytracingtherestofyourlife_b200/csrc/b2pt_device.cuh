@@ -396,8 +396,9 @@ __device__ __forceinline__ void aa_permute(int c, f3 a, float& u, float& v, floa
 
 // ---- phase 1 of the small-scene trace: candidate filter (B2FiltPair).  All 32 lanes run the same
 // straight-line code per pair of quads (no divergence), on packed FP32 pairs (FFMA2 / FADD2: two quads per
-// instruction); the output per lane is the candidate bit mask (bit nVisit-1-v for visit index v), the candidate
-// with the smallest LOWER BOUND of its hit distance and the second-smallest lower bound.
+// instruction); the output per lane is the candidate bit mask (bit nVisit-1-v for visit index v), the smallest
+// LOWER BOUND of a candidate's hit distance -- with that candidate's visit index in its low mantissa bits (FiltState) --
+// and the second-smallest lower bound.
 #ifndef B2PT_FILT_UNROLL
 #define B2PT_FILT_UNROLL 1
 #endif
@@ -405,10 +406,22 @@ constexpr int kFiltUnroll = B2PT_FILT_UNROLL;
 struct FiltState
 {
   uint32_t mask; // candidates in visit order, shifted in from the right
-  float tbl;     // smallest lower bound of t over the candidates
-  float t2;      // second smallest
-  int vb;        // visit index of the candidate holding tbl
+  // Smallest and second smallest KEY over the candidates.  A key is a lower bound of the candidate's hit distance with
+  // the candidate's visit index in its five lowest mantissa bits (kFiltKeyBits): the running minimum then carries the
+  // index of the nearest candidate along, and the loop needs no compare-and-select for it.  Replacing the low bits
+  // moves the value by less than 32 ulp (3.7e-6 relative); the bound is lowered by 8e-6 relative beforehand (cLo in
+  // filt_axis), so a key is still a lower bound.  Non-candidates get kFiltNoKey, a finite value above every distance.
+  float tbl;
+  float t2;
 };
+constexpr uint32_t kFiltKeyBits = 31u;          // B2PT_MAX_FILT = 32 visit indices
+constexpr uint32_t kFiltNoKey = 0x7f7fffe0u;    // 3.4028e38, low bits free for the index
+__device__ __forceinline__ float filt_key(float lowerBound, int visit)
+{
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xea;" : "=r"(r) : "r"(__float_as_uint(lowerBound)), "r"(~kFiltKeyBits), "r"((uint32_t)visit));
+  return __uint_as_float(r); // (a & b) | c
+}
 __device__ __forceinline__ float rcp_fast(float x)
 {
   float r;
@@ -477,8 +490,9 @@ __device__ __forceinline__ void filt_axis(const B2SmallScene& S, int pBegin, int
   asm("{ .reg .pred p; setp.ne.s32 p, %2, 0; selp.f32 %0, %0, %1, p; }" : "+f"(tlo) : "f"(inf), "r"((int)axisOk));
   // lower bound of the true distance used for ordering / pruning:  t'*(1-er) - 3*ea  (valid for either sign of t'
   // that passes the threshold); extreme grazing (er >= 0.5) gets -inf, i.e. is never pruned
-  const float cLo = er < 0.5f ? 1.0f - er : 0.f;
-  const float off = er < 0.5f ? 3.0f * ea : inf;
+  // (8e-6: room for the visit index in the low bits of the bound, FiltState; 3e38 instead of infinity keeps the key finite)
+  const float cLo = er < 0.5f ? (1.0f - er) - 8e-6f : 0.f;
+  const float off = er < 0.5f ? 3.0f * ea : 3e38f;
   const f2x rdn2 = pk2(rdn, rdn), modn2 = pk2(-odn, -odn), du2 = pk2(du, du), ou2 = pk2(ou, ou), dv2 = pk2(dv, dv),
             ov2 = pk2(ov, ov), marg2 = pk2(marg, marg), cLo2 = pk2(cLo, cLo), moff2 = pk2(-off, -off);
 #pragma unroll kFiltUnroll
@@ -486,7 +500,8 @@ __device__ __forceinline__ void filt_axis(const B2SmallScene& S, int pBegin, int
   {
     const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&S.pairs[p]);       // (c0,c1) (uc0,uc1)
     const ulonglong2 b = *(reinterpret_cast<const ulonglong2*>(&S.pairs[p]) + 1); // (hu0,hu1) (vc0,vc1)
-    const f2x hv2 = *(reinterpret_cast<const f2x*>(&S.pairs[p]) + 4);             // (hv0,hv1)
+    const ulonglong2 cc = *(reinterpret_cast<const ulonglong2*>(&S.pairs[p]) + 2); // (hv0,hv1) (vis0,vis1)
+    const f2x hv2 = cc.x;
     const f2x tp2 = fma2(a.x, rdn2, modn2);
     const f2x eu2 = sub2(fma2(tp2, du2, ou2), a.y), ev2 = sub2(fma2(tp2, dv2, ov2), b.y);
     const f2x hu2 = add2(b.x, marg2), hw2 = add2(hv2, marg2);
@@ -496,14 +511,11 @@ __device__ __forceinline__ void filt_axis(const B2SmallScene& S, int pBegin, int
     upk2(tl2, tl0, tl1);
     const bool pass0 = (tp0 > tlo) & (fabsf(eu0) <= hu0) & (fabsf(ev0) <= hw0); // no short circuit
     const bool pass1 = (tp1 > tlo) & (fabsf(eu1) <= hu1) & (fabsf(ev1) <= hw1);
-    const float l0 = pass0 ? tl0 : inf, l1 = pass1 ? tl1 : inf;
+    const float noKey = __uint_as_float(kFiltNoKey);
+    const float l0 = filt_key(pass0 ? tl0 : noKey, (int)(uint32_t)cc.y), l1 = filt_key(pass1 ? tl1 : noKey, (int)(uint32_t)(cc.y >> 32));
     F.t2 = fminf(F.t2, fmaxf(F.tbl, l0));
-    if (l0 < F.tbl)
-      F.vb = 2 * p;
     F.tbl = fminf(F.tbl, l0);
     F.t2 = fminf(F.t2, fmaxf(F.tbl, l1));
-    if (l1 < F.tbl)
-      F.vb = 2 * p + 1;
     F.tbl = fminf(F.tbl, l1);
     // (mask = mask*4 + 2*pass0 + pass1 as one shift and two predicated ORs; the compiler's own form is two selects,
     // a multiply-add and an add)
@@ -569,7 +581,6 @@ __device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, 
     FiltState F;
     F.mask = 0u;
     F.tbl = F.t2 = __int_as_float(0x7f800000);
-    F.vb = 0;
     const float Sr = fmaxf(S.sceneAbs, fmaxf(fabsf(o.x), fmaxf(fabsf(o.y), fabsf(o.z))));
     int pBegin = 0;
     for (int f = 0; f < S.nFrames; ++f)
@@ -579,7 +590,7 @@ __device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, 
     // none of them can win or tie.  Visit index v sits at mask bit nVisit-1-v.
     uint32_t rest = F.mask;
     const int top = S.nVisit - 1;
-    int v = F.vb;
+    int v = (int)(__float_as_uint(F.tbl) & kFiltKeyBits); // nearest candidate (meaningful when rest != 0)
 #ifdef B2PT_DEBUG_HIST
     int iters = 0;
     atomicAdd(&g_debugHist[__popc(rest) < 15 ? __popc(rest) : 15], 1ull); // [0..15]: candidates per ray
@@ -603,7 +614,7 @@ __device__ __forceinline__ int closest_small(const B2SmallScene& S, f3 o, f3 d, 
         atomicAdd(&g_debugHist[192 + v], 1ull);
       ++iters;
 #endif
-      if (slot >= 0 && F.t2 > closest) // valid from the first iteration on: F.vb is tested first
+      if (slot >= 0 && F.t2 > closest) // valid from the first iteration on: the nearest candidate is tested first
         break;
       v = top - (__ffs((int)rest) - 1);
     }

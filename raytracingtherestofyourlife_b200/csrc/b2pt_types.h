@@ -134,14 +134,14 @@ struct alignas(16) B2Lights
 // Filter records are stored two quads at a time so that phase 1 runs on packed FP32 pairs (FFMA2 / FADD2 on
 // sm_100): a pair holds two quads of the same frame axis; an odd group is padded with a dummy half (c = NaN, never
 // a candidate).  The visit index of a half is 2*pair + half; visitSlot[] maps it to the quad's slot.
-struct alignas(16) B2FiltPair // 48 B: two 16-byte chunks + one 8-byte chunk
+struct alignas(16) B2FiltPair // 48 B: three 16-byte chunks
 {
   float c[2];  // plane coordinate on the frame axis n
   float uc[2]; // rectangle centre on axis u
   float hu[2]; // half width (static margin included) on axis u
   float vc[2];
   float hv[2];
-  float pad[2];
+  uint32_t vis[2]; // visit indices of the two halves (2*pair, 2*pair + 1): the low bits of the filter's keys (FiltState)
 };
 struct alignas(16) B2Frame // 80 B
 {
