@@ -495,12 +495,14 @@ __device__ __forceinline__ void filt_axis(const B2SmallScene& S, int pBegin, int
   const float off = er < 0.5f ? 3.0f * ea : 3e38f;
   const f2x rdn2 = pk2(rdn, rdn), modn2 = pk2(-odn, -odn), du2 = pk2(du, du), ou2 = pk2(ou, ou), dv2 = pk2(dv, dv),
             ov2 = pk2(ov, ov), marg2 = pk2(marg, marg), cLo2 = pk2(cLo, cLo), moff2 = pk2(-off, -off);
+  const ulonglong2* P = reinterpret_cast<const ulonglong2*>(&S.pairs[pBegin]);
+  const ulonglong2* const Pend = reinterpret_cast<const ulonglong2*>(&S.pairs[pEnd]);
 #pragma unroll kFiltUnroll
-  for (int p = pBegin; p < pEnd; ++p)
+  for (; P != Pend; P += 3)
   {
-    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&S.pairs[p]);       // (c0,c1) (uc0,uc1)
-    const ulonglong2 b = *(reinterpret_cast<const ulonglong2*>(&S.pairs[p]) + 1); // (hu0,hu1) (vc0,vc1)
-    const ulonglong2 cc = *(reinterpret_cast<const ulonglong2*>(&S.pairs[p]) + 2); // (hv0,hv1) (vis0,vis1)
+    const ulonglong2 a = P[0];  // (c0,c1) (uc0,uc1)
+    const ulonglong2 b = P[1];  // (hu0,hu1) (vc0,vc1)
+    const ulonglong2 cc = P[2]; // (hv0,hv1) (vis0,vis1)
     const f2x hv2 = cc.x;
     const f2x tp2 = fma2(a.x, rdn2, modn2);
     const f2x eu2 = sub2(fma2(tp2, du2, ou2), a.y), ev2 = sub2(fma2(tp2, dv2, ov2), b.y);
@@ -519,10 +521,12 @@ __device__ __forceinline__ void filt_axis(const B2SmallScene& S, int pBegin, int
     F.tbl = fminf(F.tbl, l1);
     // (mask = mask*4 + 2*pass0 + pass1 as one shift and two predicated ORs; the compiler's own form is two selects,
     // a multiply-add and an add)
-    asm("{ .reg .pred p0, p1; setp.ne.s32 p0, %1, 0; setp.ne.s32 p1, %2, 0; shl.b32 %0, %0, 2; @p0 or.b32 %0, %0, 2; "
+    uint32_t m;
+    asm("{ .reg .pred p0, p1; setp.ne.s32 p0, %2, 0; setp.ne.s32 p1, %3, 0; shl.b32 %0, %1, 2; @p0 or.b32 %0, %0, 2; "
         "@p1 or.b32 %0, %0, 1; }"
-        : "+r"(F.mask)
-        : "r"((int)pass0), "r"((int)pass1));
+        : "=&r"(m)
+        : "r"(F.mask), "r"((int)pass0), "r"((int)pass1));
+    F.mask = m;
   }
 }
 __device__ __forceinline__ void filt_frame(const B2SmallScene& S, int f, int& pBegin, f3 o, f3 d, float Sr, float tmin,
