@@ -491,7 +491,7 @@ __device__ __forceinline__ void filt_axis(const B2SmallScene& S, int pBegin, int
   // lower bound of the true distance used for ordering / pruning:  t'*(1-er) - 3*ea  (valid for either sign of t'
   // that passes the threshold); extreme grazing (er >= 0.5) gets -inf, i.e. is never pruned
   // (8e-6: room for the visit index in the low bits of the bound, FiltState; 3e38 instead of infinity keeps the key finite)
-  const float cLo = er < 0.5f ? (1.0f - er) - 8e-6f : 0.f;
+  const float cLo = er < 0.5f ? 0.999992f - er : 0.f;
   const float off = er < 0.5f ? 3.0f * ea : 3e38f;
   const f2x rdn2 = pk2(rdn, rdn), modn2 = pk2(-odn, -odn), du2 = pk2(du, du), ou2 = pk2(ou, ou), dv2 = pk2(dv, dv),
             ov2 = pk2(ov, ov), marg2 = pk2(marg, marg), cLo2 = pk2(cLo, cLo), moff2 = pk2(-off, -off);
