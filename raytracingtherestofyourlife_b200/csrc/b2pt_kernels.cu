@@ -53,6 +53,10 @@ struct PeerPtrs
 
 // L2 prefetch of the 16-byte element a lane will load in its NEXT iteration (hides part of the HBM latency at the
 // head of every tile; the kernels keep only 8 warps per scheduler)
+#ifndef B2PT_PREFETCH_AHEAD
+#define B2PT_PREFETCH_AHEAD 32
+#endif
+constexpr int kPrefetchAhead = B2PT_PREFETCH_AHEAD; // records ahead of the one being processed (a warp's next tile = 32)
 __device__ __forceinline__ void prefetch_l2(const void* p)
 {
 #ifndef B2PT_NO_PREFETCH
@@ -1014,11 +1018,11 @@ __device__ __forceinline__ void trace_body(const B2Camera& cam, const SceneT& S,
     const int64_t idx = PRIMARY ? (((i0 >> 5) * A.numWarps + slot) << 5) + lane : base + i;
     if (PRIMARY)
       slot = slot + 1 == A.numWarps ? 0 : slot + 1;
-    if (!PRIMARY && !TAIL && i + 32 < nIn)
+    if (!PRIMARY && !TAIL && i + kPrefetchAhead < nIn)
     {
-      prefetch_l2(A.q.p0 + idx + 32);
-      prefetch_l2(A.q.p1 + idx + 32);
-      prefetch_l2(A.q.p2 + idx + 32);
+      prefetch_l2(A.q.p0 + idx + kPrefetchAhead);
+      prefetch_l2(A.q.p1 + idx + kPrefetchAhead);
+      prefetch_l2(A.q.p2 + idx + kPrefetchAhead);
     }
     if (PRIMARY ? idx < A.nPaths : i < nIn)
     {
@@ -1185,12 +1189,12 @@ __device__ __forceinline__ void shade_body(const SceneT& S, const B2Lights& LT, 
       bool survive = false;
       f3 o, d, T;
       uint32_t pid = 0, rng = 0;
-      if (!TAIL_IN && i + 32 < nk)
+      if (!TAIL_IN && i + kPrefetchAhead < nk)
       {
-        prefetch_l2(A.bins[0].p0 + binBase + i + 32);
-        prefetch_l2(A.bins[0].p1 + binBase + i + 32);
-        prefetch_l2(A.bins[0].p2 + binBase + i + 32);
-        prefetch_l2(A.bins[0].code + binBase + i + 32);
+        prefetch_l2(A.bins[0].p0 + binBase + i + kPrefetchAhead);
+        prefetch_l2(A.bins[0].p1 + binBase + i + kPrefetchAhead);
+        prefetch_l2(A.bins[0].p2 + binBase + i + kPrefetchAhead);
+        prefetch_l2(A.bins[0].code + binBase + i + kPrefetchAhead);
       }
       if (i < nk)
       {
