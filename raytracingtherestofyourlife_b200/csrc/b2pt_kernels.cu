@@ -113,6 +113,18 @@ __device__ __forceinline__ const B2Lights& stage_lights(const B2Lights& lights, 
   return a.lights;
 }
 
+// x[k] for k in 0..3 without a branch tree (the compiler turns the ternary chain over two quadruples into divergent
+// branches; three selects per quadruple keep the warp together)
+__device__ __forceinline__ uint32_t pick4(int k, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3)
+{
+  uint32_t r;
+  asm("{ .reg .pred p0, p1, p2; setp.eq.s32 p0, %1, 0; setp.eq.s32 p1, %1, 1; setp.eq.s32 p2, %1, 2;\n\t"
+      "selp.b32 %0, %4, %5, p2; selp.b32 %0, %3, %0, p1; selp.b32 %0, %2, %0, p0; }"
+      : "=&r"(r)
+      : "r"(k), "r"(x0), "r"(x1), "r"(x2), "r"(x3));
+  return r;
+}
+
 // Global tile (32 consecutive path ids) that warp w generates in round j of a PRIMARY launch: slot (w + j) mod numWarps
 // of round j.  For a fixed round the slots of the warps are a permutation, so every tile is generated exactly once.
 __device__ __forceinline__ int64_t primary_tile(int64_t j, int w, int numWarps)
@@ -504,8 +516,8 @@ __device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhS
     }
     if (bin >= 0)
     {
-      const unsigned mine = bin == 0 ? b0 : (bin == 1 ? b1 : (bin == 2 ? b2 : b3));
-      const uint32_t cnt = bin == 0 ? cnt0 : (bin == 1 ? cnt1 : (bin == 2 ? cnt2 : cnt3));
+      const unsigned mine = pick4(bin, b0, b1, b2, b3);
+      const uint32_t cnt = pick4(bin, cnt0, cnt1, cnt2, cnt3);
       const int64_t j = (int64_t)bin * A.binStride + base + cnt + __popc(mine & lt);
       A.bins[0].p0[j] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
       A.bins[0].p1[j] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
@@ -770,8 +782,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM)
     const unsigned b2 = __ballot_sync(0xffffffffu, bin == 2), b3 = __ballot_sync(0xffffffffu, bin == 3);
     if (bin >= 0)
     {
-      const unsigned mine = bin == 0 ? b0 : (bin == 1 ? b1 : (bin == 2 ? b2 : b3));
-      const uint32_t cnt = bin == 0 ? cnt0 : (bin == 1 ? cnt1 : (bin == 2 ? cnt2 : cnt3));
+      const unsigned mine = pick4(bin, b0, b1, b2, b3);
+      const uint32_t cnt = pick4(bin, cnt0, cnt1, cnt2, cnt3);
       const int64_t j = (int64_t)bin * A.binStride + base + cnt + __popc(mine & lt);
       A.bins[0].p0[j] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
       A.bins[0].p1[j] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
@@ -968,8 +980,8 @@ __device__ __forceinline__ void trace_body_wide(const B2Camera& cam, const B2Bvh
     }
     if (bin >= 0)
     {
-      const unsigned mine = bin == 0 ? b0 : (bin == 1 ? b1 : (bin == 2 ? b2 : b3));
-      const uint32_t cnt = bin == 0 ? cnt0 : (bin == 1 ? cnt1 : (bin == 2 ? cnt2 : cnt3));
+      const unsigned mine = pick4(bin, b0, b1, b2, b3);
+      const uint32_t cnt = pick4(bin, cnt0, cnt1, cnt2, cnt3);
       const int64_t j = (int64_t)bin * A.binStride + base + cnt + __popc(mine & lt);
       A.bins[0].p0[j] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
       A.bins[0].p1[j] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
@@ -1091,8 +1103,8 @@ __device__ __forceinline__ void trace_body(const B2Camera& cam, const SceneT& S,
     }
     if (bin >= 0)
     {
-      const unsigned mine = bin == 0 ? b0 : (bin == 1 ? b1 : (bin == 2 ? b2 : b3));
-      const uint32_t cnt = bin == 0 ? cnt0 : (bin == 1 ? cnt1 : (bin == 2 ? cnt2 : cnt3));
+      const unsigned mine = pick4(bin, b0, b1, b2, b3);
+      const uint32_t cnt = pick4(bin, cnt0, cnt1, cnt2, cnt3);
       const int64_t j = (int64_t)bin * A.binStride + base + cnt + __popc(mine & lt);
       A.bins[0].p0[j] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(d.x));
       A.bins[0].p1[j] = make_uint4(__float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(T.x), __float_as_uint(T.y));
