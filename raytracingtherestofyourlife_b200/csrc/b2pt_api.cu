@@ -1668,6 +1668,8 @@ static int render_impl(b2pt_ctx* ctx, int sampleBegin, int sampleCount, int maxD
     A.primQuads = primMasks ? ctx->primQuads.p + (viewMode ? v0 * B2PT_SMALL_MAX_QUADS : 0) : nullptr;
     A.tilesPerView = tilesPerView;
     A.maxDepth = maxDepth;
+    b2pt::make_fastdiv((uint32_t)N, A.divPixelsMagic, A.divPixelsShift);
+    b2pt::make_fastdiv((uint32_t)std::max(viewMode ? sampleCount : 1, 1), A.divSppMagic, A.divSppShift);
     A.nLightQuads = ctx->lights.nLightQuads;
     A.nLightSph = ctx->lights.nLightSph;
     A.seedOffset = ctx->seedOffset;

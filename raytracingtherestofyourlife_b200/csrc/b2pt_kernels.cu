@@ -132,20 +132,33 @@ __device__ __forceinline__ int64_t primary_tile(int64_t j, int w, int numWarps)
   return j * numWarps + (int64_t)(((int64_t)w + j) % numWarps);
 }
 
+// n / d for the divisors the host prepared (B2RenderArgs::div*): Granlund-Montgomery round-up with the 33rd bit of the
+// multiplier folded into an add and a shift; exact for every 32-bit n (tests/test_host_logic.py checks the recipe)
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, uint32_t magic, uint32_t shift)
+{
+  if (shift == 0xffffffffu)
+    return n; // divisor 1
+  const uint32_t t = __umulhi(n, magic);
+  return (t + ((n - t) >> 1)) >> shift;
+}
+
 // Ray `idx` of the warp's region.  PRIMARY: generated from (pixel, sample) -- idx is the path id.
 template <bool PRIMARY>
 __device__ __forceinline__ void load_ray(const B2Camera& cam, const B2RenderArgs& A, int64_t idx, f3& o, f3& d, f3& T,
-                                         uint32_t& pid, uint32_t& rng)
+                                         uint32_t& pid, uint32_t& rng, uint32_t* slotOut = nullptr)
 {
   if (PRIMARY)
   {
     pid = (uint32_t)idx; // path id chosen by the caller (tile-interleaved over the warps' regions)
-    const uint32_t pixel = pid % (uint32_t)A.nPixels;
-    uint32_t b = pid / (uint32_t)A.nPixels;
+    uint32_t b = fastdiv(pid, A.divPixelsMagic, A.divPixelsShift); // sample slot of the batch
+    const uint32_t pixel = pid - b * (uint32_t)A.nPixels;
+    if (slotOut)
+      *slotOut = b;
     if (A.views)
     { // view-batched render: every view is an independent render with the same per-(pixel, sample) streams
-      const B2Camera vc = A.views[b / (uint32_t)A.sppPerView];
-      b = b % (uint32_t)A.sppPerView;
+      const uint32_t view = fastdiv(b, A.divSppMagic, A.divSppShift);
+      const B2Camera vc = A.views[view];
+      b = b - view * (uint32_t)A.sppPerView;
       rng = pixel + A.seedOffset + (uint32_t)(A.sampleBase + (int)b) * B2PT_GOLDEN;
       d = raygen(vc, (int)pixel, rng);
       o = ld3(vc.pos);
@@ -1038,17 +1051,17 @@ __device__ __forceinline__ void trace_body(const B2Camera& cam, const SceneT& S,
     }
     if (PRIMARY ? idx < A.nPaths : i < nIn)
     {
-      load_ray<PRIMARY>(cam, A, idx, o, d, T, pid, rng);
+      uint32_t slotB = 0; // PRIMARY: sample slot of the path; the same for the 32 paths of a tile (nPixels % 32 == 0)
+      load_ray<PRIMARY>(cam, A, idx, o, d, T, pid, rng, &slotB);
       bool masked = false;
       if constexpr (PRIMARY && std::is_same<SceneT, B2SmallScene>::value)
         masked = A.primMask != nullptr;
       if constexpr (PRIMARY && std::is_same<SceneT, B2SmallScene>::value)
         if (masked)
       { // the tile's candidate mask and the view's per-quad constants (warp-uniform; nPixels % 32 == 0)
-        const int64_t tileBase = idx - lane;
-        const uint32_t slotB = (uint32_t)(tileBase / A.nPixels);
-        const uint32_t view = A.views ? slotB / (uint32_t)A.sppPerView : 0u;
-        const uint32_t tileInView = (uint32_t)((tileBase - (int64_t)slotB * A.nPixels) >> 5);
+        const uint32_t tileBase = (uint32_t)idx - (uint32_t)lane;
+        const uint32_t view = A.views ? fastdiv(slotB, A.divSppMagic, A.divSppShift) : 0u;
+        const uint32_t tileInView = (tileBase - slotB * (uint32_t)A.nPixels) >> 5;
         const uint2 mask = __ldg(A.primMask + (size_t)view * A.tilesPerView + tileInView);
 #ifdef B2PT_DEBUG_HIST
         if (lane == 0)

@@ -61,6 +61,24 @@ cudaError_t launch_primary_prep(const B2SmallScene& S, const B2Camera& cam, cons
                                 int tilesPerView, uint2* masks, B2PrimQuad* pq, cudaStream_t stream);
 // K4: color[p] += sum_b rad[b*N + p] in sample order; counts NaN samples into *nanCounter.
 int warps_per_block();
+
+// Multiplier and shift of the device's fastdiv (b2pt_kernels.cu) for a divisor d >= 1: with l = ceil(log2 d) and
+// m = floor(2^32 (2^l - d) / d) + 1,  n / d = (t + ((n - t) >> 1)) >> (l - 1),  t = umulhi(n, m), for every 32-bit n
+// (Granlund & Montgomery 1994, fig. 4.1 as used by libdivide's branch-free u32 divider).  d = 1: shift = 0xffffffff.
+inline void make_fastdiv(uint32_t d, uint32_t& magic, uint32_t& shift)
+{
+  if (d <= 1)
+  {
+    magic = 0;
+    shift = 0xffffffffu;
+    return;
+  }
+  uint32_t l = 0;
+  while (((uint64_t)1 << l) < d)
+    ++l;
+  magic = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << l) - d)) / d + 1);
+  shift = l - 1;
+}
 cudaError_t launch_accumulate(float4* color, const float4* rad, int nPixels, int samplesPerView, int nViews,
                               unsigned long long* nanCounter, cudaStream_t stream);
 cudaError_t launch_primary_hits(const B2Camera& cam, const B2SmallScene* small, const B2BvhScene* bvh,

@@ -308,6 +308,9 @@ struct B2RenderArgs
   int32_t maxDepth;
   int32_t sppPerView;
   int32_t tilesPerView; // nPixels / 32
+  // n / nPixels and n / sppPerView for 32-bit n without the division sequence (host: make_fastdiv; device: fastdiv):
+  // q = (t + ((n - t) >> 1)) >> shift with t = umulhi(n, magic); a divisor of 1 has magic = 0, shift = 0xffffffff
+  uint32_t divPixelsMagic, divPixelsShift, divSppMagic, divSppShift;
   int32_t nLightQuads, nLightSph; // light counts (reference-stream mode: draws a dead pixel still burns per depth)
   uint32_t seedOffset;
   uint32_t flags;

@@ -49,3 +49,35 @@ def test_bvh_builders_selfcheck(b2pt, n):
     # 8-wide: about n / 6 leaf-level nodes
     if n >= 300:
         assert wide_nodes < 0.45 * n
+
+
+def test_fastdiv_recipe_is_exact():
+    import numpy as np
+    """csrc/b2pt_kernels.h make_fastdiv / b2pt_kernels.cu fastdiv (n / nPixels, n / sppPerView in the primary-ray index
+    math): the Granlund-Montgomery round-up recipe, restated here, is exact for 32-bit n and every divisor in use."""
+    def make(d):
+        if d <= 1:
+            return 0, None
+        l = 0
+        while (1 << l) < d:
+            l += 1
+        return ((1 << 32) * ((1 << l) - d)) // d + 1, l - 1
+
+    def div(n, magic, shift):
+        if shift is None:
+            return n
+        t = (n * magic) >> 32
+        return ((t + ((n - t) >> 1)) & 0xffffffff) >> shift
+
+    rng = np.random.default_rng(5)
+    ds = [1, 2, 3, 5, 7, 10, 33 * 7, 128 * 128, 1024 * 1024, 1920 * 1080, 4096 * 4096, (1 << 26) - 1, 1 << 26, 1000, 1024,
+          4095, 4097] + [int(x) for x in rng.integers(1, 1 << 26, 200)]
+    for d in ds:
+        magic, shift = make(d)
+        assert magic < (1 << 32)
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, (1 << 32) - 1, (1 << 32) - d, (1 << 31), (1 << 31) - 1]
+        ns += [int(x) for x in rng.integers(0, 1 << 32, 300)]
+        ns += [k * d + r for k in (1, 7, ((1 << 32) - 1) // d) for r in (-1, 0, 1) if 0 <= k * d + r < (1 << 32)]
+        for n in ns:
+            if 0 <= n < (1 << 32):
+                assert div(n, magic, shift) == n // d, (n, d)
