@@ -1040,7 +1040,7 @@ __device__ __forceinline__ void trace_body(const B2Camera& cam, const SceneT& S,
     uint32_t pid = 0, rng = 0;
     float t = 0.f;
     int code = B2PT_MISS;
-    const int64_t idx = PRIMARY ? (((i0 >> 5) * A.numWarps + slot) << 5) + lane : base + i;
+    const int64_t idx = PRIMARY ? ((int64_t)((uint32_t)(i0 >> 5) * (uint32_t)A.numWarps + (uint32_t)slot) << 5) + lane : base + i;
     if (PRIMARY)
       slot = slot + 1 == A.numWarps ? 0 : slot + 1;
     if (!PRIMARY && !TAIL && i + kPrefetchAhead < nIn)
