@@ -57,7 +57,7 @@ def condense(dst_name, captures):
 
 
 condense("r02_cornell_ncu.csv", [
-    ("two-kernel pipeline (default), bounce 1 of a 32-sample batch at 1024^2: k_trace<queue> then k_shade (final build)", "prof_final"),
+    ("two-kernel pipeline (default), final build, 32-sample batch at 1024^2: k_trace<PRIMARY> + k_shade of bounce 0, then k_trace<queue> + k_shade of bounce 1", "prof_final2"),
     ("one-kernel pipeline (B2PT_FLAG_ONE_KERNEL_BOUNCE), the same bounce: k_bounce", "prof_fused"),
 ])
 condense("r02_bvh_ncu.csv", [
