@@ -389,6 +389,7 @@ __device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhS
         // (a branch-free form of this update -- selects, speculative read of the stack top, unconditional store above
         // it -- keeps the lanes converged but was measured 4.5 % SLOWER: every lane then touches the local-memory
         // stack every step; profiles/r02_bvh_experiments.md)
+#if defined(B2PT_STACK_T) || defined(B2PT_BRANCHY_STEP)
         if (hl && hr)
         {
           const bool rightCloser = tl > tr;
@@ -416,6 +417,21 @@ __device__ __forceinline__ void trace_body_bvh(const B2Camera& cam, const B2BvhS
           else
             cur = stack[--sp];
         }
+#else
+        // One pass for the four outcomes: the next node is a select, only the stack accesses sit under predicates (a
+        // lane that neither pushes nor pops does not touch local memory).  The four-way branch this replaces ran each
+        // outcome serially: 17 % of the kernel's instructions at 4-6 active lanes (profiles/r02_experiments.md).
+        const bool both = hl && hr, none = !(hl || hr);
+        const bool rightCloser = tl > tr;
+        const uint32_t nearChild = (hl && !(hr && rightCloser)) ? cl : crr;
+        if (both && sp < 64)
+          stack[sp++] = rightCloser ? cl : crr;
+        const bool pop = none && sp > 0;
+        const uint32_t top = pop ? stack[sp - 1] : 0u;
+        sp -= pop ? 1 : 0;
+        done = none && !pop;
+        cur = none ? top : nearChild;
+#endif
       }
       if (has && !done && (cur >> 24))
       { // leaf: primitives in ascending original index
