@@ -868,6 +868,17 @@ static int build_trace_structures(b2pt_ctx* ctx, uint32_t flags)
       k = e;
     }
     S.nVisit = 2 * nPairs;
+    { // byte ranges of the axis groups (B2Frame::grpBegin / grpEnd)
+      int begin = 0;
+      for (int f = 0; f < S.nFrames; ++f)
+        for (int a = 0; a < 3; ++a)
+        {
+          const int end = std::max(begin, S.frames[f].axisEnd[a]);
+          S.frames[f].grpBegin[a] = (uint32_t)(begin * (int)sizeof(B2FiltPair));
+          S.frames[f].grpEnd[a] = (uint32_t)(end * (int)sizeof(B2FiltPair));
+          begin = end;
+        }
+    }
     for (size_t i = 0; i < filt.size(); ++i)
       S.quads[i] = ctx->quads[(size_t)filt[i].quad]; // slot = position in the (frame, axis)-sorted list
     size_t slot = filt.size();

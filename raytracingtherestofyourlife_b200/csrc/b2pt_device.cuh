@@ -466,11 +466,11 @@ __device__ __forceinline__ f2x sub2(f2x a, f2x b)
 // E01_n = E03_n = 0 and v00_n = c the exact test's t = (T_n A)/(d_n A') carries only relative rounding (<= 10 u), and
 // t' = fma(c, r, -(on r)) with r = rcp.approx(dn) (1 ulp) differs from the true distance by at most 3 u |t| +
 // u |on| |r| <= 1.8e-7 |t| + 6e-8 S/|dn|.
-__device__ __forceinline__ void filt_axis(const B2SmallScene& S, int pBegin, int pEnd, float on, float dn, float ou,
-                                          float du, float ov, float dv, float dabs, float Sr, float eaCoef, float tmin,
-                                          FiltState& F)
+__device__ __forceinline__ void filt_axis(const B2SmallScene& S, uint32_t byteBegin, uint32_t byteEnd, float on, float dn,
+                                          float ou, float du, float ov, float dv, float dabs, float Sr, float eaCoef,
+                                          float tmin, FiltState& F)
 {
-  if (pEnd <= pBegin)
+  if (byteEnd == byteBegin)
     return;
   const float inf = __int_as_float(0x7f800000);
   const bool axisOk = fabsf(dn) > 1e-30f; // below that the exact test rejects on |det| < 1e-5
@@ -495,8 +495,9 @@ __device__ __forceinline__ void filt_axis(const B2SmallScene& S, int pBegin, int
   const float off = er < 0.5f ? 3.0f * ea : 3e38f;
   const f2x rdn2 = pk2(rdn, rdn), modn2 = pk2(-odn, -odn), du2 = pk2(du, du), ou2 = pk2(ou, ou), dv2 = pk2(dv, dv),
             ov2 = pk2(ov, ov), marg2 = pk2(marg, marg), cLo2 = pk2(cLo, cLo), moff2 = pk2(-off, -off);
-  const ulonglong2* P = reinterpret_cast<const ulonglong2*>(&S.pairs[pBegin]);
-  const ulonglong2* const Pend = reinterpret_cast<const ulonglong2*>(&S.pairs[pEnd]);
+  const char* const pairs0 = reinterpret_cast<const char*>(S.pairs);
+  const ulonglong2* P = reinterpret_cast<const ulonglong2*>(pairs0 + byteBegin);
+  const ulonglong2* const Pend = reinterpret_cast<const ulonglong2*>(pairs0 + byteEnd);
 #pragma unroll kFiltUnroll
   for (; P != Pend; P += 3)
   {
@@ -547,9 +548,9 @@ __device__ __forceinline__ void filt_frame(const B2SmallScene& S, int f, int& pB
     Sf = 4.0f * Sr; // frame coordinates are relative to org: |.| <= 2*sqrt(3)*Sr
   }
   const float dabs = fabsf(dl.x) + fabsf(dl.y) + fabsf(dl.z);
-  filt_axis(S, pBegin, Fr.axisEnd[0], ol.x, dl.x, ol.y, dl.y, ol.z, dl.z, dabs, Sf, Fr.eaCoef[0], tmin, F);
-  filt_axis(S, max(pBegin, Fr.axisEnd[0]), Fr.axisEnd[1], ol.y, dl.y, ol.z, dl.z, ol.x, dl.x, dabs, Sf, Fr.eaCoef[1], tmin, F);
-  filt_axis(S, max(pBegin, Fr.axisEnd[1]), Fr.axisEnd[2], ol.z, dl.z, ol.x, dl.x, ol.y, dl.y, dabs, Sf, Fr.eaCoef[2], tmin, F);
+  filt_axis(S, Fr.grpBegin[0], Fr.grpEnd[0], ol.x, dl.x, ol.y, dl.y, ol.z, dl.z, dabs, Sf, Fr.eaCoef[0], tmin, F);
+  filt_axis(S, Fr.grpBegin[1], Fr.grpEnd[1], ol.y, dl.y, ol.z, dl.z, ol.x, dl.x, dabs, Sf, Fr.eaCoef[1], tmin, F);
+  filt_axis(S, Fr.grpBegin[2], Fr.grpEnd[2], ol.z, dl.z, ol.x, dl.x, ol.y, dl.y, dabs, Sf, Fr.eaCoef[2], tmin, F);
   pBegin = max(pBegin, Fr.axisEnd[2]);
 }
 

@@ -143,7 +143,7 @@ struct alignas(16) B2FiltPair // 48 B: three 16-byte chunks
   float hv[2];
   uint32_t vis[2]; // visit indices of the two halves (2*pair, 2*pair + 1): the low bits of the filter's keys (FiltState)
 };
-struct alignas(16) B2Frame // 80 B
+struct alignas(16) B2Frame // 112 B
 {
   float R[9];         // rows = frame axes in world coordinates (world -> frame rotation)
   float org[3];       // frame origin (subtracted before the rotation)
@@ -157,6 +157,10 @@ struct alignas(16) B2Frame // 80 B
   // ceiling one unit above the light quad --: with the general bound the own plane passes the distance threshold.
   float eaCoef[3];
   float padf;
+  // byte offsets, from the scene's first pair, of the pairs of axis group 0,1,2: [begin, end) -- what filt_axis walks
+  // (axisEnd stays the index form k_primary_prep uses)
+  uint32_t grpBegin[3], padb;
+  uint32_t grpEnd[3], pade;
 };
 #define B2PT_MAX_FRAMES 4
 #define B2PT_MAX_PAIRS 16
